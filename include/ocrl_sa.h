@@ -1,0 +1,145 @@
+/*
+ * ocrl_sa.h -- C ABI of the B200-native slot-attention hot path (libocrl_sa.so).
+ *
+ * The reference (ugadiarov-la-phystech-edu/OCRL) has no native code; every entry point below
+ * replaces a stretch of eager PyTorch in the reference and is what a binding for this path
+ * would call.  Citations are relative to the reference tree.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch types.  All pointers are DEVICE pointers
+ *     owned by the caller (torch allocates inputs, outputs, saved state and workspaces); the
+ *     library never allocates or frees device memory and never synchronises the device.
+ *   - Work is enqueued on the cudaStream_t passed as `stream` (void* to keep this header
+ *     free of CUDA includes).
+ *   - Return value: 0 = ok, < 0 = OCRL_E_*; ocrl_last_error() gives a thread-local message.
+ *   - Tensors are dense, row-major, in the reference's layouts:
+ *       x/inputs [B,N,C_in] fp32, k/v [B,N,D] (fp32 or bf16, see kv_dtype),
+ *       slots [B,K,D] fp32, attn_vis [B,N,K] fp32.
+ *   - Built for sm_100a only; there is no CPU or other-architecture fallback.
+ */
+#ifndef OCRL_SA_H_
+#define OCRL_SA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OCRL_ABI_VERSION 1
+
+enum {
+  OCRL_OK = 0,
+  OCRL_E_SHAPE = -1,   /* unsupported or inconsistent dimensions */
+  OCRL_E_ALIGN = -2,   /* pointer not 16-byte aligned / null where required */
+  OCRL_E_ARCH = -3,    /* device is not sm_100 */
+  OCRL_E_LAUNCH = -4   /* CUDA launch / runtime error */
+};
+
+enum { OCRL_DT_F32 = 0, OCRL_DT_BF16 = 1 };
+/* math_mode: how the token contractions are evaluated */
+enum { OCRL_MATH_FP32 = 0 /* fp32 FFMA everywhere (parity mode) */,
+       OCRL_MATH_TENSOR = 1 /* bf16 operands on tensor cores, fp32 accumulate */ };
+
+/* Problem description, mirrors SlotAttention.__init__ (ocrs/common/slot_attn.py:10-45) and the
+ * Hydra keys ocr.slotattr.{num_iterations,num_slots,slot_size,mlp_hidden_size,num_slot_heads}
+ * (configs/ocr/slate.yaml:14-20). */
+typedef struct ocrl_sa_dims {
+  int32_t B;        /* images in the batch */
+  int32_t N;        /* tokens per image (H*W) */
+  int32_t C_in;     /* token feature width (ocr.cnn.hidden_size, 64) */
+  int32_t D;        /* slot_size */
+  int32_t H_mlp;    /* mlp_hidden_size */
+  int32_t K;        /* num_slots, 1..16 */
+  int32_t T;        /* num_iterations */
+  int32_t heads;    /* num_slot_heads; only 1 is supported (all shipped configs) */
+  float eps;        /* SlotAttention epsilon, 1e-8 (slot_attn.py:18,86) */
+  float ln_eps;     /* nn.LayerNorm eps, 1e-5 */
+  int32_t kv_dtype; /* OCRL_DT_* storage type of k and v */
+  int32_t math_mode;/* OCRL_MATH_* */
+} ocrl_sa_dims;
+
+/* Parameters of the iteration loop, fp32, in the reference's state_dict layout
+ * (slot_attention.{norm_slots,norm_mlp,project_q,gru,mlp}; slot_attn.py:31-45). */
+typedef struct ocrl_sa_weights {
+  const float* ln_slots_w; const float* ln_slots_b;   /* norm_slots   [D]       */
+  const float* ln_mlp_w;   const float* ln_mlp_b;     /* norm_mlp     [D]       */
+  const float* wq;                                    /* project_q.weight [D,D] */
+  const float* w_ih; const float* w_hh;               /* gru.weight_* [3D,D], rows [r;z;n] */
+  const float* b_ih; const float* b_hh;               /* gru.bias_*   [3D]      */
+  const float* w1; const float* b1;                   /* mlp.0 [H,D],[H]        */
+  const float* w2; const float* b2;                   /* mlp.2 [D,H],[D]        */
+} ocrl_sa_weights;
+
+/* Gradient accumulators with the same shapes (written, not accumulated into). */
+typedef struct ocrl_sa_weight_grads {
+  float* ln_slots_w; float* ln_slots_b;
+  float* ln_mlp_w;   float* ln_mlp_b;
+  float* wq;
+  float* w_ih; float* w_hh;
+  float* b_ih; float* b_hh;
+  float* w1; float* b1;
+  float* w2; float* b2;
+} ocrl_sa_weight_grads;
+
+/* Parameters of the per-token stage in front of the loop:
+ *   SlotAttentionEncoder.layer_norm + mlp (slot_attn.py:125-129,151) when mlp_w1 != NULL,
+ *   then SlotAttention.norm_inputs + project_k / project_v (slot_attn.py:30,36-37,54-61). */
+typedef struct ocrl_token_weights {
+  const float* enc_ln_w; const float* enc_ln_b;       /* layer_norm [C_in] (NULL: skip the MLP) */
+  const float* mlp_w1; const float* mlp_b1;           /* mlp.0 [C_in,C_in],[C_in] */
+  const float* mlp_w2; const float* mlp_b2;           /* mlp.2 [C_in,C_in],[C_in] */
+  const float* in_ln_w; const float* in_ln_b;         /* norm_inputs [C_in] */
+  const float* wk; const float* wv;                   /* project_{k,v}.weight [D,C_in] */
+} ocrl_token_weights;
+
+int ocrl_version(void);
+/* "sm_100a": the only architecture the library contains code for. */
+const char* ocrl_built_arch(void);
+const char* ocrl_last_error(void);
+
+/* Bytes the caller must provide: `fwd_ws`/`bwd_ws` scratch for the iteration kernels and
+ * `saved` for the per-iteration state kept for the backward (slots_in, updates, row sums). */
+int ocrl_sa_query_workspace(const ocrl_sa_dims* dims, size_t* fwd_ws, size_t* bwd_ws, size_t* saved);
+
+/* Token stage, forward.  Replaces slot_attn.py:151 (optional) and :54-61.
+ *   x        [B,N,C_in] fp32 tokens, or -- when pos_table != NULL -- the CNN feature map
+ *            [B,C_in,H*W] (NCHW) to which pos_table [C_in,H*W] is added while it is transposed
+ *            to token-major (ocrs/common/utils.py:28-33, slate_module.py:132-133).
+ *   y_out    [B,N,C_in] fp32 output of the token MLP (NULL if not needed / MLP skipped)
+ *   k_out,v_out [B,N,D] in dims->kv_dtype; k already scaled by D^-1/2 (slot_attn.py:61). */
+int ocrl_kv_proj_fwd(const ocrl_sa_dims* dims, const float* x, const float* pos_table,
+                     const ocrl_token_weights* w, float* y_out, void* k_out, void* v_out,
+                     void* stream);
+
+/* Token stage, backward of norm_inputs + project_k/v (autograd of slot_attn.py:54-61).
+ *   x [B,N,C_in] is the input of norm_inputs; dk,dv [B,N,D] fp32.
+ *   Writes dx [B,N,C_in], d in_ln_w/b [C_in], dwk, dwv [D,C_in].
+ *   ws: scratch of ocrl_kv_proj_bwd_workspace(dims) bytes. */
+size_t ocrl_kv_proj_bwd_workspace(const ocrl_sa_dims* dims);
+int ocrl_kv_proj_bwd(const ocrl_sa_dims* dims, const float* x, const ocrl_token_weights* w,
+                     const float* dk, const float* dv, float* dx, float* d_ln_w, float* d_ln_b,
+                     float* dwk, float* dwv, void* ws, void* stream);
+
+/* The fused T-iteration loop, forward.  Replaces slot_attn.py:64-102.
+ *   k,v [B,N,D]; slots0 [B,K,D]; slots_out [B,K,D]; attn_vis_out [B,N,K] or NULL;
+ *   saved: NULL (inference) or `saved` bytes from ocrl_sa_query_workspace;
+ *   workspace: `fwd_ws` bytes (may be NULL when fwd_ws == 0). */
+int ocrl_sa_iter_fwd(const ocrl_sa_dims* dims, const void* k, const void* v, const float* slots0,
+                     const ocrl_sa_weights* w, float* slots_out, float* attn_vis_out,
+                     void* saved, void* workspace, void* stream);
+
+/* The fused backward of the loop; attention logits are recomputed from k and the saved
+ * per-iteration slots rather than stored (autograd of slot_attn.py:64-102).
+ *   d_slots [B,K,D]; d_attn_vis [B,N,K] or NULL;
+ *   writes dk, dv [B,N,D] fp32, d_slots0 [B,K,D] and every member of dw. */
+int ocrl_sa_iter_bwd(const ocrl_sa_dims* dims, const void* k, const void* v, const void* saved,
+                     const ocrl_sa_weights* w, const float* d_slots, const float* d_attn_vis,
+                     float* dk, float* dv, float* d_slots0, const ocrl_sa_weight_grads* dw,
+                     void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCRL_SA_H_ */

@@ -1,0 +1,120 @@
+"""ctypes binding of libocrl_sa.so (include/ocrl_sa.h).  No torch types cross this boundary:
+only device pointers, sizes and the raw cudaStream_t.
+
+There is no CPU or library fallback: if the shared library is missing, ``lib()`` raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_size_t, c_void_p
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libocrl_sa.so")
+
+DT_F32, DT_BF16 = 0, 1
+MATH_FP32, MATH_TENSOR = 0, 1
+
+EXPORTS = [
+    "ocrl_version", "ocrl_built_arch", "ocrl_last_error", "ocrl_sa_query_workspace",
+    "ocrl_kv_proj_fwd", "ocrl_kv_proj_bwd_workspace", "ocrl_kv_proj_bwd",
+    "ocrl_sa_iter_fwd", "ocrl_sa_iter_bwd",
+]
+
+
+class SaDims(Structure):
+    _fields_ = [("B", c_int32), ("N", c_int32), ("C_in", c_int32), ("D", c_int32), ("H_mlp", c_int32),
+                ("K", c_int32), ("T", c_int32), ("heads", c_int32), ("eps", c_float), ("ln_eps", c_float),
+                ("kv_dtype", c_int32), ("math_mode", c_int32)]
+
+
+_SA_W = ["ln_slots_w", "ln_slots_b", "ln_mlp_w", "ln_mlp_b", "wq", "w_ih", "w_hh", "b_ih", "b_hh",
+         "w1", "b1", "w2", "b2"]
+_TOK_W = ["enc_ln_w", "enc_ln_b", "mlp_w1", "mlp_b1", "mlp_w2", "mlp_b2", "in_ln_w", "in_ln_b", "wk", "wv"]
+
+
+class SaWeights(Structure):
+    _fields_ = [(n, c_void_p) for n in _SA_W]
+
+
+class SaWeightGrads(Structure):
+    _fields_ = [(n, c_void_p) for n in _SA_W]
+
+
+class TokenWeights(Structure):
+    _fields_ = [(n, c_void_p) for n in _TOK_W]
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m ocrl_b200.build` "
+                "(there is no CPU or PyTorch fallback for the slot-attention path)")
+        L = ctypes.CDLL(LIB_PATH)
+        L.ocrl_version.restype = c_int
+        L.ocrl_built_arch.restype = c_char_p
+        L.ocrl_last_error.restype = c_char_p
+        L.ocrl_sa_query_workspace.argtypes = [POINTER(SaDims), POINTER(c_size_t), POINTER(c_size_t), POINTER(c_size_t)]
+        L.ocrl_kv_proj_fwd.argtypes = [POINTER(SaDims), c_void_p, c_void_p, POINTER(TokenWeights), c_void_p,
+                                       c_void_p, c_void_p, c_void_p]
+        L.ocrl_kv_proj_bwd_workspace.argtypes = [POINTER(SaDims)]
+        L.ocrl_kv_proj_bwd_workspace.restype = c_size_t
+        L.ocrl_kv_proj_bwd.argtypes = [POINTER(SaDims), c_void_p, POINTER(TokenWeights), c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+        L.ocrl_sa_iter_fwd.argtypes = [POINTER(SaDims), c_void_p, c_void_p, c_void_p, POINTER(SaWeights), c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_void_p]
+        L.ocrl_sa_iter_bwd.argtypes = [POINTER(SaDims), c_void_p, c_void_p, c_void_p, POINTER(SaWeights), c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, POINTER(SaWeightGrads), c_void_p,
+                                       c_void_p]
+        for name in ("ocrl_sa_query_workspace", "ocrl_kv_proj_fwd", "ocrl_kv_proj_bwd", "ocrl_sa_iter_fwd",
+                     "ocrl_sa_iter_bwd"):
+            getattr(L, name).restype = c_int
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().ocrl_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def ptr(t) -> c_void_p:
+    if t is None:
+        return c_void_p(0)
+    assert t.is_cuda and t.is_contiguous(), "libocrl_sa takes contiguous CUDA tensors"
+    return c_void_p(t.data_ptr())
+
+
+def stream_ptr() -> c_void_p:
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def make_dims(B, N, C_in, D, H_mlp, K, T, heads=1, eps=1e-8, ln_eps=1e-5, kv_dtype=DT_F32, math_mode=MATH_FP32):
+    return SaDims(B, N, C_in, D, H_mlp, K, T, heads, eps, ln_eps, kv_dtype, math_mode)
+
+
+def query_workspace(dims: SaDims):
+    f, b, s = c_size_t(0), c_size_t(0), c_size_t(0)
+    check(lib().ocrl_sa_query_workspace(ctypes.byref(dims), ctypes.byref(f), ctypes.byref(b), ctypes.byref(s)),
+          "ocrl_sa_query_workspace")
+    return f.value, b.value, s.value
+
+
+def sa_weights(**tensors) -> SaWeights:
+    return SaWeights(*[ptr(tensors[n]) for n in _SA_W])
+
+
+def sa_weight_grads(**tensors) -> SaWeightGrads:
+    return SaWeightGrads(*[ptr(tensors[n]) for n in _SA_W])
+
+
+def token_weights(**tensors) -> TokenWeights:
+    return TokenWeights(*[ptr(tensors.get(n)) for n in _TOK_W])

@@ -1,0 +1,74 @@
+"""In-tree build of libocrl_sa.so for sm_100a (nvcc cross-compiles without a GPU).
+
+    python -m ocrl_b200.build [--force] [--verbose]
+
+The shared library is written next to the sources (ocrl_b200/csrc/libocrl_sa.so) so that it
+travels with the repository snapshot to the GPU box; it is git-ignored.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(CSRC, "libocrl_sa.so")
+BUILD = os.path.join(CSRC, "build")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+
+
+def _sources():
+    return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _digest():
+    h = hashlib.sha256()
+    for f in sorted(os.listdir(CSRC)) + ["../../include/ocrl_sa.h"]:
+        p = os.path.join(CSRC, f)
+        if os.path.isfile(p) and f.endswith((".cu", ".cuh", ".h")):
+            h.update(f.encode())
+            h.update(open(p, "rb").read())
+    h.update(" ".join(FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(BUILD, exist_ok=True)
+    stamp = os.path.join(BUILD, "digest.txt")
+    dig = _digest()
+    if not force and os.path.isfile(OUT) and os.path.isfile(stamp) and open(stamp).read() == dig:
+        return OUT
+    if not os.path.isfile(NVCC):
+        raise RuntimeError(f"nvcc not found at {NVCC}; libocrl_sa.so must be built where the CUDA toolkit is")
+
+    def compile_one(src):
+        obj = os.path.join(BUILD, src[:-3] + ".o")
+        cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        log = os.path.join(BUILD, src[:-3] + ".ptxas.log")
+        with open(log, "w") as f:
+            f.write(r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stderr[-4000:]}")
+        if verbose:
+            sys.stderr.write(r.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(compile_one, _sources()))
+    cmd = [NVCC, "-shared", "-o", OUT, *objs, "-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stderr[-4000:]}")
+    with open(stamp, "w") as f:
+        f.write(dig)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

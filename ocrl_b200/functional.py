@@ -1,0 +1,173 @@
+"""Host-side operators over libocrl_sa.so: plain calls for inference and a
+``torch.autograd.Function`` for training.  Every arithmetic step of the slot-attention path runs
+in the hand-written sm_100a kernels behind the C ABI; torch is used for device memory and streams.
+
+Reference being replaced: ``SlotAttention.forward`` (ocrs/common/slot_attn.py:47-102) and the
+token LayerNorm+MLP of ``SlotAttentionEncoder.forward`` (slot_attn.py:151).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import abi
+
+Tensor = torch.Tensor
+
+SA_PARAM_ORDER = [
+    "norm_inputs.weight", "norm_inputs.bias", "norm_slots.weight", "norm_slots.bias",
+    "norm_mlp.weight", "norm_mlp.bias", "project_q.weight", "project_k.weight", "project_v.weight",
+    "gru.weight_ih", "gru.weight_hh", "gru.bias_ih", "gru.bias_hh",
+    "mlp.0.weight", "mlp.0.bias", "mlp.2.weight", "mlp.2.bias",
+]
+
+_KV_DTYPES = {"fp32": (abi.DT_F32, torch.float32), "bf16": (abi.DT_BF16, torch.bfloat16)}
+
+
+def _f32c(t: Tensor) -> Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _require_cuda(t: Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: ocrl_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+
+
+def _sa_weights(p: Dict[str, Tensor]) -> abi.SaWeights:
+    return abi.sa_weights(
+        ln_slots_w=p["norm_slots.weight"], ln_slots_b=p["norm_slots.bias"],
+        ln_mlp_w=p["norm_mlp.weight"], ln_mlp_b=p["norm_mlp.bias"], wq=p["project_q.weight"],
+        w_ih=p["gru.weight_ih"], w_hh=p["gru.weight_hh"], b_ih=p["gru.bias_ih"], b_hh=p["gru.bias_hh"],
+        w1=p["mlp.0.weight"], b1=p["mlp.0.bias"], w2=p["mlp.2.weight"], b2=p["mlp.2.bias"])
+
+
+def kv_project(x: Tensor, p: Dict[str, Tensor], *, kv: str = "fp32", enc: Optional[Dict[str, Tensor]] = None,
+               pos_table: Optional[Tensor] = None, want_y: bool = False, ln_eps: float = 1e-5):
+    """Token stage: [pos add + NCHW->tokens] -> [LN+MLP of the encoder] -> norm_inputs -> k, v.
+
+    x: [B,N,C] tokens, or the NCHW feature map [B,C,H,W] when ``pos_table`` ([C,H*W]) is given.
+    enc: optional {"layer_norm.weight","layer_norm.bias","mlp.0.weight",...} of SlotAttentionEncoder.
+    Returns (k, v, y) with y = token-MLP output [B,N,C] (None unless want_y).
+    """
+    _require_cuda(x, "kv_project")
+    x = _f32c(x)
+    if pos_table is not None:
+        B, C = x.shape[0], x.shape[1]
+        N = x.shape[2] * x.shape[3]
+        pos_table = _f32c(pos_table).reshape(C, N)
+    else:
+        B, N, C = x.shape
+    D = p["project_k.weight"].shape[0]
+    dt_code, dt = _KV_DTYPES[kv]
+    dims = abi.make_dims(B, N, C, D, D, 1, 1, kv_dtype=dt_code, ln_eps=ln_eps)
+    k = torch.empty(B, N, D, device=x.device, dtype=dt)
+    v = torch.empty(B, N, D, device=x.device, dtype=dt)
+    y = torch.empty(B, N, C, device=x.device, dtype=torch.float32) if want_y else None
+    keep = {n: _f32c(p[n]) for n in ("norm_inputs.weight", "norm_inputs.bias", "project_k.weight", "project_v.weight")}
+    tw = dict(in_ln_w=keep["norm_inputs.weight"], in_ln_b=keep["norm_inputs.bias"],
+              wk=keep["project_k.weight"], wv=keep["project_v.weight"])
+    if enc is not None:
+        e = {n: _f32c(t) for n, t in enc.items()}
+        keep.update({"e." + n: t for n, t in e.items()})
+        tw.update(enc_ln_w=e["layer_norm.weight"], enc_ln_b=e["layer_norm.bias"], mlp_w1=e["mlp.0.weight"],
+                  mlp_b1=e["mlp.0.bias"], mlp_w2=e["mlp.2.weight"], mlp_b2=e["mlp.2.bias"])
+    w = abi.token_weights(**tw)
+    abi.check(abi.lib().ocrl_kv_proj_fwd(ctypes.byref(dims), abi.ptr(x), abi.ptr(pos_table), ctypes.byref(w),
+                                         abi.ptr(y), abi.ptr(k), abi.ptr(v), abi.stream_ptr()), "ocrl_kv_proj_fwd")
+    return k, v, y
+
+
+def iterate(k: Tensor, v: Tensor, slots0: Tensor, p: Dict[str, Tensor], num_iterations: int, *,
+            epsilon: float = 1e-8, ln_eps: float = 1e-5, want_attn: bool = True, save: bool = False):
+    """The fused T-iteration loop.  k, v: [B,N,D] fp32 or bf16; slots0 [B,K,D].
+    Returns (slots, attn_vis or None, saved or None)."""
+    _require_cuda(k, "iterate")
+    B, N, D = k.shape
+    K = slots0.shape[1]
+    H = p["mlp.0.weight"].shape[0]
+    dt_code = abi.DT_BF16 if k.dtype == torch.bfloat16 else abi.DT_F32
+    dims = abi.make_dims(B, N, 64, D, H, K, num_iterations, eps=epsilon, ln_eps=ln_eps, kv_dtype=dt_code)
+    pw = {n: _f32c(p[n]) for n in SA_PARAM_ORDER if n in p}
+    slots0 = _f32c(slots0)
+    slots = torch.empty(B, K, D, device=k.device, dtype=torch.float32)
+    attn = torch.empty(B, N, K, device=k.device, dtype=torch.float32) if want_attn else None
+    saved = None
+    if save:
+        _, _, saved_bytes = abi.query_workspace(dims)
+        saved = torch.empty(saved_bytes // 4, device=k.device, dtype=torch.float32)
+    w = _sa_weights(pw)
+    abi.check(abi.lib().ocrl_sa_iter_fwd(ctypes.byref(dims), abi.ptr(k), abi.ptr(v), abi.ptr(slots0), ctypes.byref(w),
+                                         abi.ptr(slots), abi.ptr(attn), abi.ptr(saved), None, abi.stream_ptr()),
+              "ocrl_sa_iter_fwd")
+    return slots, attn, saved
+
+
+def slot_attention(inputs: Tensor, slots0: Tensor, p: Dict[str, Tensor], num_iterations: int, *,
+                   epsilon: float = 1e-8, kv: str = "fp32", enc: Optional[Dict[str, Tensor]] = None,
+                   pos_table: Optional[Tensor] = None, want_attn: bool = True) -> Tuple[Tensor, Optional[Tensor]]:
+    """Inference-only SlotAttention.forward (no autograd graph)."""
+    k, v, _ = kv_project(inputs, p, kv=kv, enc=enc, pos_table=pos_table)
+    slots, attn, _ = iterate(k, v, slots0, p, num_iterations, epsilon=epsilon, want_attn=want_attn)
+    return slots, attn
+
+
+class SlotAttentionFunction(torch.autograd.Function):
+    """SlotAttention.forward(inputs, slots) with a fused CUDA forward and backward.
+
+    The backward recomputes the attention logits from k and the saved per-iteration slots; only
+    O(T*K*D) state per image is kept between the passes (plus k, v themselves).
+    """
+
+    @staticmethod
+    def forward(ctx, inputs, slots0, num_iterations, epsilon, kv, *params):
+        p = dict(zip(SA_PARAM_ORDER, params))
+        inputs_c = _f32c(inputs)
+        k, v, _ = kv_project(inputs_c, p, kv=kv)
+        slots, attn, saved = iterate(k, v, slots0, p, num_iterations, epsilon=epsilon, want_attn=True, save=True)
+        ctx.save_for_backward(inputs_c, k, v, saved, *[_f32c(t) for t in params])
+        ctx.meta = (num_iterations, epsilon, kv, slots0.shape[1])
+        return slots, attn
+
+    @staticmethod
+    def backward(ctx, d_slots, d_attn):
+        inputs, k, v, saved, *params = ctx.saved_tensors
+        T, epsilon, kv, K = ctx.meta
+        p = dict(zip(SA_PARAM_ORDER, params))
+        B, N, D = k.shape
+        C = inputs.shape[-1]
+        H = p["mlp.0.weight"].shape[0]
+        dt_code = abi.DT_BF16 if k.dtype == torch.bfloat16 else abi.DT_F32
+        dims = abi.make_dims(B, N, C, D, H, K, T, eps=epsilon, kv_dtype=dt_code)
+        dev = k.device
+        _, bwd_ws, _ = abi.query_workspace(dims)
+        ws = torch.empty(max(bwd_ws, 16), device=dev, dtype=torch.uint8)
+        dk = torch.empty(B, N, D, device=dev, dtype=torch.float32)
+        dv = torch.empty(B, N, D, device=dev, dtype=torch.float32)
+        d_slots0 = torch.empty(B, K, D, device=dev, dtype=torch.float32)
+        g = {n: torch.empty_like(p[n]) for n in SA_PARAM_ORDER}
+        dw = abi.sa_weight_grads(
+            ln_slots_w=g["norm_slots.weight"], ln_slots_b=g["norm_slots.bias"], ln_mlp_w=g["norm_mlp.weight"],
+            ln_mlp_b=g["norm_mlp.bias"], wq=g["project_q.weight"], w_ih=g["gru.weight_ih"], w_hh=g["gru.weight_hh"],
+            b_ih=g["gru.bias_ih"], b_hh=g["gru.bias_hh"], w1=g["mlp.0.weight"], b1=g["mlp.0.bias"],
+            w2=g["mlp.2.weight"], b2=g["mlp.2.bias"])
+        w = _sa_weights(p)
+        d_slots = _f32c(d_slots)
+        d_attn_c = _f32c(d_attn) if d_attn is not None else None
+        L = abi.lib()
+        abi.check(L.ocrl_sa_iter_bwd(ctypes.byref(dims), abi.ptr(k), abi.ptr(v), abi.ptr(saved), ctypes.byref(w),
+                                     abi.ptr(d_slots), abi.ptr(d_attn_c), abi.ptr(dk), abi.ptr(dv), abi.ptr(d_slots0),
+                                     ctypes.byref(dw), abi.ptr(ws), abi.stream_ptr()), "ocrl_sa_iter_bwd")
+        # norm_inputs + project_k / project_v
+        ws2 = torch.empty(max(L.ocrl_kv_proj_bwd_workspace(ctypes.byref(dims)), 16), device=dev, dtype=torch.uint8)
+        dx = torch.empty_like(inputs)
+        tw = abi.token_weights(in_ln_w=p["norm_inputs.weight"], in_ln_b=p["norm_inputs.bias"],
+                               wk=p["project_k.weight"], wv=p["project_v.weight"])
+        abi.check(L.ocrl_kv_proj_bwd(ctypes.byref(dims), abi.ptr(inputs), ctypes.byref(tw), abi.ptr(dk), abi.ptr(dv),
+                                     abi.ptr(dx), abi.ptr(g["norm_inputs.weight"]), abi.ptr(g["norm_inputs.bias"]),
+                                     abi.ptr(g["project_k.weight"]), abi.ptr(g["project_v.weight"]), abi.ptr(ws2),
+                                     abi.stream_ptr()), "ocrl_kv_proj_bwd")
+        return (dx, d_slots0, None, None, None, *[g[n] for n in SA_PARAM_ORDER])
