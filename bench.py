@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""Benchmark of the slot-attention hot path: SLATE slot-encode images/s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--kv fp32|bf16] [--impl reference]
+
+One "step" = one batch of B synthetic 64x64 frames per GPU through ``SLATE.__call__`` (CNN
+encoder -> token stage -> fused T-iteration slot-attention kernel), K=6 slots, T=3 iterations,
+D=192 (configs/ocr/slate.yaml + README override), seeded random-init weights.
+
+Prints ONE JSON line (rank 0).  ``value`` = images/s with frames resident in HBM; ``e2e`` = the
+same through the public API from pinned HOST buffers (H2D of the frames and D2H of the slots in
+the timed region); ``roofline`` = fused iteration kernel, algorithmic bytes / CUDA-event time
+against the measured HBM peak; ``cpu_baseline`` = the oracle port on the host cores.
+``--impl reference`` times the reference's CPU path (oracle port, all host threads) instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "slot-encode images/s"
+UNIT = "images/s"
+HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step")
+    ap.add_argument("--size", type=int, default=64, help="frame size (64 -> N=4096 tokens)")
+    ap.add_argument("--slots", type=int, default=6)
+    ap.add_argument("--iters", type=int, default=3)
+    ap.add_argument("--slot-size", type=int, default=192)
+    ap.add_argument("--kv", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--impl", default="ocrl_b200", choices=["ocrl_b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pool", type=int, default=512, help="distinct frames in the synthetic pool")
+    return ap.parse_args()
+
+
+def workload(a):
+    return {"workload": f"SLATE encode, {a.size}x{a.size} random-N5C4S4S2 frames (N={a.size * a.size} tokens), "
+                        f"K={a.slots}, T={a.iters}, D={a.slot_size}, batch {a.batch}/GPU",
+            "frame": a.size, "tokens": a.size * a.size, "num_slots": a.slots, "num_iterations": a.iters,
+            "slot_size": a.slot_size, "batch_per_gpu": a.batch, "kv_storage": a.kv,
+            "weights": "seeded random-init (pretrained_encoders/slate.pth absent from the reference checkout)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm on the host cores (oracle port; the Python reference cannot travel)
+# ------------------------------------------------------------------------------------------------
+def cpu_encode_fn(a, frames_u8):
+    from oracle import slot_oracle as so
+    from ocrl_b200.config import slate_config
+    import ocrl_b200
+
+    torch.manual_seed(0)
+    model = ocrl_b200.SLATE(*slate_config(num_slots=a.slots, num_iterations=a.iters, slot_size=a.slot_size,
+                                          mlp_hidden_size=a.slot_size, obs_size=a.size))
+    p = {k: v.detach() for k, v in model._module.state_dict().items()}
+    obs = frames_u8[: a.batch].permute(0, 3, 1, 2).float() / 255.0
+    g = torch.Generator().manual_seed(1)
+
+    def step():
+        with torch.no_grad():
+            noise = torch.randn(a.batch, a.slots, a.slot_size, generator=g)
+            return so.slate_encode(obs, noise, p, a.iters)[0]
+
+    return step
+
+
+def time_cpu(a, frames_u8, steps, warmup):
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    step = cpu_encode_fn(a, frames_u8)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return a.batch * steps / dt, dt / steps * 1e3, cores
+
+
+def run_reference(a, rank):
+    """--impl reference: the reference's CPU path for the same metric and config."""
+    if rank != 0:
+        return
+    from ocrl_b200 import synth
+
+    frames = torch.from_numpy(synth.random_objs_frames(max(a.batch, 64), a.size, seed=0))
+    steps = max(1, a.steps)
+    ips, ms, cores = time_cpu(a, frames, steps, max(1, min(a.warmup, 2)))
+    sample = f"{steps} steps of one {a.batch}-frame batch, oracle port (torch CPU ops, fp32), {cores} threads"
+    line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+            "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload(a),
+            "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if a.impl == "reference":
+        run_reference(a, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the ocrl_b200 path has no CPU fallback; use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    import ocrl_b200
+    from ocrl_b200 import functional as F
+    from ocrl_b200 import synth
+    from ocrl_b200.config import slate_config
+
+    os.environ["OCRL_KV_DTYPE"] = a.kv
+    torch.backends.cudnn.allow_tf32 = False  # fp32 end to end, like the reference's CPU path
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True
+    torch.manual_seed(0)
+    model = ocrl_b200.SLATE(*slate_config(num_slots=a.slots, num_iterations=a.iters, slot_size=a.slot_size,
+                                          mlp_hidden_size=a.slot_size, obs_size=a.size))
+    model.to(dev)
+    model.eval()
+
+    # each rank owns its own shard of the frame pool (no data-path collective: images are independent)
+    pool_u8 = torch.from_numpy(synth.random_objs_frames(a.pool, a.size, seed=1000 + rank))
+    pool_host = synth.to_obs(pool_u8).contiguous().pin_memory()  # float32 CHW in [0,1], as the reference API takes
+    pool_dev = pool_host.to(dev)
+    nb = a.pool // a.batch
+    assert nb >= 1, "--pool must be >= --batch"
+    torch.manual_seed(1 + rank)
+
+    def step_resident(i):
+        obs = pool_dev[(i % nb) * a.batch:(i % nb + 1) * a.batch]
+        with torch.no_grad():
+            return model(obs)
+
+    out_host = torch.empty(a.batch, a.slots, a.slot_size, dtype=torch.float32).pin_memory()
+    obs_stage = torch.empty(a.batch, 3, a.size, a.size, device=dev)
+
+    def step_e2e(i):
+        src = pool_host[(i % nb) * a.batch:(i % nb + 1) * a.batch]
+        obs_stage.copy_(src, non_blocking=True)
+        with torch.no_grad():
+            slots = model(obs_stage)
+        out_host.copy_(slots, non_blocking=True)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, kernel_timers=False):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        F.KERNEL_EVENTS = [] if kernel_timers else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        ev = F.KERNEL_EVENTS
+        F.KERNEL_EVENTS = None
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, ev
+
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+    ms_total, events = timed(step_resident, a.steps, a.warmup, kernel_timers=True)
+    clk = clocks.stop() if rank == 0 else None
+    ms_e2e, _ = timed(step_e2e, a.steps, max(3, a.warmup))
+
+    images = a.batch * a.steps * world
+    value = images / ms_total * 1e3
+    e2e_value = images / ms_e2e * 1e3
+
+    # roofline of the fused iteration kernel (rank 0's launches; CUDA events on the launch stream)
+    it_ms = [s.elapsed_time(e) for name, s, e in events if name == "sa_iter_fwd"]
+    tk_ms = [s.elapsed_time(e) for name, s, e in events if name == "kv_proj_fwd"]
+    N, D, K = a.size * a.size, a.slot_size, a.slots
+    esz = 4 if a.kv == "fp32" else 2
+    bytes_img = 2 * N * D * esz + N * K * 4 + 2 * K * D * 4
+    peak, peak_src = HBM_FALLBACK_GBS, "fallback"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        pass
+    it_avg = sum(it_ms) / max(1, len(it_ms))
+    achieved = a.batch * bytes_img / (it_avg * 1e-3) / 1e9 if it_ms else None
+    roofline = {"kernel": "sa_iter_fwd_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak if achieved else None), "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_image": bytes_img, "avg_launch_ms": it_avg, "launches_timed": len(it_ms),
+                "token_stage_avg_ms": (sum(tk_ms) / len(tk_ms) if tk_ms else None)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32" if a.kv == "fp32" else "bf16 k/v storage, f32 accumulate", "data": "synthetic",
+                "config": dict(workload(a), l2="k/v working set per step %.0f MB > 126 MB L2; frame pool of %d rotates"
+                               % (a.batch * 2 * N * D * esz / 1e6, a.pool),
+                               cnn="cuDNN fp32 via torch (TF32 off); token stage + iteration loop hand-written CUDA"),
+                "clocks": clk,
+                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
+                        "h2d_bytes_per_step": a.batch * 3 * a.size * a.size * 4,
+                        "d2h_bytes_per_step": a.batch * a.slots * a.slot_size * 4},
+                "gpu_launches": len(events) if events else 0,
+                "roofline": roofline}
+        if world == 1 and not a.no_cpu_baseline:
+            csteps = 6
+            ips, cms, cores = time_cpu(a, pool_u8, csteps, 1)
+            line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{csteps} batches of {a.batch} frames ({cms:.0f} ms each), oracle port "
+                                              f"of the reference path with torch CPU ops, fp32"}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

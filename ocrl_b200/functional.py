@@ -25,6 +25,27 @@ SA_PARAM_ORDER = [
 
 _KV_DTYPES = {"fp32": (abi.DT_F32, torch.float32), "bf16": (abi.DT_BF16, torch.bfloat16)}
 
+# When set to a list, every C-ABI launch appends (name, start_event, end_event) recorded on the
+# launching stream; bench.py uses it to time the kernels live inside the step.
+KERNEL_EVENTS = None
+
+
+class _timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if KERNEL_EVENTS is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if KERNEL_EVENTS is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            KERNEL_EVENTS.append((self.name, self.e0, e1))
+        return False
+
 
 def _f32c(t: Tensor) -> Tensor:
     if t.dtype != torch.float32:
@@ -76,8 +97,10 @@ def kv_project(x: Tensor, p: Dict[str, Tensor], *, kv: str = "fp32", enc: Option
         tw.update(enc_ln_w=e["layer_norm.weight"], enc_ln_b=e["layer_norm.bias"], mlp_w1=e["mlp.0.weight"],
                   mlp_b1=e["mlp.0.bias"], mlp_w2=e["mlp.2.weight"], mlp_b2=e["mlp.2.bias"])
     w = abi.token_weights(**tw)
-    abi.check(abi.lib().ocrl_kv_proj_fwd(ctypes.byref(dims), abi.ptr(x), abi.ptr(pos_table), ctypes.byref(w),
-                                         abi.ptr(y), abi.ptr(k), abi.ptr(v), abi.stream_ptr()), "ocrl_kv_proj_fwd")
+    with _timed("kv_proj_fwd"):
+        abi.check(abi.lib().ocrl_kv_proj_fwd(ctypes.byref(dims), abi.ptr(x), abi.ptr(pos_table), ctypes.byref(w),
+                                             abi.ptr(y), abi.ptr(k), abi.ptr(v), abi.stream_ptr()),
+                  "ocrl_kv_proj_fwd")
     return k, v, y
 
 
@@ -100,9 +123,10 @@ def iterate(k: Tensor, v: Tensor, slots0: Tensor, p: Dict[str, Tensor], num_iter
         _, _, saved_bytes = abi.query_workspace(dims)
         saved = torch.empty(saved_bytes // 4, device=k.device, dtype=torch.float32)
     w = _sa_weights(pw)
-    abi.check(abi.lib().ocrl_sa_iter_fwd(ctypes.byref(dims), abi.ptr(k), abi.ptr(v), abi.ptr(slots0), ctypes.byref(w),
-                                         abi.ptr(slots), abi.ptr(attn), abi.ptr(saved), None, abi.stream_ptr()),
-              "ocrl_sa_iter_fwd")
+    with _timed("sa_iter_fwd"):
+        abi.check(abi.lib().ocrl_sa_iter_fwd(ctypes.byref(dims), abi.ptr(k), abi.ptr(v), abi.ptr(slots0),
+                                             ctypes.byref(w), abi.ptr(slots), abi.ptr(attn), abi.ptr(saved), None,
+                                             abi.stream_ptr()), "ocrl_sa_iter_fwd")
     return slots, attn, saved
 
 

@@ -1,0 +1,102 @@
+"""GPU parity of the drop-in modules (SLATE / SLATE_Module / SlotAttentionEncoder / SlotAttention)
+against the frozen reference outputs."""
+import pytest
+import torch
+
+import ocrl_b200
+from ocrl_b200.config import slate_config, slot_attention_config
+from tests.golden_io import load_case, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(autouse=True)
+def _fp32_convs():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def _inject_noise(encoder, noise):
+    def init_slots(batch, like):
+        return encoder.slot_mu + torch.exp(encoder.slot_log_sigma) * noise.to(like.device)
+
+    encoder.init_slots = init_slots
+
+
+def _load_hot(module, params):
+    sd = module.state_dict()
+    for k, v in params.items():
+        assert k in sd and sd[k].shape == v.shape, k
+        sd[k] = v
+    module.load_state_dict(sd)
+
+
+@pytest.mark.parametrize("name,cfg", [("slate_encode_64", slate_config()),
+                                      ("bcdec_encode_32", slot_attention_config(obs_size=32))])
+def test_slate_call_matches_reference(name, cfg):
+    meta, g = load_case(name)
+    model = ocrl_b200.SLATE(*cfg)
+    _load_hot(model._module, g["p"])
+    model.to("cuda")
+    model.eval()
+    _inject_noise(model._module._slotattn, g["in"]["noise"])
+    obs = (g["in"]["frames_u8"].permute(0, 3, 1, 2).float() / 255.0).cuda()
+    with torch.no_grad():
+        slots = model(obs)
+        slots_m, masks = model(obs, with_masks=True)
+        _, attns = model(obs, with_attns=True)
+    assert slots.shape == g["out"]["slots"].shape and masks.shape == g["out"]["masks"].shape
+    assert rel_err(slots.cpu(), g["out"]["slots"]) < TOL
+    assert torch.equal(slots, slots_m)
+    assert rel_err(masks.cpu(), g["out"]["masks"]) < TOL
+    assert rel_err(attns.cpu(), g["out"]["attns"]) < TOL
+    # argmax segmentation (what calculate_ari consumes, utils/tools.py:309-320)
+    mine, ref = masks.cpu().flatten(2).argmax(1), g["out"]["masks"].flatten(2).argmax(1)
+    top2 = g["out"]["masks"].flatten(2).topk(2, dim=1).values
+    decidable = (top2[:, 0] - top2[:, 1]) > 1e-4
+    assert bool(((mine == ref) | ~decidable).all())
+    # the bare module also works with a single argument (sb3s/ocr_extractor.py:45)
+    with torch.no_grad():
+        assert torch.equal(model._module(obs), slots)
+
+
+def test_encoder_module_matches_reference():
+    meta, g = load_case("encoder_slate")
+    enc = ocrl_b200.SlotAttentionEncoder(meta["T"], meta["K"], meta["C"], meta["D"], meta["H"], 4, 1)
+    enc.load_state_dict(g["p"])
+    enc.cuda()
+    _inject_noise(enc, g["in"]["noise"])
+    with torch.no_grad():
+        slots, attn = enc(g["in"]["x"].cuda())
+    assert rel_err(slots.cpu(), g["out"]["slots"]) < TOL and rel_err(attn.cpu(), g["out"]["attn"]) < TOL
+
+
+@pytest.mark.parametrize("name", ["sa_small_grad", "sa_k11_t5_ragged"])
+def test_slot_attention_module_matches_reference(name):
+    meta, g = load_case(name)
+    sa = ocrl_b200.SlotAttention(meta["T"], meta["K"], meta["C"], meta["D"], meta["H"], 1, meta["eps"])
+    sa.load_state_dict(g["p"])
+    sa.cuda()
+    x, s0 = g["in"]["inputs"].cuda(), g["in"]["slots0"].cuda()
+    with torch.no_grad():
+        slots, attn = sa(x, s0)
+    assert rel_err(slots.cpu(), g["out"]["slots"]) < TOL and rel_err(attn.cpu(), g["out"]["attn"]) < TOL
+    # inputs are not mutated, outputs are fresh contiguous fp32 tensors
+    assert torch.equal(x.cpu(), g["in"]["inputs"]) and slots.is_contiguous() and slots.dtype == torch.float32
+
+
+def test_bf16_mode_through_the_module(monkeypatch):
+    meta, g = load_case("slate_encode_64")
+    monkeypatch.setenv("OCRL_KV_DTYPE", "bf16")
+    model = ocrl_b200.SLATE(*slate_config())
+    assert model._module._slotattn.slot_attention.kv_dtype == "bf16"
+    _load_hot(model._module, g["p"])
+    model.to("cuda")
+    _inject_noise(model._module._slotattn, g["in"]["noise"])
+    obs = (g["in"]["frames_u8"].permute(0, 3, 1, 2).float() / 255.0).cuda()
+    with torch.no_grad():
+        slots, masks = model(obs, with_masks=True)
+    assert rel_err(slots.cpu(), g["out"]["slots"]) < 2e-2
+    assert rel_err(masks.cpu(), g["out"]["masks"]) < 2e-2

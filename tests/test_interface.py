@@ -1,0 +1,113 @@
+"""CPU-side checks of the drop-in boundary: checkpoint layout, seeded init, OCR wrapper API,
+C-ABI exports, error conventions (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import ocrl_b200
+from ocrl_b200 import abi, synth
+from ocrl_b200.config import slate_config, slot_attention_config
+from tests.golden_io import load_json
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("tag,cfg", [("slate", slate_config()), ("bcdec", slot_attention_config(obs_size=32))])
+def test_state_dict_layout_matches_reference(tag, cfg):
+    ref = load_json(f"state_dict_{tag}.json")
+    model = ocrl_b200.SLATE(*cfg)
+    mine = {k: list(v.shape) for k, v in model._module.state_dict().items()}
+    assert list(mine.keys()) == list(ref["keys"].keys())
+    assert mine == ref["keys"]
+    assert model.rep_dim == ref["rep_dim"] and model.num_slots == ref["num_slots"]
+    assert sum(p.numel() for p in model._module.parameters()) == ref["n_params"]
+
+
+def test_seeded_init_equals_reference_init():
+    """Same seed -> same weights as the reference constructors (parity runs use random init)."""
+    sums = load_json("seed0_param_sums.json")
+    torch.manual_seed(0)
+    model = ocrl_b200.SLATE(*slate_config())
+    for k, v in model._module.state_dict().items():
+        assert abs(float(v.double().sum()) - sums[k]) <= 1e-9 * max(1.0, abs(sums[k])), k
+
+
+def test_wrapper_api_surface():
+    model = ocrl_b200.SLATE(*slate_config())
+    assert model.name == "SLATE"
+    for attr in ("__call__", "get_loss", "update", "train", "eval", "to", "set_zero_grad", "do_step", "get_samples",
+                 "save", "load", "wandb_watch"):
+        assert callable(getattr(model, attr))
+    assert isinstance(model._module, torch.nn.Module)
+    assert [len(g["params"]) for g in model._opt.param_groups] == [36, 36, 82]
+    ckpt = model.save()
+    assert set(ckpt) == {"ocr_module_state_dict", "ocr_opt_state_dict"}
+    other = ocrl_b200.SLATE(*slate_config())
+    other.load(ckpt)
+    for (k, a), (_, b) in zip(model._module.state_dict().items(), other._module.state_dict().items()):
+        assert torch.equal(a, b), k
+
+
+def test_use_cnn_feat_shapes():
+    model = ocrl_b200.SLATE(*slate_config(use_cnn_feat=True, obs_size=16))
+    assert model.num_slots == 256 and model.rep_dim == 67
+    out = model(torch.rand(2, 3, 16, 16))  # this branch never runs slot attention (slate_module.py:183-185)
+    assert out.shape == (2, 256, 67)
+
+
+def test_no_cpu_fallback():
+    model = ocrl_b200.SLATE(*slate_config(obs_size=16))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model(torch.rand(2, 3, 16, 16))
+    sa = ocrl_b200.SlotAttention(3, 6, 64, 192, 192, 2)
+    with pytest.raises(NotImplementedError):
+        sa(torch.rand(1, 4, 64), torch.rand(1, 6, 192))
+    with pytest.raises(AssertionError):
+        ocrl_b200.SLATE(*slate_config(obs_size=16))._module(torch.rand(1, 3, 16, 16), True, True)
+
+
+def test_abi_exports_every_declared_symbol():
+    lib = abi.lib()
+    header = open(os.path.join(ROOT, "include", "ocrl_sa.h")).read()
+    declared = set(re.findall(r"\b(ocrl_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(abi.EXPORTS), declared ^ set(abi.EXPORTS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.ocrl_version() == 1 and lib.ocrl_built_arch() == b"sm_100a"
+    assert ctypes.sizeof(abi.SaDims) == 48 and ctypes.sizeof(abi.SaWeights) == 13 * 8
+    assert ctypes.sizeof(abi.TokenWeights) == 10 * 8
+
+
+def test_abi_rejects_bad_dims_without_a_gpu():
+    lib = abi.lib()
+    f, b, s = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
+    d = abi.make_dims(2, 100, 64, 192, 192, 6, 3)
+    assert lib.ocrl_sa_query_workspace(ctypes.byref(d), ctypes.byref(f), ctypes.byref(b), ctypes.byref(s)) == 0
+    assert s.value == 4 * 2 * 3 * (2 * 6 * 192 + 6)
+    for bad in (abi.make_dims(2, 100, 64, 192, 192, 17, 3), abi.make_dims(2, 100, 64, 100, 192, 6, 3),
+                abi.make_dims(2, 100, 64, 192, 192, 6, 3, heads=2)):
+        assert lib.ocrl_sa_query_workspace(ctypes.byref(bad), ctypes.byref(f), ctypes.byref(b), ctypes.byref(s)) == -1
+        assert len(lib.ocrl_last_error()) > 0
+
+
+def test_synthetic_frames_are_deterministic():
+    a = synth.random_objs_frames(3, 64, seed=5)
+    b = synth.random_objs_frames(3, 64, seed=5)
+    assert a.shape == (3, 64, 64, 3) and a.dtype.name == "uint8" and (a == b).all()
+    assert (a.reshape(3, -1).max(1) > 0).all()
+    assert synth.push_frames(2, 64, seed=1).shape == (2, 64, 64, 3)
+    obs = synth.to_obs(torch.from_numpy(a))
+    assert obs.shape == (3, 3, 64, 64) and float(obs.max()) <= 1.0
+
+
+def test_schedules():
+    from ocrl_b200.adjacent import cosine_anneal, linear_warmup
+
+    assert cosine_anneal(0, 1.0, 0.1, 0, 100) == pytest.approx(1.0)
+    assert cosine_anneal(50, 1.0, 0.1, 0, 100) == pytest.approx(0.55)
+    assert cosine_anneal(100, 1.0, 0.1, 0, 100) == 0.1
+    assert linear_warmup(0, 0, 1, 0, 10) == pytest.approx(0.1)
+    assert linear_warmup(10, 0, 1, 0, 10) == 1
