@@ -64,12 +64,12 @@ class SlotAttention(nn.Module):
             "mlp.2.weight": self.mlp[2].weight, "mlp.2.bias": self.mlp[2].bias,
         }
 
-    def _check(self, inputs, slots):
+    def _check(self, inputs, slots, fmap=False):
         if self.num_heads != 1:
             raise NotImplementedError("ocrl_b200.SlotAttention supports num_slot_heads=1 (all shipped configs)")
         if not inputs.is_cuda:
             raise RuntimeError("ocrl_b200.SlotAttention runs on CUDA (sm_100a) only; there is no CPU fallback")
-        if inputs.dim() != 3 or slots.dim() != 3 or inputs.shape[0] != slots.shape[0]:
+        if inputs.dim() != (4 if fmap else 3) or slots.dim() != 3 or inputs.shape[0] != slots.shape[0]:
             raise ValueError(f"expected inputs [B,N,C] and slots [B,K,D], got {tuple(inputs.shape)}, {tuple(slots.shape)}")
 
     def forward(self, inputs, slots, *, _enc=None, _pos_table=None):
@@ -78,7 +78,7 @@ class SlotAttention(nn.Module):
         ``_enc`` / ``_pos_table`` are private hooks used by the encoder / SLATE module to fuse the
         token LayerNorm+MLP and the position-table add into the projection kernel (inference only).
         """
-        self._check(inputs, slots)
+        self._check(inputs, slots, fmap=_pos_table is not None)
         p = self._params()
         needs_grad = torch.is_grad_enabled() and (
             inputs.requires_grad or slots.requires_grad or any(t.requires_grad for t in p.values()))
