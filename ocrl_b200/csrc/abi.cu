@@ -3,7 +3,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "common.cuh"
+#include "slot_math.cuh"
 
 namespace ocrl {
 
@@ -103,7 +103,7 @@ int ocrl_sa_query_workspace(const ocrl_sa_dims* d, size_t* fwd_ws, size_t* bwd_w
   if (rc) return rc;
   if (fwd_ws) *fwd_ws = 0;
   if (bwd_ws) *bwd_ws = sa_iter_bwd_workspace(d);
-  if (saved) *saved = sizeof(float) * (size_t)d->B * d->T * (2 * (size_t)d->K * d->D + d->K);
+  if (saved) *saved = sizeof(float) * (size_t)d->B * d->T * (size_t)SavedLayout(d->K, d->D, d->H_mlp).stride();
   return OCRL_OK;
 }
 

@@ -10,7 +10,7 @@
 // across the cluster through distributed shared memory, and the GRUCell + residual MLP + next
 // query projection run distributed over the cluster (each CTA owns D/CL output features) with
 // DSMEM pushes + cluster barriers between the dependent layers.
-#include "common.cuh"
+#include "slot_math.cuh"
 
 namespace ocrl {
 
@@ -21,7 +21,7 @@ struct IterFwdArgs {
   ocrl_sa_weights w;
   float* slots_out;
   float* attn_out;  // may be null
-  float* saved;     // may be null: [B][T][2*K*D + K]
+  float* saved;     // may be null: [B][T][SavedLayout::stride()]
   int B, N, D, H, K, T, CL;
   float eps, ln_eps;
 };
@@ -41,68 +41,6 @@ struct FwdCfg {
   static_assert(NV <= 32, "group too large");
   static_assert(D % 64 == 0, "D must be a multiple of 64");
 };
-
-// out[j*ldo + out_off + row] = dot(W[row0+row, 0:L], vec[j, 0:L]) for row < nrows, j < KP.
-// One warp handles RB rows at a time; weights stream from global (L2-resident, shared by the batch).
-template <int KP, int RB>
-__device__ __forceinline__ void rows_dot(const float* __restrict__ W, int L, int row0, int nrows,
-                                         const float* vec, float* out, int ldo, int out_off, int warp,
-                                         int lane, int nwarps) {
-  constexpr int NV = RB * KP;
-  const int nb = (nrows + RB - 1) / RB;
-  for (int b = warp; b < nb; b += nwarps) {
-    float acc[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) acc[i] = 0.f;
-    for (int c = 0; c < L / 64; ++c) {
-      float2 wv[RB];
-#pragma unroll
-      for (int r = 0; r < RB; ++r) {
-        const int row = b * RB + r;
-        wv[r] = (row < nrows)
-                    ? __ldg(reinterpret_cast<const float2*>(W + (size_t)(row0 + row) * L + 64 * c + 2 * lane))
-                    : make_float2(0.f, 0.f);
-      }
-#pragma unroll
-      for (int j = 0; j < KP; ++j) {
-        const float2 x = *reinterpret_cast<const float2*>(vec + j * L + 64 * c + 2 * lane);
-#pragma unroll
-        for (int r = 0; r < RB; ++r) acc[r * KP + j] = fmaf(wv[r].x, x.x, fmaf(wv[r].y, x.y, acc[r * KP + j]));
-      }
-    }
-    int base;
-    xreduce<NV>(acc, lane, base);
-    if (XReduce<NV, 16>::primary(lane)) {
-#pragma unroll
-      for (int i = 0; i < XReduce<NV, 16>::kFinal; ++i) {
-        const int idx = base + i;
-        const int r = idx / KP, j = idx % KP;
-        const int row = b * RB + r;
-        if (row < nrows) out[j * ldo + out_off + row] = acc[i];
-      }
-    }
-  }
-}
-
-// LayerNorm of `rows` rows of length L held in shared memory (warp per row).
-__device__ __forceinline__ void ln_rows(const float* src, const float* __restrict__ gw,
-                                        const float* __restrict__ gb, float* dst, int rows, int L, float eps,
-                                        int warp, int lane, int nwarps) {
-  for (int j = warp; j < rows; j += nwarps) {
-    float s = 0.f;
-    for (int d = lane; d < L; d += 32) s += src[j * L + d];
-    const float mean = warp_sum(s) / (float)L;
-    float q = 0.f;
-    for (int d = lane; d < L; d += 32) {
-      const float t = src[j * L + d] - mean;
-      q = fmaf(t, t, q);
-    }
-    const float rstd = rsqrtf(warp_sum(q) / (float)L + eps);
-    for (int d = lane; d < L; d += 32) dst[j * L + d] = (src[j * L + d] - mean) * rstd * __ldg(gw + d) + __ldg(gb + d);
-  }
-}
-
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
 template <typename KV, int D, int KP>
 __global__ void __launch_bounds__(FwdCfg<KV, D, KP>::NT, 1) sa_iter_fwd_kernel(const IterFwdArgs a) {
@@ -166,7 +104,9 @@ __global__ void __launch_bounds__(FwdCfg<KV, D, KP>::NT, 1) sa_iter_fwd_kernel(c
   cluster.sync();  // every CTA's shared memory is initialised before any remote push
 
   // q = W_q LN_s(slots): each CTA computes DS output features and pushes them to all peers
-  auto compute_q = [&]() {
+  const SavedLayout SL(K, D, H);
+  auto saved_at = [&](int t) { return a.saved + ((size_t)img * a.T + t) * SL.stride(); };
+  auto compute_q = [&](int tq) {  // tq: the iteration that will consume this q
     ln_rows(s_prev, a.w.ln_slots_w, a.w.ln_slots_b, lnb, K, D, a.ln_eps, warp, lane, NW);
     __syncthreads();
     rows_dot<KP, G>(a.w.wq, D, rank * DS, DS, lnb, gates, DS, 0, warp, lane, NW);
@@ -175,10 +115,11 @@ __global__ void __launch_bounds__(FwdCfg<KV, D, KP>::NT, 1) sa_iter_fwd_kernel(c
       const int j = e / DS, o = e % DS;
       const float val = gates[j * DS + o];
       for (int r = 0; r < CL; ++r) cluster.map_shared_rank(q_s, r)[j * D + rank * DS + o] = val;
+      if (a.saved) saved_at(tq)[SL.off_q() + j * D + rank * DS + o] = val;
     }
     cluster.sync();
   };
-  compute_q();
+  compute_q(0);
 
   float* my_scr = scratch + warp * 64;
   uint64_t* my_bar = bars + warp * STAGES;
@@ -200,10 +141,10 @@ __global__ void __launch_bounds__(FwdCfg<KV, D, KP>::NT, 1) sa_iter_fwd_kernel(c
   for (int t = 0; t < a.T; ++t) {
     const bool last = (t == a.T - 1);
     if (a.saved) {  // slots entering iteration t, for the backward
-      float* sv = a.saved + ((size_t)img * a.T + t) * (2 * K * D + K);
+      float* sv = saved_at(t);
       for (int e = tid; e < K * DS; e += NT) {
         const int j = e / DS, o = e % DS;
-        sv[j * D + rank * DS + o] = s_prev[j * D + rank * DS + o];
+        sv[SL.off_h() + j * D + rank * DS + o] = s_prev[j * D + rank * DS + o];
       }
     }
 
@@ -348,9 +289,9 @@ __global__ void __launch_bounds__(FwdCfg<KV, D, KP>::NT, 1) sa_iter_fwd_kernel(c
       const float upd = tot / st;
       for (int r = 0; r < CL; ++r) cluster.map_shared_rank(upd_full, r)[j * D + rank * DS + o] = upd;
       if (a.saved) {
-        float* sv = a.saved + ((size_t)img * a.T + t) * (2 * K * D + K);
-        sv[K * D + j * D + rank * DS + o] = upd;
-        if (rank == 0 && o == 0) sv[2 * K * D + j] = st;
+        float* sv = saved_at(t);
+        sv[SL.off_u() + j * D + rank * DS + o] = upd;
+        if (rank == 0 && o == 0) sv[SL.off_s() + j] = st;
       }
     }
     cluster.sync();  // #2: updates[K][D] complete everywhere
@@ -377,6 +318,14 @@ __global__ void __launch_bounds__(FwdCfg<KV, D, KP>::NT, 1) sa_iter_fwd_kernel(c
       const float ng = tanhf(gin + rg * ghn);
       const float hn = (1.f - zg) * ng + zg * s_prev[j * D + f];
       for (int r = 0; r < CL; ++r) cluster.map_shared_rank(h_full, r)[j * D + f] = hn;
+      if (a.saved) {
+        float* sv = saved_at(t);
+        sv[SL.off_r() + j * D + f] = rg;
+        sv[SL.off_z() + j * D + f] = zg;
+        sv[SL.off_n() + j * D + f] = ng;
+        sv[SL.off_ghn() + j * D + f] = ghn;
+        sv[SL.off_hp() + j * D + f] = hn;
+      }
     }
     cluster.sync();  // #3: GRU output complete everywhere
 
@@ -387,8 +336,10 @@ __global__ void __launch_bounds__(FwdCfg<KV, D, KP>::NT, 1) sa_iter_fwd_kernel(c
     __syncthreads();
     for (int e = tid; e < K * HS; e += NT) {
       const int j = e / HS, o = e % HS;
-      const float hv = fmaxf(gates[j * HS + o] + __ldg(a.w.b1 + rank * HS + o), 0.f);
+      const float pre = gates[j * HS + o] + __ldg(a.w.b1 + rank * HS + o);
+      const float hv = fmaxf(pre, 0.f);
       for (int r = 0; r < CL; ++r) cluster.map_shared_rank(hid_full, r)[j * H + rank * HS + o] = hv;
+      if (a.saved) saved_at(t)[SL.off_pre() + j * H + rank * HS + o] = pre;
     }
     cluster.sync();  // #4: hidden layer complete everywhere
     rows_dot<KP, G>(a.w.w2, H, rank * DS, DS, hid_full, gates, DS, 0, warp, lane, NW);
@@ -401,7 +352,7 @@ __global__ void __launch_bounds__(FwdCfg<KV, D, KP>::NT, 1) sa_iter_fwd_kernel(c
       if (last) a.slots_out[((size_t)img * K + j) * D + f] = sn;
     }
     cluster.sync();  // #5: new slots complete everywhere
-    if (!last) compute_q();  // #6
+    if (!last) compute_q(t + 1);  // #6
   }
 }
 
