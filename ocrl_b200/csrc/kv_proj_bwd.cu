@@ -221,7 +221,7 @@ int kv_proj_bwd_launch(const ocrl_sa_dims* d, const float* x, const ocrl_token_w
       return OCRL_E_SHAPE;
   }
   OCRL_CHECK_CUDA(cudaGetLastError());
-  kv_proj_bwd_reduce_kernel<<<32, 256, 0, stream>>>(a.partial, grid, d->D, 1.0f, dwk, dwv, d_ln_w, d_ln_b);
+  kv_proj_bwd_reduce_kernel<<<32, 256, 0, stream>>>(a.partial, grid, d->D, a.kscale, dwk, dwv, d_ln_w, d_ln_b);
   OCRL_CHECK_CUDA(cudaGetLastError());
   return OCRL_OK;
 }

@@ -19,7 +19,7 @@ struct SavedLayout {
   __host__ __device__ int off_hp() const { return 7 * K * D; }   // GRU output h'                [K][D]
   __host__ __device__ int off_pre() const { return 8 * K * D; }  // MLP pre-activation           [K][H]
   __host__ __device__ int off_s() const { return 8 * K * D + K * H; }  // sum_n (a+eps)            [K]
-  __host__ __device__ int stride() const { return 8 * K * D + K * H + K; }
+  __host__ __device__ int stride() const { return (8 * K * D + K * H + K + 3) & ~3; }  // 16-byte multiple
 };
 
 // out[j*ldo + out_off + row] = dot(W[row0+row, 0:L], vec[j, 0:L]) for row < nrows, j < KP.

@@ -86,7 +86,7 @@ def test_abi_rejects_bad_dims_without_a_gpu():
     f, b, s = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
     d = abi.make_dims(2, 100, 64, 192, 192, 6, 3)
     assert lib.ocrl_sa_query_workspace(ctypes.byref(d), ctypes.byref(f), ctypes.byref(b), ctypes.byref(s)) == 0
-    assert s.value == 4 * 2 * 3 * (2 * 6 * 192 + 6)
+    assert s.value == 4 * 2 * 3 * ((8 * 6 * 192 + 6 * 192 + 6 + 3) // 4 * 4)
     for bad in (abi.make_dims(2, 100, 64, 192, 192, 17, 3), abi.make_dims(2, 100, 64, 100, 192, 6, 3),
                 abi.make_dims(2, 100, 64, 192, 192, 6, 3, heads=2)):
         assert lib.ocrl_sa_query_workspace(ctypes.byref(bad), ctypes.byref(f), ctypes.byref(b), ctypes.byref(s)) == -1
