@@ -1,0 +1,130 @@
+"""Data parallelism for the OCR wrappers: one process per GPU, batch sharded by image.
+
+Encode / rollout needs no communication (images are independent).  For OCR
+training the only exchange is the gradient all-reduce: parameters are bucketed in reverse
+construction order (the order autograd finishes them) and every bucket is all-reduced with NCCL
+on a side stream as soon as its last gradient has been accumulated, so the exchange of the
+decoder / slot-attention gradients runs under the rest of the backward (NVLink 5 / NVSwitch; NVLS
+in-switch reduction when NCCL selects it).  ``clip_grad_norm_`` and Adam then run identically on
+every rank (ocrs/base.py:60-74 semantics, loss is a per-rank batch mean so the average of the rank
+gradients is the global-batch gradient).
+"""
+from __future__ import annotations
+
+import os
+from typing import List
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
+    """Initialise torch.distributed from torchrun's environment; returns (rank, world, local_rank)."""
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend)
+    return rank, world, local
+
+
+def shard(batch: torch.Tensor, rank: int, world: int) -> torch.Tensor:
+    """Contiguous batch shard of this rank (mirrors run_sb3s.py's one-process-per-device layout)."""
+    per = (batch.shape[0] + world - 1) // world
+    return batch[rank * per:(rank + 1) * per]
+
+
+class GradientReducer:
+    """Bucketed, overlapped gradient averaging over the default process group."""
+
+    def __init__(self, params: List[torch.nn.Parameter], bucket_bytes: int = 4 << 20):
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.params = [p for p in params if p.requires_grad]
+        self.buckets: List[List[torch.nn.Parameter]] = []
+        cur, size = [], 0
+        for p in reversed(self.params):  # reverse construction order ~ order gradients become ready
+            cur.append(p)
+            size += p.numel() * p.element_size()
+            if size >= bucket_bytes:
+                self.buckets.append(cur)
+                cur, size = [], 0
+        if cur:
+            self.buckets.append(cur)
+        self._bucket_of = {id(p): i for i, b in enumerate(self.buckets) for p in b}
+        self._pending = [0] * len(self.buckets)
+        self._flat = [None] * len(self.buckets)
+        self._work = [None] * len(self.buckets)
+        self._stream = None
+        self._hooks = []
+        if self.world > 1:
+            for p in self.params:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+        self.reset()
+
+    def reset(self):
+        self._pending = [len(b) for b in self.buckets]
+        self._work = [None] * len(self.buckets)
+
+    def _on_grad(self, p):
+        i = self._bucket_of[id(p)]
+        self._pending[i] -= 1
+        if self._pending[i] == 0:
+            self._launch(i)
+
+    def _launch(self, i):
+        bucket = self.buckets[i]
+        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in bucket]
+        dev = grads[0].device
+        if dev.type == "cuda":
+            if self._stream is None:
+                self._stream = torch.cuda.Stream(device=dev)
+            self._stream.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(self._stream):
+                flat = torch.cat([g.reshape(-1) for g in grads])
+                self._work[i] = dist.all_reduce(flat, async_op=True)
+        else:
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            self._work[i] = dist.all_reduce(flat, async_op=True)
+        self._flat[i] = flat
+
+    def finish(self):
+        """Wait for every bucket, write the averaged gradients back (call after backward)."""
+        if self.world == 1:
+            return
+        for i, bucket in enumerate(self.buckets):
+            if self._work[i] is None:  # parameters that received no gradient this step
+                self._launch(i)
+        for i, bucket in enumerate(self.buckets):
+            self._work[i].wait()
+            flat = self._flat[i]
+            if flat.is_cuda:
+                torch.cuda.current_stream(flat.device).wait_stream(self._stream)
+            flat.div_(self.world)
+            off = 0
+            for p in bucket:
+                n = p.numel()
+                if p.grad is None:
+                    p.grad = torch.empty_like(p)
+                p.grad.copy_(flat[off:off + n].view_as(p))
+                off += n
+        self.reset()
+
+
+def make_data_parallel(model, bucket_bytes: int = 4 << 20):
+    """Turn an OCR wrapper (``ocrl_b200.SLATE``-style object with ``_module`` and ``update``) into
+    its data-parallel version in place: parameters are broadcast from rank 0 and ``update`` averages
+    gradients across ranks between backward and the gradient clip."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return model
+    for t in list(model._module.parameters()) + list(model._module.buffers()):
+        dist.broadcast(t.data, src=0)
+    reducer = GradientReducer(list(model._module.parameters()), bucket_bytes)
+    model._grad_reducer = reducer
+    model._after_backward = reducer.finish
+    return model
