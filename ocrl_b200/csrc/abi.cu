@@ -20,7 +20,7 @@ int token_stage_launch(const ocrl_sa_dims* d, const float* x, const float* pos, 
                        float* y_out, void* k_out, void* v_out, cudaStream_t stream);
 int sa_iter_fwd_launch(const ocrl_sa_dims* d, const void* k, const void* v, const float* slots0,
                        const ocrl_sa_weights* w, float* slots_out, float* attn_out, float* saved,
-                       cudaStream_t stream);
+                       void* workspace, cudaStream_t stream);
 int sa_iter_bwd_launch(const ocrl_sa_dims* d, const void* k, const void* v, const float* saved,
                        const ocrl_sa_weights* w, const float* d_slots, const float* d_attn, float* dk, float* dv,
                        float* d_slots0, const ocrl_sa_weight_grads* dw, void* ws, cudaStream_t stream);
@@ -48,6 +48,17 @@ int sa_iter_pick_cluster(const ocrl_sa_dims* d) {
     return cl;
   }
   return 1;
+}
+
+// Warps per CTA of the iteration kernel: 4-warp CTAs let two clusters share every SM (the slot
+// update of one image overlaps the token pass of another); needs <= ~112 KB of shared memory per CTA.
+int sa_iter_pick_warps(int D, int KP, int CL) {
+  if (const char* e = getenv("OCRL_SA_WARPS")) {
+    const int w = atoi(e);
+    if (w == 4 || w == 8) return w;
+  }
+  (void)D; (void)KP; (void)CL;
+  return 8;
 }
 
 static int check_dims(const ocrl_sa_dims* d) {
@@ -150,7 +161,6 @@ int ocrl_kv_proj_bwd(const ocrl_sa_dims* d, const float* x, const ocrl_token_wei
 int ocrl_sa_iter_fwd(const ocrl_sa_dims* d, const void* k, const void* v, const float* slots0,
                      const ocrl_sa_weights* w, float* slots_out, float* attn_vis_out, void* saved, void* workspace,
                      void* stream) {
-  (void)workspace;
   int rc = check_dims(d);
   if (rc) return rc;
   if ((rc = check_arch())) return rc;
@@ -164,7 +174,7 @@ int ocrl_sa_iter_fwd(const ocrl_sa_dims* d, const void* k, const void* v, const 
     return OCRL_E_ALIGN;
   }
   if (d->B == 0) return OCRL_OK;
-  return sa_iter_fwd_launch(d, k, v, slots0, w, slots_out, attn_vis_out, reinterpret_cast<float*>(saved),
+  return sa_iter_fwd_launch(d, k, v, slots0, w, slots_out, attn_vis_out, reinterpret_cast<float*>(saved), workspace,
                             (cudaStream_t)stream);
 }
 

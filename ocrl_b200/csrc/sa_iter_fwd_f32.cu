@@ -1,0 +1,5 @@
+// fp32 k/v instantiations of the fused iteration forward
+#include "sa_iter_fwd.cuh"
+namespace ocrl {
+template int sa_iter_fwd_dispatch<float>(const IterFwdArgs&, cudaStream_t);
+}

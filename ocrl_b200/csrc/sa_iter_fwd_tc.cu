@@ -1,0 +1,554 @@
+// Fused T-iteration slot-attention forward, tensor-core variant for bf16 k/v
+// (replaces ocrs/common/slot_attn.py:64-102; selected when kv_dtype = bf16, math_mode = TENSOR).
+//
+// Same decomposition as sa_iter_fwd.cuh (one cluster per image, slots resident in shared memory,
+// GRU/MLP distributed over the cluster through DSMEM) but the two token contractions run on the
+// tensor cores, flash-attention style with the roles of queries and keys swapped:
+//   logits^T [slots x 16 tokens] = q [16 x D] . k_tile^T      (A = q fragments, B = k via ldmatrix)
+//   softmax over the slot axis = across the 8 lane-rows of the accumulator fragment (3 shuffles)
+//   U^T [D x slots] += v_tile^T [D x 16 tokens] . w^T         (A = v via ldmatrix.trans, B = the softmax
+//                                                             accumulator re-used in registers as bf16)
+// k/v tiles of 16 tokens stream global -> shared with 16-byte cp.async into rows padded by 16 bytes
+// (conflict-free ldmatrix), a 3-stage ring private to each warp: no block barrier in the token loop.
+// Accumulation is fp32; the token-sum S uses the same bf16-rounded weights as the numerator.
+#include "slot_math.cuh"
+
+namespace ocrl {
+
+template <int D, int KP, int NPW_>
+struct TcCfg {
+  static constexpr int NPW = NPW_;              // warps that stream tokens (each owns a tile ring)
+  static constexpr int NW = 8;                  // all warps take part in the slot update
+  static constexpr int NT = NW * 32;
+  static constexpr int GT = 16;                 // tokens per warp group
+  static constexpr int PITCH = D * 2 + 16;      // bytes per padded bf16 row
+  static constexpr int TILE_BYTES = GT * PITCH; // k or v of one group
+  static constexpr int STAGE_BYTES = 2 * TILE_BYTES;
+  static constexpr int STAGES = (KP > 8 && D >= 192) ? 2 : 3;
+  static constexpr int NKS = D / 16;            // k-steps of the logits / m-tiles of U^T
+  static constexpr int NSL = KP / 8;            // slot n-tiles (1 or 2)
+  static constexpr int RB = (KP <= 8) ? 4 : 2;  // rows per batch in the slot-update matvecs
+  static constexpr int CHUNKS_PER_ROW = D * 2 / 16;
+  static_assert(KP == 8 || KP == 16, "slots are padded to 8 or 16");
+  static_assert(D % 64 == 0, "D must be a multiple of 64");
+};
+
+template <int D, int KP, int NWT>
+__global__ void __launch_bounds__(TcCfg<D, KP, NWT>::NT, 1) sa_iter_fwd_tc_kernel(const IterFwdArgs a) {
+  using Cfg = TcCfg<D, KP, NWT>;
+  constexpr int NW = Cfg::NW, NPW = Cfg::NPW, NT = Cfg::NT, GT = Cfg::GT, PITCH = Cfg::PITCH, STAGES = Cfg::STAGES;
+  constexpr int NKS = Cfg::NKS, NSL = Cfg::NSL, RB = Cfg::RB, NC = D / 64;
+  typedef __nv_bfloat16 bf16;
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = a.CL;
+  const int rank = (int)cluster.block_rank();
+  const int img = blockIdx.x / CL;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g8 = lane >> 2, t4 = lane & 3;
+  const int K = a.K, H = a.H, N = a.N;
+  const int DS = D / CL, HS = H / CL;
+  const int LMAX = D > H ? D : H;
+
+  // ---- shared memory carve-up (must match tc_smem_bytes) ----------------------------------------
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* sp = smem_raw;
+  const size_t ring_bytes = (size_t)NPW * STAGES * Cfg::STAGE_BYTES;
+  const size_t ured_bytes = (size_t)NPW * KP * D * sizeof(float);
+  unsigned char* ring = sp;                    // k/v tiles in the token pass, staged weights in the slot update
+  float* wstage = reinterpret_cast<float*>(sp);
+  sp += ring_bytes;
+  float* ured = reinterpret_cast<float*>(sp);  // per-warp partial U; later the raw dot products ("gates")
+  {
+    const size_t gates_bytes = sizeof(float) * 6 * (size_t)KP * DS;
+    sp += (ured_bytes > gates_bytes ? ured_bytes : gates_bytes);
+  }
+  unsigned char* qb = sp; sp += 16 * PITCH;    // q as bf16, 16 padded rows (rows >= K are zero)
+  auto take = [&](size_t n) { float* p = reinterpret_cast<float*>(sp); sp += sizeof(float) * n; return p; };
+  float* s_prev = take(KP * D);
+  float* q_s = take(KP * D);
+  float* rs_buf = take(KP * D);
+  float* upd_full = take(KP * D);
+  float* h_full = take(KP * D);
+  float* hid_full = take(KP * H);
+  float* lnb = rs_buf;  // LayerNorm output; live only while rs_buf is not (see the barriers around them)
+  float* gates = ured;
+  float* rs_S = take(16 * KP);
+  float* sred = take(NPW * KP);
+  float* lnp = take(4 * D);            // norm_slots w,b  norm_mlp w,b
+  float* bsl = take(6 * DS + HS + DS); // bias slices: b_ih[3][DS], b_hh[3][DS], b1[HS], b2[DS]
+  sp = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(sp) + 7) & ~uintptr_t(7));
+  uint64_t* wbar = reinterpret_cast<uint64_t*>(sp);  // weights landed: 0 = GRU, 1 = W1, 2 = W2, 3 = Wq
+  // the CTA's weight slices fit in the idle ring -> stream them with bulk copies under the exchanges
+  const size_t gru_floats = (size_t)DS * D, w1_floats = (size_t)HS * D, w2_floats = (size_t)DS * H;
+  const bool w_smem = sizeof(float) * (6 * gru_floats + w1_floats + w2_floats) <= ring_bytes;
+  float* ws_gru = wstage;                 // [ih_r, ih_z, ih_n, hh_r, hh_z, hh_n][DS][D]
+  float* ws_w1 = ws_gru + 6 * gru_floats; // [HS][D]
+  float* ws_w2 = ws_w1 + w1_floats;       // [DS][H]
+  float* ws_wq = wstage;                  // [DS][D], re-uses the first GRU block once the GRU is done
+
+  const bf16* kimg = reinterpret_cast<const bf16*>(a.k) + (size_t)img * N * D;
+  const bf16* vimg = reinterpret_cast<const bf16*>(a.v) + (size_t)img * N * D;
+
+  const int groups_total = (N + GT - 1) / GT;
+  const int gpc = (groups_total + CL - 1) / CL;
+  const int g_begin = rank * gpc;
+  const int g_end = min(groups_total, g_begin + gpc);
+  const int my_groups = max(0, g_end - g_begin);
+  const int warp_groups = (warp < NPW && my_groups > warp) ? (my_groups - warp + NPW - 1) / NPW : 0;
+
+  for (int e = tid; e < KP * D; e += NT) {
+    const int j = e / D;
+    s_prev[e] = (j < K) ? a.slots0[(size_t)img * K * D + e] : 0.f;
+    upd_full[e] = 0.f; h_full[e] = 0.f; q_s[e] = 0.f;
+  }
+  for (int e = tid; e < KP * H; e += NT) hid_full[e] = 0.f;
+  for (int e = tid; e < KP * D; e += NT) lnb[e] = 0.f;
+  for (int e = tid; e < 16 * PITCH / 4; e += NT) reinterpret_cast<uint32_t*>(qb)[e] = 0u;
+  for (int e = tid; e < D; e += NT) {
+    lnp[e] = __ldg(a.w.ln_slots_w + e); lnp[D + e] = __ldg(a.w.ln_slots_b + e);
+    lnp[2 * D + e] = __ldg(a.w.ln_mlp_w + e); lnp[3 * D + e] = __ldg(a.w.ln_mlp_b + e);
+  }
+  for (int e = tid; e < 3 * DS; e += NT) {
+    const int g = e / DS, o = e % DS;
+    bsl[e] = __ldg(a.w.b_ih + g * D + rank * DS + o);
+    bsl[3 * DS + e] = __ldg(a.w.b_hh + g * D + rank * DS + o);
+  }
+  for (int e = tid; e < HS; e += NT) bsl[6 * DS + e] = __ldg(a.w.b1 + rank * HS + e);
+  for (int e = tid; e < DS; e += NT) bsl[6 * DS + HS + e] = __ldg(a.w.b2 + rank * DS + e);
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&wbar[i], 1);
+  }
+  mbar_fence_init();
+  __syncthreads();
+  if (w_smem && tid == 0) {  // query weights for the first projection
+    fence_proxy_async();
+    mbar_expect_tx(&wbar[3], (uint32_t)(sizeof(float) * gru_floats));
+    bulk_g2s(ws_wq, a.w.wq + (size_t)rank * DS * D, (uint32_t)(sizeof(float) * gru_floats), &wbar[3]);
+  }
+  cluster.sync();
+
+  int trace_i = 0;
+  auto TRACE = [&]() {
+    if (a.trace != nullptr && blockIdx.x == 0 && tid == 0) a.trace[trace_i] = clock64();
+    ++trace_i;
+  };
+  TRACE();
+  const SavedLayout SL(K, D, H);
+  auto saved_at = [&](int t) { return a.saved + ((size_t)img * a.T + t) * SL.stride(); };
+
+  auto compute_q = [&](int tq) {  // tq-th use of the staged query weights
+    ln_rows_fast<D>(s_prev, lnp, lnp + D, lnb, K, a.ln_eps, warp, lane, NW);
+    __syncthreads();
+    DotDesc d;
+    d.vec0 = d.vec1 = lnb; d.out0 = gates;
+    d.njobs = 1; d.split = 1; d.split_mod = 1; d.row_stride = 0; d.nrows = DS;
+    d.out_stride = 0; d.ldo = DS;
+    if (w_smem) {
+      mbar_wait(&wbar[3], (uint32_t)(tq & 1));
+      d.W0 = d.W1 = ws_wq; d.row_base = 0;
+      rows_dot_desc<KP, RB, NC, 2, false>(d, warp, lane, NW);
+    } else {
+      d.W0 = d.W1 = a.w.wq; d.row_base = rank * DS;
+      rows_dot_desc<KP, RB, NC, 2>(d, warp, lane, NW);
+    }
+    __syncthreads();
+    for (int e = tid; e < K * DS; e += NT) {
+      const int j = e / DS, o = e % DS;
+      const float val = gates[j * DS + o];
+      for (int r = 0; r < CL; ++r) cluster.map_shared_rank(q_s, r)[j * D + rank * DS + o] = val;
+      if (a.saved) saved_at(tq)[SL.off_q() + j * D + rank * DS + o] = val;
+    }
+    cluster.sync();
+    // bf16 copy of the complete q for the tensor-core pass (rows >= K stay zero)
+    for (int e = tid; e < K * (D / 2); e += NT) {
+      const int j = e / (D / 2), c2 = e % (D / 2);
+      const float2 x = *reinterpret_cast<const float2*>(q_s + j * D + 2 * c2);
+      *reinterpret_cast<uint32_t*>(qb + j * PITCH + 4 * c2) = pack_bf16x2(x.x, x.y);
+    }
+    __syncthreads();
+  };
+  compute_q(0);
+
+  unsigned char* my_ring = ring + (size_t)warp * STAGES * Cfg::STAGE_BYTES;
+
+  // all 32 lanes copy one 16-token group of k and v into ring stage `st` (zero-fill past N)
+  auto issue = [&](int local_group, int st) {
+    const int tok0 = (g_begin + warp + local_group * NPW) * GT;
+    unsigned char* kd = my_ring + (size_t)st * Cfg::STAGE_BYTES;
+    unsigned char* vd = kd + Cfg::TILE_BYTES;
+#pragma unroll
+    for (int i = 0; i < GT * Cfg::CHUNKS_PER_ROW / 32; ++i) {
+      const int c = lane + 32 * i;
+      const int row = c / Cfg::CHUNKS_PER_ROW, col = c % Cfg::CHUNKS_PER_ROW;
+      const bool ok = (tok0 + row) < N;
+      const size_t src = (size_t)(ok ? tok0 + row : 0) * D + col * 8;
+      cp_async16(kd + row * PITCH + col * 16, kimg + src, ok ? 16 : 0);
+      cp_async16(vd + row * PITCH + col * 16, vimg + src, ok ? 16 : 0);
+    }
+  };
+
+  for (int t = 0; t < a.T; ++t) {
+    const bool last = (t == a.T - 1);
+    if (a.saved) {
+      float* sv = saved_at(t);
+      for (int e = tid; e < K * DS; e += NT) {
+        const int j = e / DS, o = e % DS;
+        sv[SL.off_h() + j * D + rank * DS + o] = s_prev[j * D + rank * DS + o];
+      }
+    }
+
+    TRACE();  // [1 + 9t] start of token pass
+    // ------------------------------ token pass on the tensor cores ---------------------------------
+    float UT[NSL][NKS][4];  // U^T fragments: rows d = 16*mt + g8 (+8), cols slots 8*sl + 2*t4 + {0,1}
+#pragma unroll
+    for (int sl = 0; sl < NSL; ++sl)
+#pragma unroll
+      for (int mt = 0; mt < NKS; ++mt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) UT[sl][mt][i] = 0.f;
+    float Sl[NSL] = {};  // sum of the (bf16-rounded) weights of slot 8*sl + g8 seen by this lane
+    {
+      uint32_t qa[NKS][4];  // A fragments of q (16 slot rows x D)
+      {
+        const int row = (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int colb = (lane >> 4) * 16;
+#pragma unroll
+        for (int ks = 0; ks < NKS; ++ks) ldmatrix_x4(qa[ks], qb + row * PITCH + ks * 32 + colb);
+      }
+      // per-lane byte offset inside a k / v tile for the x4 loads (same for both operands)
+      const int frag_off = ((lane & 7) + (lane >> 4) * 8) * PITCH + ((lane >> 3) & 1) * 16;
+
+      for (int p = 0; p < STAGES - 1; ++p) {
+        if (p < warp_groups) issue(p, p % STAGES);
+        cp_async_commit();
+      }
+      for (int lg = 0; lg < warp_groups; ++lg) {
+        {
+          const int nxt = lg + STAGES - 1;
+          if (nxt < warp_groups) issue(nxt, nxt % STAGES);
+          cp_async_commit();
+        }
+        cp_async_wait<STAGES - 1>();
+        __syncwarp();
+        const unsigned char* kb = my_ring + (size_t)(lg % STAGES) * Cfg::STAGE_BYTES;
+        const unsigned char* vb = kb + Cfg::TILE_BYTES;
+        const int tok0 = (g_begin + warp + lg * NPW) * GT;
+
+        // logits^T: two 8-token blocks, two interleaved accumulator chains each for ILP
+        float lgA[2][4] = {}, lgB[2][4] = {};
+#pragma unroll
+        for (int ks = 0; ks < NKS; ++ks) {
+          uint32_t kf[4];
+          ldmatrix_x4(kf, kb + frag_off + ks * 32);
+          if (ks & 1) {
+            mma_bf16_16816(lgB[0], qa[ks], kf[0], kf[1]);
+            mma_bf16_16816(lgB[1], qa[ks], kf[2], kf[3]);
+          } else {
+            mma_bf16_16816(lgA[0], qa[ks], kf[0], kf[1]);
+            mma_bf16_16816(lgA[1], qa[ks], kf[2], kf[3]);
+          }
+        }
+        // K-way softmax over the slot axis (rows of the fragment): lanes with equal t4 hold a column
+        uint32_t wb[NSL][2];  // B fragments of w^T for the U^T product: [slot tile][token half]
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+          float x[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) x[i] = lgA[nb][i] + lgB[nb][i];
+          const bool lo_ok = g8 < K, hi_ok = (NSL > 1) && (g8 + 8 < K);
+          float m0 = lo_ok ? x[0] : -INFINITY, m1 = lo_ok ? x[1] : -INFINITY;
+          if (hi_ok) { m0 = fmaxf(m0, x[2]); m1 = fmaxf(m1, x[3]); }
+#pragma unroll
+          for (int o = 4; o < 32; o <<= 1) {
+            m0 = fmaxf(m0, __shfl_xor_sync(FULL, m0, o));
+            m1 = fmaxf(m1, __shfl_xor_sync(FULL, m1, o));
+          }
+          float e[4];
+          e[0] = lo_ok ? __expf(x[0] - m0) : 0.f;
+          e[1] = lo_ok ? __expf(x[1] - m1) : 0.f;
+          e[2] = hi_ok ? __expf(x[2] - m0) : 0.f;
+          e[3] = hi_ok ? __expf(x[3] - m1) : 0.f;
+          float s0 = e[0] + e[2], s1 = e[1] + e[3];
+#pragma unroll
+          for (int o = 4; o < 32; o <<= 1) {
+            s0 += __shfl_xor_sync(FULL, s0, o);
+            s1 += __shfl_xor_sync(FULL, s1, o);
+          }
+          const float i0 = 1.f / s0, i1 = 1.f / s1;
+          const int tk0 = tok0 + nb * 8 + 2 * t4;  // tokens of this lane's two columns
+          const bool v0 = tk0 < N, v1 = (tk0 + 1) < N;
+          float av[4] = {e[0] * i0, e[1] * i1, e[2] * i0, e[3] * i1};
+          if (last && a.attn_out) {
+            float* ao = a.attn_out + ((size_t)img * N + tk0) * K;
+            if (lo_ok) {
+              if (v0) ao[g8] = av[0];
+              if (v1) ao[K + g8] = av[1];
+            }
+            if (hi_ok) {
+              if (v0) ao[g8 + 8] = av[2];
+              if (v1) ao[K + g8 + 8] = av[3];
+            }
+          }
+          // weights a + eps, rounded to bf16 once and used for both the numerator and the token sum
+          const __nv_bfloat162 wlo = __floats2bfloat162_rn((lo_ok && v0) ? av[0] + a.eps : 0.f,
+                                                          (lo_ok && v1) ? av[1] + a.eps : 0.f);
+          wb[0][nb] = *reinterpret_cast<const uint32_t*>(&wlo);
+          Sl[0] += __low2float(wlo) + __high2float(wlo);
+          if constexpr (NSL > 1) {
+            const __nv_bfloat162 whi = __floats2bfloat162_rn((hi_ok && v0) ? av[2] + a.eps : 0.f,
+                                                            (hi_ok && v1) ? av[3] + a.eps : 0.f);
+            wb[1][nb] = *reinterpret_cast<const uint32_t*>(&whi);
+            Sl[1] += __low2float(whi) + __high2float(whi);
+          }
+        }
+        // U^T += v_tile^T . w^T
+#pragma unroll
+        for (int mt = 0; mt < NKS; ++mt) {
+          uint32_t vf[4];
+          ldmatrix_x4_trans(vf, vb + frag_off + mt * 32);
+          // ldmatrix order: [tok 0-7, d 0-7], [tok 0-7, d 8-15], [tok 8-15, d 0-7], [tok 8-15, d 8-15]
+          // mma A order:    a0 = (d 0-7, tok 0-7), a1 = (d 8-15, tok 0-7), a2 = (d 0-7, tok 8-15), a3 = (d 8-15, tok 8-15)
+          const uint32_t af[4] = {vf[0], vf[1], vf[2], vf[3]};
+#pragma unroll
+          for (int sl = 0; sl < NSL; ++sl) mma_bf16_16816(UT[sl][mt], af, wb[sl][0], wb[sl][1]);
+        }
+        __syncwarp();  // every lane is done with this stage before it is refilled
+      }
+      cp_async_wait<0>();
+    }
+
+    // ------------------------------ CTA reduction of the partial sums -------------------------------
+    TRACE();  // token pass done (this warp)
+    TRACE();
+    if (warp < NPW) {
+#pragma unroll
+    for (int sl = 0; sl < NSL; ++sl)
+#pragma unroll
+      for (int mt = 0; mt < NKS; ++mt) {
+        const int s0 = sl * 8 + 2 * t4, d0 = mt * 16 + g8;
+        float* u = ured + (size_t)warp * KP * D;
+        u[s0 * D + d0] = UT[sl][mt][0];
+        u[(s0 + 1) * D + d0] = UT[sl][mt][1];
+        u[s0 * D + d0 + 8] = UT[sl][mt][2];
+        u[(s0 + 1) * D + d0 + 8] = UT[sl][mt][3];
+      }
+#pragma unroll
+    for (int sl = 0; sl < NSL; ++sl) {
+      float s = Sl[sl];
+      s += __shfl_xor_sync(FULL, s, 1);
+      s += __shfl_xor_sync(FULL, s, 2);
+      if (t4 == 0) sred[warp * KP + sl * 8 + g8] = s;
+    }
+    }
+    __syncthreads();  // partial sums visible; every warp is done with the ring
+    if (w_smem && tid == 0) {  // stream this CTA's GRU / MLP weight slices into the idle ring
+      fence_proxy_async();
+      const uint32_t gb = (uint32_t)(sizeof(float) * gru_floats);
+      mbar_expect_tx(&wbar[0], 6 * gb);
+      for (int gsel = 0; gsel < 3; ++gsel) {
+        bulk_g2s(ws_gru + gsel * gru_floats, a.w.w_ih + ((size_t)gsel * D + rank * DS) * D, gb, &wbar[0]);
+        bulk_g2s(ws_gru + (3 + gsel) * gru_floats, a.w.w_hh + ((size_t)gsel * D + rank * DS) * D, gb, &wbar[0]);
+      }
+      mbar_expect_tx(&wbar[1], (uint32_t)(sizeof(float) * w1_floats));
+      bulk_g2s(ws_w1, a.w.w1 + (size_t)rank * HS * D, (uint32_t)(sizeof(float) * w1_floats), &wbar[1]);
+      mbar_expect_tx(&wbar[2], (uint32_t)(sizeof(float) * w2_floats));
+      bulk_g2s(ws_w2, a.w.w2 + (size_t)rank * DS * H, (uint32_t)(sizeof(float) * w2_floats), &wbar[2]);
+    }
+    for (int e = tid; e < K * D; e += NT) {
+      const int j = e / D, d = e % D;
+      float s = 0.f;
+#pragma unroll
+      for (int w8 = 0; w8 < NPW; ++w8) s += ured[((size_t)w8 * KP + j) * D + d];
+      const int r = d / DS, o = d % DS;
+      cluster.map_shared_rank(rs_buf, r)[(rank * KP + j) * DS + o] = s;
+    }
+    if (tid < K) {
+      float s = 0.f;
+      for (int w8 = 0; w8 < NPW; ++w8) s += sred[w8 * KP + tid];
+      for (int r = 0; r < CL; ++r) cluster.map_shared_rank(rs_S, r)[rank * KP + tid] = s;
+    }
+    TRACE();
+    cluster.sync();  // #1
+    TRACE();
+    for (int e = tid; e < K * DS; e += NT) {
+      const int j = e / DS, o = e % DS;
+      float tot = 0.f, st = 0.f;
+      for (int r = 0; r < CL; ++r) {
+        tot += rs_buf[(r * KP + j) * DS + o];
+        st += rs_S[r * KP + j];
+      }
+      const float upd = tot / st;
+      for (int r = 0; r < CL; ++r) cluster.map_shared_rank(upd_full, r)[j * D + rank * DS + o] = upd;
+      if (a.saved) {
+        float* sv = saved_at(t);
+        sv[SL.off_u() + j * D + rank * DS + o] = upd;
+        if (rank == 0 && o == 0) sv[SL.off_s() + j] = st;
+      }
+    }
+    cluster.sync();  // #2
+    TRACE();
+
+    // ------------------------------ GRUCell (this CTA's DS features) ---------------------------------
+    {
+      DotDesc d;
+      d.vec0 = upd_full; d.vec1 = s_prev; d.out0 = gates;
+      d.njobs = 6; d.split = 3; d.split_mod = 3; d.nrows = DS; d.out_stride = KP * DS; d.ldo = DS;
+      if (w_smem) {
+        mbar_wait(&wbar[0], (uint32_t)(t & 1));
+        d.W0 = ws_gru; d.W1 = ws_gru + 3 * gru_floats; d.row_base = 0; d.row_stride = DS;
+        rows_dot_desc<KP, RB, NC, 2, false>(d, warp, lane, NW);
+      } else {
+        d.W0 = a.w.w_ih; d.W1 = a.w.w_hh; d.row_base = rank * DS; d.row_stride = D;
+        rows_dot_desc<KP, RB, NC, 2>(d, warp, lane, NW);
+      }
+    }
+    __syncthreads();
+    if (w_smem && !last && tid == 0) {  // the first GRU block is free: fetch the query weights behind it
+      fence_proxy_async();
+      mbar_expect_tx(&wbar[3], (uint32_t)(sizeof(float) * gru_floats));
+      bulk_g2s(ws_wq, a.w.wq + (size_t)rank * DS * D, (uint32_t)(sizeof(float) * gru_floats), &wbar[3]);
+    }
+    for (int e = tid; e < K * DS; e += NT) {
+      const int j = e / DS, o = e % DS;
+      const int f = rank * DS + o;
+      const float gir = gates[(0 * KP + j) * DS + o] + bsl[o];
+      const float giz = gates[(1 * KP + j) * DS + o] + bsl[DS + o];
+      const float gin = gates[(2 * KP + j) * DS + o] + bsl[2 * DS + o];
+      const float ghr = gates[(3 * KP + j) * DS + o] + bsl[3 * DS + o];
+      const float ghz = gates[(4 * KP + j) * DS + o] + bsl[4 * DS + o];
+      const float ghn = gates[(5 * KP + j) * DS + o] + bsl[5 * DS + o];
+      const float rg = sigmoidf_(gir + ghr);
+      const float zg = sigmoidf_(giz + ghz);
+      const float ng = tanhf(gin + rg * ghn);
+      const float hn = (1.f - zg) * ng + zg * s_prev[j * D + f];
+      for (int r = 0; r < CL; ++r) cluster.map_shared_rank(h_full, r)[j * D + f] = hn;
+      if (a.saved) {
+        float* sv = saved_at(t);
+        sv[SL.off_r() + j * D + f] = rg;
+        sv[SL.off_z() + j * D + f] = zg;
+        sv[SL.off_n() + j * D + f] = ng;
+        sv[SL.off_ghn() + j * D + f] = ghn;
+        sv[SL.off_hp() + j * D + f] = hn;
+      }
+    }
+    cluster.sync();  // #3
+    TRACE();
+
+    // ------------------------------ residual MLP ------------------------------------------------------
+    ln_rows_fast<D>(h_full, lnp + 2 * D, lnp + 3 * D, lnb, K, a.ln_eps, warp, lane, NW);
+    __syncthreads();
+    {
+      DotDesc d;
+      d.vec0 = d.vec1 = lnb; d.out0 = gates;
+      d.njobs = 1; d.split = 1; d.split_mod = 1; d.row_stride = 0; d.nrows = HS; d.out_stride = 0; d.ldo = HS;
+      if (w_smem) {
+        mbar_wait(&wbar[1], (uint32_t)(t & 1));
+        d.W0 = d.W1 = ws_w1; d.row_base = 0;
+        rows_dot_desc<KP, RB, NC, 2, false>(d, warp, lane, NW);
+      } else {
+        d.W0 = d.W1 = a.w.w1; d.row_base = rank * HS;
+        rows_dot_desc<KP, RB, NC, 2>(d, warp, lane, NW);
+      }
+    }
+    __syncthreads();
+    for (int e = tid; e < K * HS; e += NT) {
+      const int j = e / HS, o = e % HS;
+      const float pre = gates[j * HS + o] + bsl[6 * DS + o];
+      const float hv = fmaxf(pre, 0.f);
+      for (int r = 0; r < CL; ++r) cluster.map_shared_rank(hid_full, r)[j * H + rank * HS + o] = hv;
+      if (a.saved) saved_at(t)[SL.off_pre() + j * H + rank * HS + o] = pre;
+    }
+    cluster.sync();  // #4
+    TRACE();
+    {
+      DotDesc d;
+      d.vec0 = d.vec1 = hid_full; d.out0 = gates;
+      d.njobs = 1; d.split = 1; d.split_mod = 1; d.row_stride = 0; d.nrows = DS; d.out_stride = 0; d.ldo = DS;
+      if (w_smem) {
+        mbar_wait(&wbar[2], (uint32_t)(t & 1));
+        d.W0 = d.W1 = ws_w2; d.row_base = 0;
+        rows_dot_desc_len<KP, RB, 2, false>(d, H, warp, lane, NW);
+      } else {
+        d.W0 = d.W1 = a.w.w2; d.row_base = rank * DS;
+        rows_dot_desc_len<KP, RB, 2>(d, H, warp, lane, NW);
+      }
+    }
+    __syncthreads();
+    for (int e = tid; e < K * DS; e += NT) {
+      const int j = e / DS, o = e % DS;
+      const int f = rank * DS + o;
+      const float sn = h_full[j * D + f] + gates[j * DS + o] + bsl[6 * DS + HS + o];
+      for (int r = 0; r < CL; ++r) cluster.map_shared_rank(s_prev, r)[j * D + f] = sn;
+      if (last) a.slots_out[((size_t)img * K + j) * D + f] = sn;
+    }
+    cluster.sync();  // #5
+    TRACE();
+    if (!last) compute_q(t + 1);  // #6
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+template <int D, int KP, int NWT>
+static size_t tc_smem_bytes(int H, int CL) {
+  using Cfg = TcCfg<D, KP, NWT>;
+  const size_t ring_bytes = (size_t)Cfg::NPW * Cfg::STAGES * Cfg::STAGE_BYTES;
+  const size_t ured_bytes = (size_t)Cfg::NPW * KP * D * sizeof(float);
+  const int LMAX = D > H ? D : H;
+  const size_t gates_bytes = sizeof(float) * 6 * (size_t)KP * (D / CL);
+  size_t b = ring_bytes + (ured_bytes > gates_bytes ? ured_bytes : gates_bytes);
+  b += 16 * Cfg::PITCH;
+  b += sizeof(float) * ((size_t)KP * D * 5 + (size_t)KP * H + 16 * KP + Cfg::NPW * KP + 4 * D +
+                        6 * (D / CL) + H / CL + D / CL);
+  b += 8 + 4 * sizeof(uint64_t);
+  return b + 128;
+}
+
+template <int D, int KP, int NWT>
+static int launch_tc(const IterFwdArgs& a, cudaStream_t stream) {
+  using Cfg = TcCfg<D, KP, NWT>;
+  auto kern = sa_iter_fwd_tc_kernel<D, KP, NWT>;
+  const size_t smem = tc_smem_bytes<D, KP, NWT>(a.H, a.CL);
+  if (smem > 227 * 1024) {
+    set_error("sa_iter_fwd(tensor): shared memory %zu B exceeds 227 KB (D=%d K=%d H=%d)", smem, D, a.K, a.H);
+    return OCRL_E_SHAPE;
+  }
+  OCRL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (a.CL > 8) OCRL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(a.B * a.CL));
+  cfg.blockDim = dim3(Cfg::NT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)a.CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  OCRL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+  return OCRL_OK;
+}
+
+template <int D>
+static int tc_dispatch_k(const IterFwdArgs& a, cudaStream_t s) {
+  constexpr int NW = (D >= 192) ? 4 : 8;  // token-pass warps: ring = NPW * stages * 2 * 16 * (2D+16) bytes
+  if (a.K <= 8) return launch_tc<D, 8, NW>(a, s);
+  return launch_tc<D, 16, NW>(a, s);
+}
+
+int sa_iter_fwd_tc_dispatch(const IterFwdArgs& a, cudaStream_t s) {
+  switch (a.D) {
+    case 64: return tc_dispatch_k<64>(a, s);
+    case 128: return tc_dispatch_k<128>(a, s);
+    case 192: return tc_dispatch_k<192>(a, s);
+    default:
+      set_error("sa_iter_fwd(tensor): slot_size=%d not supported (64, 128, 192)", a.D);
+      return OCRL_E_SHAPE;
+  }
+}
+
+}  // namespace ocrl

@@ -8,6 +8,7 @@ token LayerNorm+MLP of ``SlotAttentionEncoder.forward`` (slot_attn.py:151).
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -45,6 +46,13 @@ class _timed:
             e1.record()
             KERNEL_EVENTS.append((self.name, self.e0, e1))
         return False
+
+
+def _math_mode(dt_code: int) -> int:
+    """bf16 k/v run the token contractions on the tensor cores unless OCRL_SA_MATH=fp32 forces FFMA."""
+    if dt_code == abi.DT_BF16 and os.environ.get("OCRL_SA_MATH", "tensor") != "fp32":
+        return abi.MATH_TENSOR
+    return abi.MATH_FP32
 
 
 def _f32c(t: Tensor) -> Tensor:
@@ -105,7 +113,8 @@ def kv_project(x: Tensor, p: Dict[str, Tensor], *, kv: str = "fp32", enc: Option
 
 
 def iterate(k: Tensor, v: Tensor, slots0: Tensor, p: Dict[str, Tensor], num_iterations: int, *,
-            epsilon: float = 1e-8, ln_eps: float = 1e-5, want_attn: bool = True, save: bool = False):
+            epsilon: float = 1e-8, ln_eps: float = 1e-5, want_attn: bool = True, save: bool = False,
+            _workspace: Optional[Tensor] = None):
     """The fused T-iteration loop.  k, v: [B,N,D] fp32 or bf16; slots0 [B,K,D].
     Returns (slots, attn_vis or None, saved or None)."""
     _require_cuda(k, "iterate")
@@ -113,7 +122,8 @@ def iterate(k: Tensor, v: Tensor, slots0: Tensor, p: Dict[str, Tensor], num_iter
     K = slots0.shape[1]
     H = p["mlp.0.weight"].shape[0]
     dt_code = abi.DT_BF16 if k.dtype == torch.bfloat16 else abi.DT_F32
-    dims = abi.make_dims(B, N, 64, D, H, K, num_iterations, eps=epsilon, ln_eps=ln_eps, kv_dtype=dt_code)
+    dims = abi.make_dims(B, N, 64, D, H, K, num_iterations, eps=epsilon, ln_eps=ln_eps, kv_dtype=dt_code,
+                         math_mode=_math_mode(dt_code))
     pw = {n: _f32c(p[n]) for n in SA_PARAM_ORDER if n in p}
     slots0 = _f32c(slots0)
     slots = torch.empty(B, K, D, device=k.device, dtype=torch.float32)
@@ -125,8 +135,8 @@ def iterate(k: Tensor, v: Tensor, slots0: Tensor, p: Dict[str, Tensor], num_iter
     w = _sa_weights(pw)
     with _timed("sa_iter_fwd"):
         abi.check(abi.lib().ocrl_sa_iter_fwd(ctypes.byref(dims), abi.ptr(k), abi.ptr(v), abi.ptr(slots0),
-                                             ctypes.byref(w), abi.ptr(slots), abi.ptr(attn), abi.ptr(saved), None,
-                                             abi.stream_ptr()), "ocrl_sa_iter_fwd")
+                                             ctypes.byref(w), abi.ptr(slots), abi.ptr(attn), abi.ptr(saved),
+                                             abi.ptr(_workspace), abi.stream_ptr()), "ocrl_sa_iter_fwd")
     return slots, attn, saved
 
 
