@@ -108,10 +108,13 @@ int ocrl_sa_query_workspace(const ocrl_sa_dims* dims, size_t* fwd_ws, size_t* bw
  *            [B,C_in,H*W] (NCHW) to which pos_table [C_in,H*W] is added while it is transposed
  *            to token-major (ocrs/common/utils.py:28-33, slate_module.py:132-133).
  *   y_out    [B,N,C_in] fp32 output of the token MLP (NULL if not needed / MLP skipped)
- *   k_out,v_out [B,N,D] in dims->kv_dtype; k already scaled by D^-1/2 (slot_attn.py:61). */
+ *   k_out,v_out [B,N,D] in dims->kv_dtype; k already scaled by D^-1/2 (slot_attn.py:61).
+ *   workspace: ocrl_kv_proj_fwd_workspace(dims) bytes of scratch (bf16 weight copies for the tensor-core
+ *            path); may be NULL, which selects the fp32 FFMA kernel. */
+size_t ocrl_kv_proj_fwd_workspace(const ocrl_sa_dims* dims);
 int ocrl_kv_proj_fwd(const ocrl_sa_dims* dims, const float* x, const float* pos_table,
                      const ocrl_token_weights* w, float* y_out, void* k_out, void* v_out,
-                     void* stream);
+                     void* workspace, void* stream);
 
 /* Token stage, backward of norm_inputs + project_k/v (autograd of slot_attn.py:54-61).
  *   x [B,N,C_in] is the input of norm_inputs; dk,dv [B,N,D] fp32.

@@ -19,7 +19,7 @@ MATH_FP32, MATH_TENSOR = 0, 1
 
 EXPORTS = [
     "ocrl_version", "ocrl_built_arch", "ocrl_last_error", "ocrl_sa_query_workspace",
-    "ocrl_kv_proj_fwd", "ocrl_kv_proj_bwd_workspace", "ocrl_kv_proj_bwd",
+    "ocrl_kv_proj_fwd_workspace", "ocrl_kv_proj_fwd", "ocrl_kv_proj_bwd_workspace", "ocrl_kv_proj_bwd",
     "ocrl_sa_iter_fwd", "ocrl_sa_iter_bwd",
 ]
 
@@ -63,7 +63,9 @@ def lib() -> ctypes.CDLL:
         L.ocrl_last_error.restype = c_char_p
         L.ocrl_sa_query_workspace.argtypes = [POINTER(SaDims), POINTER(c_size_t), POINTER(c_size_t), POINTER(c_size_t)]
         L.ocrl_kv_proj_fwd.argtypes = [POINTER(SaDims), c_void_p, c_void_p, POINTER(TokenWeights), c_void_p,
-                                       c_void_p, c_void_p, c_void_p]
+                                       c_void_p, c_void_p, c_void_p, c_void_p]
+        L.ocrl_kv_proj_fwd_workspace.argtypes = [POINTER(SaDims)]
+        L.ocrl_kv_proj_fwd_workspace.restype = c_size_t
         L.ocrl_kv_proj_bwd_workspace.argtypes = [POINTER(SaDims)]
         L.ocrl_kv_proj_bwd_workspace.restype = c_size_t
         L.ocrl_kv_proj_bwd.argtypes = [POINTER(SaDims), c_void_p, POINTER(TokenWeights), c_void_p, c_void_p,

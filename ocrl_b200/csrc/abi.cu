@@ -29,6 +29,9 @@ int kv_proj_bwd_launch(const ocrl_sa_dims* d, const float* x, const ocrl_token_w
                        const float* dv, float* dx, float* d_ln_w, float* d_ln_b, float* dwk, float* dwv, void* ws,
                        cudaStream_t stream);
 size_t kv_proj_bwd_workspace(const ocrl_sa_dims* d);
+size_t kv_proj_tc_workspace(const ocrl_sa_dims* d);
+int kv_proj_tc_launch(const ocrl_sa_dims* d, const float* x, const float* pos, const ocrl_token_weights* w, float* y_out,
+                      void* k_out, void* v_out, void* workspace, cudaStream_t stream);
 
 // Cluster size = CTAs per image.  Needs D % CL == 0 and H % CL == 0 (each CTA owns D/CL slot
 // features in the GRU/MLP) and enough tokens per CTA to keep 8 warps busy.
@@ -44,7 +47,10 @@ int sa_iter_pick_cluster(const ocrl_sa_dims* d) {
       continue;
     }
     if (cl == 16) continue;  // non-portable size only on request
-    if (cl > 1 && d->N / cl < 256) continue;
+    // measured on B200 (profiles/r1/sweep_cl.log): ~2048-4096 tokens per CTA is the sweet spot -- larger
+    // clusters spend more time in the DSMEM exchanges of the slot update than they save in the token pass
+    const int want = d->N >= 8192 ? 4 : (d->N >= 512 ? 2 : 1);
+    if (cl > want) continue;
     return cl;
   }
   return 1;
@@ -118,8 +124,13 @@ int ocrl_sa_query_workspace(const ocrl_sa_dims* d, size_t* fwd_ws, size_t* bwd_w
   return OCRL_OK;
 }
 
+size_t ocrl_kv_proj_fwd_workspace(const ocrl_sa_dims* d) {
+  if (check_dims(d)) return 0;
+  return kv_proj_tc_workspace(d);
+}
+
 int ocrl_kv_proj_fwd(const ocrl_sa_dims* d, const float* x, const float* pos_table, const ocrl_token_weights* w,
-                     float* y_out, void* k_out, void* v_out, void* stream) {
+                     float* y_out, void* k_out, void* v_out, void* workspace, void* stream) {
   int rc = check_dims(d);
   if (rc) return rc;
   if ((rc = check_arch())) return rc;
@@ -133,6 +144,10 @@ int ocrl_kv_proj_fwd(const ocrl_sa_dims* d, const float* x, const float* pos_tab
     return OCRL_E_ALIGN;
   }
   if (d->B == 0) return OCRL_OK;
+  if (d->kv_dtype == OCRL_DT_BF16 && d->math_mode == OCRL_MATH_TENSOR && workspace != nullptr) {
+    rc = kv_proj_tc_launch(d, x, pos_table, w, y_out, k_out, v_out, workspace, (cudaStream_t)stream);
+    if (rc != OCRL_E_SHAPE) return rc;  // shapes the tcgen05 kernel does not cover take the FFMA kernel
+  }
   return token_stage_launch(d, x, pos_table, w, y_out, k_out, v_out, (cudaStream_t)stream);
 }
 

@@ -92,7 +92,10 @@ def kv_project(x: Tensor, p: Dict[str, Tensor], *, kv: str = "fp32", enc: Option
         B, N, C = x.shape
     D = p["project_k.weight"].shape[0]
     dt_code, dt = _KV_DTYPES[kv]
-    dims = abi.make_dims(B, N, C, D, D, 1, 1, kv_dtype=dt_code, ln_eps=ln_eps)
+    dims = abi.make_dims(B, N, C, D, D, 1, 1, kv_dtype=dt_code, ln_eps=ln_eps, math_mode=_math_mode(dt_code))
+    ws = None
+    if dims.math_mode == abi.MATH_TENSOR:  # bf16 weight copies for the tcgen05 kernel
+        ws = torch.empty(abi.lib().ocrl_kv_proj_fwd_workspace(ctypes.byref(dims)), device=x.device, dtype=torch.uint8)
     k = torch.empty(B, N, D, device=x.device, dtype=dt)
     v = torch.empty(B, N, D, device=x.device, dtype=dt)
     y = torch.empty(B, N, C, device=x.device, dtype=torch.float32) if want_y else None
@@ -107,7 +110,7 @@ def kv_project(x: Tensor, p: Dict[str, Tensor], *, kv: str = "fp32", enc: Option
     w = abi.token_weights(**tw)
     with _timed("kv_proj_fwd"):
         abi.check(abi.lib().ocrl_kv_proj_fwd(ctypes.byref(dims), abi.ptr(x), abi.ptr(pos_table), ctypes.byref(w),
-                                             abi.ptr(y), abi.ptr(k), abi.ptr(v), abi.stream_ptr()),
+                                             abi.ptr(y), abi.ptr(k), abi.ptr(v), abi.ptr(ws), abi.stream_ptr()),
                   "ocrl_kv_proj_fwd")
     return k, v, y
 

@@ -29,7 +29,7 @@ def test_kv_projection_matches_oracle(name):
     assert rel_err(k.cpu(), k_ref) < 1e-5 and rel_err(v.cpu(), v_ref) < 1e-5
     kb, vb, _ = F.kv_project(g["in"]["inputs"].cuda(), _cuda(g["p"]), kv="bf16")
     assert kb.dtype == torch.bfloat16
-    assert rel_err(kb.float().cpu(), k_ref) < 4e-3 and rel_err(vb.float().cpu(), v_ref) < 4e-3
+    assert rel_err(kb.float().cpu(), k_ref) < 8e-3 and rel_err(vb.float().cpu(), v_ref) < 8e-3
 
 
 @pytest.mark.parametrize("name", SA_CASES)
