@@ -43,7 +43,10 @@ def parse():
     ap.add_argument("--slots", type=int, default=6)
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--slot-size", type=int, default=192)
-    ap.add_argument("--kv", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"],
+                    help="bf16: bf16 k/v + tensor cores (north-star bf16 mode, 2e-2 parity); fp32: exact-parity mode")
+    ap.add_argument("--no-graph", action="store_true", help="do not replay the step from a CUDA graph")
+    ap.add_argument("--no-other-mode", action="store_true", help="skip the short run of the other precision mode")
     ap.add_argument("--impl", default="ocrl_b200", choices=["ocrl_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pool", type=int, default=512, help="distinct frames in the synthetic pool")
@@ -54,7 +57,7 @@ def workload(a):
     return {"workload": f"SLATE encode, {a.size}x{a.size} random-N5C4S4S2 frames (N={a.size * a.size} tokens), "
                         f"K={a.slots}, T={a.iters}, D={a.slot_size}, batch {a.batch}/GPU",
             "frame": a.size, "tokens": a.size * a.size, "num_slots": a.slots, "num_iterations": a.iters,
-            "slot_size": a.slot_size, "batch_per_gpu": a.batch, "kv_storage": a.kv,
+            "slot_size": a.slot_size, "batch_per_gpu": a.batch, "mode": a.mode,
             "weights": "seeded random-init (pretrained_encoders/slate.pth absent from the reference checkout)"}
 
 
@@ -162,6 +165,121 @@ class Clocks:
 
 
 # ------------------------------------------------------------------------------------------------
+def measure(a, mode, steps, warmup, dev, dist, rank, world, pool_host, pool_dev, want_events=True):
+    """One precision mode: eager loop (kernel events -> roofline), CUDA-graph resident loop (value) and
+    CUDA-graph end-to-end loop from pinned host frames (e2e)."""
+    import ocrl_b200
+    from ocrl_b200 import functional as F
+    from ocrl_b200.config import slate_config
+
+    os.environ["OCRL_KV_DTYPE"] = "bf16" if mode == "bf16" else "fp32"
+    os.environ.pop("OCRL_CONV_DTYPE", None)  # module default: bf16 convs in bf16 mode, fp32 convs otherwise
+    torch.backends.cudnn.allow_tf32 = False  # fp32 mode is fp32 end to end, like the reference's CPU path
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True
+    torch.manual_seed(0)
+    model = ocrl_b200.SLATE(*slate_config(num_slots=a.slots, num_iterations=a.iters, slot_size=a.slot_size,
+                                          mlp_hidden_size=a.slot_size, obs_size=a.size))
+    model.to(dev)
+    model.eval()
+    nb = a.pool // a.batch
+    torch.manual_seed(1 + rank)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n_steps, n_warm, kernel_timers=False):
+        for i in range(n_warm):
+            fn(i)
+        barrier()
+        F.KERNEL_EVENTS = [] if kernel_timers else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n_steps):
+            fn(n_warm + i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        ev = F.KERNEL_EVENTS
+        F.KERNEL_EVENTS = None
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, ev
+
+    def batch_dev(i):
+        return pool_dev[(i % nb) * a.batch:(i % nb + 1) * a.batch]
+
+    def batch_host(i):
+        return pool_host[(i % nb) * a.batch:(i % nb + 1) * a.batch]
+
+    def step_eager(i):
+        with torch.no_grad():
+            return model(batch_dev(i))
+
+    ms_eager, events = timed(step_eager, steps, warmup, kernel_timers=want_events)
+
+    out_host = torch.empty(a.batch, a.slots, a.slot_size, dtype=torch.float32).pin_memory()
+    graphed = None
+    if not a.no_graph:
+        try:
+            graphed = ocrl_b200.GraphedEncoder(model, batch_dev(0))
+        except Exception as exc:  # report, fall back to eager launches
+            sys.stderr.write(f"bench.py: CUDA graph capture failed ({exc}); timing eager launches\n")
+    if graphed is not None:
+        def step_resident(i):
+            graphed(batch_dev(i))
+
+        def step_e2e(i):
+            out_host.copy_(graphed(batch_host(i)), non_blocking=True)
+    else:
+        obs_stage = torch.empty(a.batch, 3, a.size, a.size, device=dev)
+        step_resident = step_eager
+
+        def step_e2e(i):
+            obs_stage.copy_(batch_host(i), non_blocking=True)
+            with torch.no_grad():
+                out_host.copy_(model(obs_stage), non_blocking=True)
+
+    ms_res, _ = timed(step_resident, steps, warmup)
+    ms_e2e, _ = timed(step_e2e, steps, max(3, warmup))
+    images = a.batch * steps * world
+    res = {"value": images / ms_res * 1e3, "ms_per_step": ms_res / steps, "eager_value": images / ms_eager * 1e3,
+           "e2e_value": images / ms_e2e * 1e3, "e2e_ms_per_step": ms_e2e / steps, "graph": graphed is not None,
+           "events": events or []}
+    return res
+
+
+def roofline_of(a, mode, events):
+    it_ms = [s.elapsed_time(e) for name, s, e in events if name == "sa_iter_fwd"]
+    tk_ms = [s.elapsed_time(e) for name, s, e in events if name == "kv_proj_fwd"]
+    N, D, K = a.size * a.size, a.slot_size, a.slots
+    esz = 2 if mode == "bf16" else 4
+    bytes_img = 2 * N * D * esz + N * K * 4 + 2 * K * D * 4  # SURVEY.md 8(d)
+    tok_bytes_img = N * 64 * (2 if mode == "bf16" else 4) + 2 * N * D * esz
+    peak, peak_src = HBM_FALLBACK_GBS, "fallback"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        pass
+    it_avg = sum(it_ms) / max(1, len(it_ms))
+    tk_avg = sum(tk_ms) / max(1, len(tk_ms))
+    achieved = a.batch * bytes_img / (it_avg * 1e-3) / 1e9 if it_ms else None
+    tok_achieved = a.batch * tok_bytes_img / (tk_avg * 1e-3) / 1e9 if tk_ms else None
+    return {"kernel": "sa_iter_fwd_tc_kernel (mma.sync bf16)" if mode == "bf16" else "sa_iter_fwd_kernel (fp32 FFMA)",
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": (achieved / peak if achieved else None), "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_image": bytes_img, "avg_launch_ms": it_avg, "launches_timed": len(it_ms),
+            "token_stage": {"kernel": "kv_proj_tc_kernel (tcgen05 + TMA)" if mode == "bf16" else "token_stage_kernel (fp32 FFMA)",
+                            "avg_launch_ms": tk_avg, "achieved": tok_achieved, "unit": "GB/s",
+                            "frac": (tok_achieved / peak if tok_achieved else None),
+                            "algorithmic_bytes_per_image": tok_bytes_img}}
+
+
 def main():
     a = parse()
     rank = int(os.environ.get("RANK", 0))
@@ -180,112 +298,50 @@ def main():
 
         dist.init_process_group("nccl", device_id=dev)
 
-    import ocrl_b200
-    from ocrl_b200 import functional as F
     from ocrl_b200 import synth
-    from ocrl_b200.config import slate_config
-
-    os.environ["OCRL_KV_DTYPE"] = a.kv
-    torch.backends.cudnn.allow_tf32 = False  # fp32 end to end, like the reference's CPU path
-    torch.backends.cuda.matmul.allow_tf32 = False
-    torch.backends.cudnn.benchmark = True
-    torch.manual_seed(0)
-    model = ocrl_b200.SLATE(*slate_config(num_slots=a.slots, num_iterations=a.iters, slot_size=a.slot_size,
-                                          mlp_hidden_size=a.slot_size, obs_size=a.size))
-    model.to(dev)
-    model.eval()
 
     # each rank owns its own shard of the frame pool (no data-path collective: images are independent)
     pool_u8 = torch.from_numpy(synth.random_objs_frames(a.pool, a.size, seed=1000 + rank))
     pool_host = synth.to_obs(pool_u8).contiguous().pin_memory()  # float32 CHW in [0,1], as the reference API takes
     pool_dev = pool_host.to(dev)
-    nb = a.pool // a.batch
-    assert nb >= 1, "--pool must be >= --batch"
-    torch.manual_seed(1 + rank)
-
-    def step_resident(i):
-        obs = pool_dev[(i % nb) * a.batch:(i % nb + 1) * a.batch]
-        with torch.no_grad():
-            return model(obs)
-
-    out_host = torch.empty(a.batch, a.slots, a.slot_size, dtype=torch.float32).pin_memory()
-    obs_stage = torch.empty(a.batch, 3, a.size, a.size, device=dev)
-
-    def step_e2e(i):
-        src = pool_host[(i % nb) * a.batch:(i % nb + 1) * a.batch]
-        obs_stage.copy_(src, non_blocking=True)
-        with torch.no_grad():
-            slots = model(obs_stage)
-        out_host.copy_(slots, non_blocking=True)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, warmup, kernel_timers=False):
-        for i in range(warmup):
-            fn(i)
-        barrier()
-        F.KERNEL_EVENTS = [] if kernel_timers else None
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            fn(warmup + i)
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        ev = F.KERNEL_EVENTS
-        F.KERNEL_EVENTS = None
-        if dist is not None:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, ev
+    assert a.pool // a.batch >= 1, "--pool must be >= --batch"
 
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
-    ms_total, events = timed(step_resident, a.steps, a.warmup, kernel_timers=True)
+    main_res = measure(a, a.mode, a.steps, a.warmup, dev, dist, rank, world, pool_host, pool_dev)
     clk = clocks.stop() if rank == 0 else None
-    ms_e2e, _ = timed(step_e2e, a.steps, max(3, a.warmup))
-
-    images = a.batch * a.steps * world
-    value = images / ms_total * 1e3
-    e2e_value = images / ms_e2e * 1e3
-
-    # roofline of the fused iteration kernel (rank 0's launches; CUDA events on the launch stream)
-    it_ms = [s.elapsed_time(e) for name, s, e in events if name == "sa_iter_fwd"]
-    tk_ms = [s.elapsed_time(e) for name, s, e in events if name == "kv_proj_fwd"]
-    N, D, K = a.size * a.size, a.slot_size, a.slots
-    esz = 4 if a.kv == "fp32" else 2
-    bytes_img = 2 * N * D * esz + N * K * 4 + 2 * K * D * 4
-    peak, peak_src = HBM_FALLBACK_GBS, "fallback"
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured"
-    except Exception:
-        pass
-    it_avg = sum(it_ms) / max(1, len(it_ms))
-    achieved = a.batch * bytes_img / (it_avg * 1e-3) / 1e9 if it_ms else None
-    roofline = {"kernel": "sa_iter_fwd_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak if achieved else None), "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_image": bytes_img, "avg_launch_ms": it_avg, "launches_timed": len(it_ms),
-                "token_stage_avg_ms": (sum(tk_ms) / len(tk_ms) if tk_ms else None)}
+    other = None
+    if not a.no_other_mode:
+        om = "fp32" if a.mode == "bf16" else "bf16"
+        other = (om, measure(a, om, max(5, a.steps // 3), 3, dev, dist, rank, world, pool_host, pool_dev))
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-                "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32" if a.kv == "fp32" else "bf16 k/v storage, f32 accumulate", "data": "synthetic",
+        N, D = a.size * a.size, a.slot_size
+        esz = 2 if a.mode == "bf16" else 4
+        mine = [e for e in main_res["events"]]
+        line = {"metric": METRIC, "value": main_res["value"], "unit": UNIT, "n_gpus": world, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None,
+                "dtype": ("bf16 (bf16 convs / k / v / tensor-core operands, f32 accumulate, f32 slot update)"
+                          if a.mode == "bf16" else "f32"),
+                "data": "synthetic",
                 "config": dict(workload(a), l2="k/v working set per step %.0f MB > 126 MB L2; frame pool of %d rotates"
                                % (a.batch * 2 * N * D * esz / 1e6, a.pool),
-                               cnn="cuDNN fp32 via torch (TF32 off); token stage + iteration loop hand-written CUDA"),
+                               cnn="cuDNN via torch (library call); token stage + iteration loop hand-written CUDA",
+                               launch="CUDA graph replay of SLATE.__call__" if main_res["graph"] else "eager launches"),
                 "clocks": clk,
-                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
+                "e2e": {"value": main_res["e2e_value"], "unit": UNIT, "ms_per_step": main_res["e2e_ms_per_step"],
                         "h2d_bytes_per_step": a.batch * 3 * a.size * a.size * 4,
                         "d2h_bytes_per_step": a.batch * a.slots * a.slot_size * 4},
-                "gpu_launches": len(events) if events else 0,
-                "roofline": roofline}
+                "gpu_launches": len(mine), "eager_value": main_res["eager_value"],
+                "roofline": roofline_of(a, a.mode, main_res["events"])}
+        if other is not None:
+            om, r = other
+            rf = roofline_of(a, om, r["events"])
+            line["other_mode"] = {"mode": om, "value": r["value"], "e2e": r["e2e_value"], "unit": UNIT,
+                                  "ms_per_step": r["ms_per_step"], "roofline_frac": rf["frac"],
+                                  "iter_kernel_ms": rf["avg_launch_ms"], "token_stage_ms": rf["token_stage"]["avg_launch_ms"]}
         if world == 1 and not a.no_cpu_baseline:
             csteps = 6
             ips, cms, cores = time_cpu(a, pool_u8, csteps, 1)

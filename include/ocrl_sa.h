@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define OCRL_ABI_VERSION 1
+#define OCRL_ABI_VERSION 2
 
 enum {
   OCRL_OK = 0,
@@ -38,6 +38,10 @@ enum {
 };
 
 enum { OCRL_DT_F32 = 0, OCRL_DT_BF16 = 1 };
+/* x_format: layout / type of the token-stage input */
+enum { OCRL_X_TOKENS_F32 = 0  /* [B,N,C_in] fp32 */,
+       OCRL_X_NCHW_F32 = 1    /* CNN feature map [B,C_in,H*W] fp32 (transposed on the way in) */,
+       OCRL_X_TOKENS_BF16 = 2 /* [B,N,C_in] bf16, e.g. a channels-last bf16 feature map (tensor path only) */ };
 /* math_mode: how the token contractions are evaluated */
 enum { OCRL_MATH_FP32 = 0 /* fp32 FFMA everywhere (parity mode) */,
        OCRL_MATH_TENSOR = 1 /* bf16 operands on tensor cores, fp32 accumulate */ };
@@ -58,6 +62,7 @@ typedef struct ocrl_sa_dims {
   float ln_eps;     /* nn.LayerNorm eps, 1e-5 */
   int32_t kv_dtype; /* OCRL_DT_* storage type of k and v */
   int32_t math_mode;/* OCRL_MATH_* */
+  int32_t x_format; /* OCRL_X_* (token stage only) */
 } ocrl_sa_dims;
 
 /* Parameters of the iteration loop, fp32, in the reference's state_dict layout
@@ -104,15 +109,16 @@ const char* ocrl_last_error(void);
 int ocrl_sa_query_workspace(const ocrl_sa_dims* dims, size_t* fwd_ws, size_t* bwd_ws, size_t* saved);
 
 /* Token stage, forward.  Replaces slot_attn.py:151 (optional) and :54-61.
- *   x        [B,N,C_in] fp32 tokens, or -- when pos_table != NULL -- the CNN feature map
- *            [B,C_in,H*W] (NCHW) to which pos_table [C_in,H*W] is added while it is transposed
- *            to token-major (ocrs/common/utils.py:28-33, slate_module.py:132-133).
+ *   x        the tokens in dims->x_format: [B,N,C_in] fp32 / bf16, or the CNN feature map
+ *            [B,C_in,H*W] (NCHW), transposed to token-major on the way in (slate_module.py:133).
+ *   pos_table NULL, or the position-embedding table [C_in,H*W] fp32 that is added to every image's
+ *            tokens (ocrs/common/utils.py:28-33).
  *   y_out    [B,N,C_in] fp32 output of the token MLP (NULL if not needed / MLP skipped)
  *   k_out,v_out [B,N,D] in dims->kv_dtype; k already scaled by D^-1/2 (slot_attn.py:61).
  *   workspace: ocrl_kv_proj_fwd_workspace(dims) bytes of scratch (bf16 weight copies for the tensor-core
  *            path); may be NULL, which selects the fp32 FFMA kernel. */
 size_t ocrl_kv_proj_fwd_workspace(const ocrl_sa_dims* dims);
-int ocrl_kv_proj_fwd(const ocrl_sa_dims* dims, const float* x, const float* pos_table,
+int ocrl_kv_proj_fwd(const ocrl_sa_dims* dims, const void* x, const float* pos_table,
                      const ocrl_token_weights* w, float* y_out, void* k_out, void* v_out,
                      void* workspace, void* stream);
 

@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(HERE, "csrc", "libocrl_sa.so")
 
 DT_F32, DT_BF16 = 0, 1
 MATH_FP32, MATH_TENSOR = 0, 1
+X_TOKENS_F32, X_NCHW_F32, X_TOKENS_BF16 = 0, 1, 2
 
 EXPORTS = [
     "ocrl_version", "ocrl_built_arch", "ocrl_last_error", "ocrl_sa_query_workspace",
@@ -27,7 +28,7 @@ EXPORTS = [
 class SaDims(Structure):
     _fields_ = [("B", c_int32), ("N", c_int32), ("C_in", c_int32), ("D", c_int32), ("H_mlp", c_int32),
                 ("K", c_int32), ("T", c_int32), ("heads", c_int32), ("eps", c_float), ("ln_eps", c_float),
-                ("kv_dtype", c_int32), ("math_mode", c_int32)]
+                ("kv_dtype", c_int32), ("math_mode", c_int32), ("x_format", c_int32)]
 
 
 _SA_W = ["ln_slots_w", "ln_slots_b", "ln_mlp_w", "ln_mlp_b", "wq", "w_ih", "w_hh", "b_ih", "b_hh",
@@ -99,8 +100,9 @@ def stream_ptr() -> c_void_p:
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def make_dims(B, N, C_in, D, H_mlp, K, T, heads=1, eps=1e-8, ln_eps=1e-5, kv_dtype=DT_F32, math_mode=MATH_FP32):
-    return SaDims(B, N, C_in, D, H_mlp, K, T, heads, eps, ln_eps, kv_dtype, math_mode)
+def make_dims(B, N, C_in, D, H_mlp, K, T, heads=1, eps=1e-8, ln_eps=1e-5, kv_dtype=DT_F32, math_mode=MATH_FP32,
+              x_format=X_TOKENS_F32):
+    return SaDims(B, N, C_in, D, H_mlp, K, T, heads, eps, ln_eps, kv_dtype, math_mode, x_format)
 
 
 def query_workspace(dims: SaDims):

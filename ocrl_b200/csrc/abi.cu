@@ -16,7 +16,7 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-int token_stage_launch(const ocrl_sa_dims* d, const float* x, const float* pos, const ocrl_token_weights* w,
+int token_stage_launch(const ocrl_sa_dims* d, const void* x, const float* pos, const ocrl_token_weights* w,
                        float* y_out, void* k_out, void* v_out, cudaStream_t stream);
 int sa_iter_fwd_launch(const ocrl_sa_dims* d, const void* k, const void* v, const float* slots0,
                        const ocrl_sa_weights* w, float* slots_out, float* attn_out, float* saved,
@@ -30,7 +30,7 @@ int kv_proj_bwd_launch(const ocrl_sa_dims* d, const float* x, const ocrl_token_w
                        cudaStream_t stream);
 size_t kv_proj_bwd_workspace(const ocrl_sa_dims* d);
 size_t kv_proj_tc_workspace(const ocrl_sa_dims* d);
-int kv_proj_tc_launch(const ocrl_sa_dims* d, const float* x, const float* pos, const ocrl_token_weights* w, float* y_out,
+int kv_proj_tc_launch(const ocrl_sa_dims* d, const void* x, const float* pos, const ocrl_token_weights* w, float* y_out,
                       void* k_out, void* v_out, void* workspace, cudaStream_t stream);
 
 // Cluster size = CTAs per image.  Needs D % CL == 0 and H % CL == 0 (each CTA owns D/CL slot
@@ -129,7 +129,7 @@ size_t ocrl_kv_proj_fwd_workspace(const ocrl_sa_dims* d) {
   return kv_proj_tc_workspace(d);
 }
 
-int ocrl_kv_proj_fwd(const ocrl_sa_dims* d, const float* x, const float* pos_table, const ocrl_token_weights* w,
+int ocrl_kv_proj_fwd(const ocrl_sa_dims* d, const void* x, const float* pos_table, const ocrl_token_weights* w,
                      float* y_out, void* k_out, void* v_out, void* workspace, void* stream) {
   int rc = check_dims(d);
   if (rc) return rc;

@@ -29,7 +29,7 @@ struct ProjTcParams {
   const float* in_ln_w; const float* in_ln_b;
   const float* pos;                               // [64][N] or null (token-major input)
   float* y_out;                                   // [M][64] or null
-  int has_mlp, nchw, N, D;
+  int has_mlp, x_format, N, D;
   long long M;
   int ntiles;
   float ln_eps;
@@ -206,11 +206,13 @@ kv_proj_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         const long long tile = blockIdx.x + (long long)it * gridDim.x;
         const int s = it & 1;
         unsigned char* dst = X_s + s * X_BYTES;
-        mbar_expect_tx(&full[s], X_BYTES);
-        if (p.nchw) {
+        mbar_expect_tx(&full[s], p.x_format == OCRL_X_TOKENS_BF16 ? X_BYTES / 2 : X_BYTES);
+        if (p.x_format == OCRL_X_NCHW_F32) {
           const long long m0 = tile * PT_TM;
           const int b = (int)(m0 / p.N), n0 = (int)(m0 % p.N);
           tma_load_2d(dst, &tm_x, n0, b * PT_C, &full[s]);           // [64 ch][128 tokens] fp32
+        } else if (p.x_format == OCRL_X_TOKENS_BF16) {
+          tma_load_2d(dst, &tm_x, 0, (int)(tile * PT_TM), &full[s]);  // [128 tokens][64] bf16, swizzled
         } else {
           tma_load_2d(dst, &tm_x, 0, (int)(tile * PT_TM), &full[s]);  // cols 0-31, 128 rows, swizzled
           tma_load_2d(dst + X_BYTES / 2, &tm_x, 32, (int)(tile * PT_TM), &full[s]);
@@ -274,11 +276,20 @@ kv_proj_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       float x[PT_C];
       mbar_wait(&full[s], (uint32_t)((it >> 1) & 1));
       const unsigned char* xs = X_s + s * X_BYTES;
-      if (p.nchw) {
-        const int n = (int)((tile * PT_TM) % p.N) + row;
+      if (p.x_format == OCRL_X_NCHW_F32) {
 #pragma unroll
-        for (int c = 0; c < PT_C; ++c)
-          x[c] = reinterpret_cast<const float*>(xs)[c * PT_TM + row] + __ldg(p.pos + (size_t)c * p.N + n);
+        for (int c = 0; c < PT_C; ++c) x[c] = reinterpret_cast<const float*>(xs)[c * PT_TM + row];
+      } else if (p.x_format == OCRL_X_TOKENS_BF16) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 u = *reinterpret_cast<const uint4*>(xs + row * 128 + ((c ^ (row & 7)) << 4));
+          const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            x[8 * c + 2 * i] = __uint_as_float(w4[i] << 16);
+            x[8 * c + 2 * i + 1] = __uint_as_float(w4[i] & 0xffff0000u);
+          }
+        }
       } else {
 #pragma unroll
         for (int h = 0; h < 2; ++h)
@@ -290,6 +301,11 @@ kv_proj_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           }
       }
       mbar_arrive(&empty[s]);
+      if (p.pos != nullptr) {  // position table [64][N]: coalesced across the 128 row threads
+        const int n = (int)((tile * PT_TM + row) % p.N);
+#pragma unroll
+        for (int c = 0; c < PT_C; ++c) x[c] += __ldg(p.pos + (size_t)c * p.N + n);
+      }
 
       if (p.has_mlp) {
         row_layer_norm(x, prm, prm + 64, p.ln_eps);
@@ -427,12 +443,12 @@ size_t kv_proj_tc_workspace(const ocrl_sa_dims* d) {
 }
 
 // returns OCRL_E_SHAPE when this shape has to take the FFMA kernel instead
-int kv_proj_tc_launch(const ocrl_sa_dims* d, const float* x, const float* pos, const ocrl_token_weights* w, float* y_out,
+int kv_proj_tc_launch(const ocrl_sa_dims* d, const void* x, const float* pos, const ocrl_token_weights* w, float* y_out,
                       void* k_out, void* v_out, void* workspace, cudaStream_t stream) {
   const int D = d->D;
   const long long M = (long long)d->B * d->N;
   if (d->C_in != PT_C || (D != 64 && D != 128 && D != 192) || workspace == nullptr) return OCRL_E_SHAPE;
-  if (pos != nullptr && (d->N % PT_TM) != 0) return OCRL_E_SHAPE;  // a tile must not straddle two images
+  if (d->x_format == OCRL_X_NCHW_F32 && (d->N % PT_TM) != 0) return OCRL_E_SHAPE;  // a tile must not straddle two images
   if (!encode_fn()) return OCRL_E_SHAPE;
   __nv_bfloat16* w1b = reinterpret_cast<__nv_bfloat16*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
   __nv_bfloat16* w2b = w1b + 64 * 64;
@@ -444,9 +460,12 @@ int kv_proj_tc_launch(const ocrl_sa_dims* d, const float* x, const float* pos, c
 
   CUtensorMap tm_x, tm_w1, tm_w2, tm_wkv, tm_k, tm_v;
   bool ok = true;
-  if (pos != nullptr)  // NCHW feature map viewed as [B*64][N]; box = 128 tokens x 64 channels
+  if (d->x_format == OCRL_X_NCHW_F32)  // NCHW feature map viewed as [B*64][N]; box = 128 tokens x 64 channels
     ok &= make_map(&tm_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, (uint64_t)d->N, (uint64_t)d->B * PT_C,
                    (uint64_t)d->N * 4, PT_TM, PT_C, CU_TENSOR_MAP_SWIZZLE_NONE);
+  else if (d->x_format == OCRL_X_TOKENS_BF16)  // bf16 tokens [M][64]: one 128-byte-swizzled box of 128 rows
+    ok &= make_map(&tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, x, PT_C, (uint64_t)M, PT_C * 2, PT_C, PT_TM,
+                   CU_TENSOR_MAP_SWIZZLE_128B);
   else  // tokens [M][64]; two boxes of 32 features (128 B) x 128 rows, 128-byte swizzle
     ok &= make_map(&tm_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, PT_C, (uint64_t)M, PT_C * 4, 32, PT_TM,
                    CU_TENSOR_MAP_SWIZZLE_128B);
@@ -465,7 +484,7 @@ int kv_proj_tc_launch(const ocrl_sa_dims* d, const float* x, const float* pos, c
   ProjTcParams p;
   p.enc_ln_w = w->enc_ln_w; p.enc_ln_b = w->enc_ln_b; p.b1 = w->mlp_b1; p.b2 = w->mlp_b2;
   p.in_ln_w = w->in_ln_w; p.in_ln_b = w->in_ln_b; p.pos = pos; p.y_out = y_out;
-  p.has_mlp = has_mlp ? 1 : 0; p.nchw = pos != nullptr ? 1 : 0; p.N = d->N; p.D = D; p.M = M;
+  p.has_mlp = has_mlp ? 1 : 0; p.x_format = d->x_format; p.N = d->N; p.D = D; p.M = M;
   p.ntiles = (int)((M + PT_TM - 1) / PT_TM);
   p.ln_eps = d->ln_eps;
   int dev = 0, sms = 148;

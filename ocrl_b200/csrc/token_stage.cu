@@ -17,8 +17,9 @@ constexpr int TS_TM = 128;      // tokens per tile
 constexpr int TS_NT = 256;
 
 struct TokenStageArgs {
-  const float* x;          // [B,N,C] or NCHW [B,C,N] when pos != null
+  const float* x;          // [B,N,C], or NCHW [B,C,N] when nchw != 0
   const float* pos;        // [C,N] or null
+  int nchw;
   ocrl_token_weights w;
   float* y_out;            // [B,N,C] or null
   void* k_out;
@@ -99,12 +100,21 @@ __global__ void __launch_bounds__(TS_NT, 1) token_stage_kernel(const TokenStageA
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long m0 = tile * TS_TM;
     // ---- load the input tile ----------------------------------------------------------------
-    if (a.pos == nullptr) {
+    if (!a.nchw) {
       for (int e = tid; e < TS_TM * (TS_C / 4); e += TS_NT) {
         const int r = e / (TS_C / 4), c4 = e % (TS_C / 4);
         const long long m = m0 + r;
         float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (m < a.M) xv = __ldg(reinterpret_cast<const float4*>(a.x + m * TS_C) + c4);
+        if (m < a.M) {
+          xv = __ldg(reinterpret_cast<const float4*>(a.x + m * TS_C) + c4);
+          if (a.pos != nullptr) {
+            const int n = (int)(m % a.N);
+            xv.x += __ldg(a.pos + (long long)(4 * c4 + 0) * a.N + n);
+            xv.y += __ldg(a.pos + (long long)(4 * c4 + 1) * a.N + n);
+            xv.z += __ldg(a.pos + (long long)(4 * c4 + 2) * a.N + n);
+            xv.w += __ldg(a.pos + (long long)(4 * c4 + 3) * a.N + n);
+          }
+        }
         *reinterpret_cast<float4*>(As + r * TS_LD + 4 * c4) = xv;
       }
     } else {
@@ -116,7 +126,7 @@ __global__ void __launch_bounds__(TS_NT, 1) token_stage_kernel(const TokenStageA
         if (m < a.M) {
           const long long b = m / a.N;
           const int n = (int)(m - b * a.N);
-          xv = __ldg(a.x + (b * TS_C + c) * a.N + n) + __ldg(a.pos + (long long)c * a.N + n);
+          xv = __ldg(a.x + (b * TS_C + c) * a.N + n) + (a.pos ? __ldg(a.pos + (long long)c * a.N + n) : 0.f);
         }
         As[r * TS_LD + c] = xv;
       }
@@ -187,7 +197,7 @@ __global__ void __launch_bounds__(TS_NT, 1) token_stage_kernel(const TokenStageA
   }
 }
 
-int token_stage_launch(const ocrl_sa_dims* d, const float* x, const float* pos, const ocrl_token_weights* w,
+int token_stage_launch(const ocrl_sa_dims* d, const void* x, const float* pos, const ocrl_token_weights* w,
                        float* y_out, void* k_out, void* v_out, cudaStream_t stream) {
   if (d->C_in != TS_C) {
     set_error("kv_proj: C_in=%d not supported (64)", d->C_in);
@@ -197,8 +207,12 @@ int token_stage_launch(const ocrl_sa_dims* d, const float* x, const float* pos, 
     set_error("kv_proj: slot_size=%d not supported (64, 128, 192)", d->D);
     return OCRL_E_SHAPE;
   }
+  if (d->x_format != OCRL_X_TOKENS_F32 && d->x_format != OCRL_X_NCHW_F32) {
+    set_error("kv_proj: bf16 tokens need the tensor-core path (kv_dtype = bf16, math_mode = tensor, N %% 128 == 0)");
+    return OCRL_E_SHAPE;
+  }
   TokenStageArgs a;
-  a.x = x; a.pos = pos; a.w = *w; a.y_out = y_out; a.k_out = k_out; a.v_out = v_out;
+  a.x = reinterpret_cast<const float*>(x); a.pos = pos; a.nchw = (d->x_format == OCRL_X_NCHW_F32); a.w = *w; a.y_out = y_out; a.k_out = k_out; a.v_out = v_out;
   a.B = d->B; a.N = d->N; a.D = d->D; a.M = (long long)d->B * d->N;
   a.ln_eps = d->ln_eps;
   a.kscale = 1.0f / sqrtf((float)d->D);

@@ -78,21 +78,34 @@ def kv_project(x: Tensor, p: Dict[str, Tensor], *, kv: str = "fp32", enc: Option
                pos_table: Optional[Tensor] = None, want_y: bool = False, ln_eps: float = 1e-5):
     """Token stage: [pos add + NCHW->tokens] -> [LN+MLP of the encoder] -> norm_inputs -> k, v.
 
-    x: [B,N,C] tokens, or the NCHW feature map [B,C,H,W] when ``pos_table`` ([C,H*W]) is given.
+    x: [B,N,C] tokens, or a CNN feature map [B,C,H,W] (NCHW-contiguous fp32, or channels-last fp32 / bf16,
+    whose memory already is token-major); ``pos_table`` ([C,H*W]) is added to every image's tokens.
     enc: optional {"layer_norm.weight","layer_norm.bias","mlp.0.weight",...} of SlotAttentionEncoder.
     Returns (k, v, y) with y = token-MLP output [B,N,C] (None unless want_y).
     """
     _require_cuda(x, "kv_project")
-    x = _f32c(x)
-    if pos_table is not None:
+    x_format = abi.X_TOKENS_F32
+    if x.dim() == 4:  # CNN feature map [B,C,H,W]
         B, C = x.shape[0], x.shape[1]
         N = x.shape[2] * x.shape[3]
-        pos_table = _f32c(pos_table).reshape(C, N)
+        if not x.is_contiguous() and x.permute(0, 2, 3, 1).is_contiguous():
+            x = x.permute(0, 2, 3, 1).reshape(B, N, C)  # channels-last memory == token-major [B,N,C], no copy
+            if x.dtype == torch.bfloat16 and kv == "bf16" and _math_mode(abi.DT_BF16) == abi.MATH_TENSOR:
+                x_format = abi.X_TOKENS_BF16
+            else:
+                x = x.float()
+        else:
+            x = _f32c(x)
+            x_format = abi.X_NCHW_F32
     else:
+        x = _f32c(x)
         B, N, C = x.shape
+    if pos_table is not None:
+        pos_table = _f32c(pos_table).reshape(C, N)
     D = p["project_k.weight"].shape[0]
     dt_code, dt = _KV_DTYPES[kv]
-    dims = abi.make_dims(B, N, C, D, D, 1, 1, kv_dtype=dt_code, ln_eps=ln_eps, math_mode=_math_mode(dt_code))
+    dims = abi.make_dims(B, N, C, D, D, 1, 1, kv_dtype=dt_code, ln_eps=ln_eps, math_mode=_math_mode(dt_code),
+                         x_format=x_format)
     ws = None
     if dims.math_mode == abi.MATH_TENSOR:  # bf16 weight copies for the tcgen05 kernel
         ws = torch.empty(abi.lib().ocrl_kv_proj_fwd_workspace(ctypes.byref(dims)), device=x.device, dtype=torch.uint8)

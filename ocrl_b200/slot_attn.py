@@ -78,7 +78,7 @@ class SlotAttention(nn.Module):
         ``_enc`` / ``_pos_table`` are private hooks used by the encoder / SLATE module to fuse the
         token LayerNorm+MLP and the position-table add into the projection kernel (inference only).
         """
-        self._check(inputs, slots, fmap=_pos_table is not None)
+        self._check(inputs, slots, fmap=inputs.dim() == 4)
         p = self._params()
         needs_grad = torch.is_grad_enabled() and (
             inputs.requires_grad or slots.requires_grad or any(t.requires_grad for t in p.values()))

@@ -100,3 +100,23 @@ def test_bf16_mode_through_the_module(monkeypatch):
         slots, masks = model(obs, with_masks=True)
     assert rel_err(slots.cpu(), g["out"]["slots"]) < 2e-2
     assert rel_err(masks.cpu(), g["out"]["masks"]) < 2e-2
+
+
+@pytest.mark.parametrize("conv", ["tf32", "bf16"])
+def test_bf16_mode_with_tensor_core_convs(monkeypatch, conv):
+    """bf16 mode end to end: channels-last cuDNN convs (TF32 or bf16) feeding the tcgen05 token stage
+    (bf16 tokens when the convs are bf16) and the tensor-core iteration kernel; 2e-2 tolerance."""
+    meta, g = load_case("slate_encode_64")
+    monkeypatch.setenv("OCRL_KV_DTYPE", "bf16")
+    monkeypatch.setenv("OCRL_CONV_DTYPE", conv)
+    model = ocrl_b200.SLATE(*slate_config())
+    _load_hot(model._module, g["p"])
+    model.to("cuda")
+    model.eval()
+    _inject_noise(model._module._slotattn, g["in"]["noise"])
+    obs = (g["in"]["frames_u8"].permute(0, 3, 1, 2).float() / 255.0).cuda()
+    with torch.no_grad():
+        slots, masks = model(obs, with_masks=True)
+    es, em = rel_err(slots.cpu(), g["out"]["slots"]), rel_err(masks.cpu(), g["out"]["masks"])
+    print(f"bf16 mode, {conv} convs: slots rel err {es:.2e}, masks rel err {em:.2e}")
+    assert es < 2e-2 and em < 2e-2
