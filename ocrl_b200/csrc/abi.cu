@@ -30,6 +30,7 @@ int kv_proj_bwd_launch(const ocrl_sa_dims* d, const float* x, const ocrl_token_w
                        cudaStream_t stream);
 size_t kv_proj_bwd_workspace(const ocrl_sa_dims* d);
 size_t kv_proj_tc_workspace(const ocrl_sa_dims* d);
+size_t sa_iter_tc_workspace(const ocrl_sa_dims* d);
 int kv_proj_tc_launch(const ocrl_sa_dims* d, const void* x, const float* pos, const ocrl_token_weights* w, float* y_out,
                       void* k_out, void* v_out, void* workspace, cudaStream_t stream);
 
@@ -118,7 +119,7 @@ const char* ocrl_last_error(void) { return g_err; }
 int ocrl_sa_query_workspace(const ocrl_sa_dims* d, size_t* fwd_ws, size_t* bwd_ws, size_t* saved) {
   int rc = check_dims(d);
   if (rc) return rc;
-  if (fwd_ws) *fwd_ws = 0;
+  if (fwd_ws) *fwd_ws = sa_iter_tc_workspace(d);
   if (bwd_ws) *bwd_ws = sa_iter_bwd_workspace(d);
   if (saved) *saved = sizeof(float) * (size_t)d->B * d->T * (size_t)SavedLayout(d->K, d->D, d->H_mlp).stride();
   return OCRL_OK;

@@ -11,20 +11,22 @@
 // k/v tiles of 16 tokens stream global -> shared with 16-byte cp.async into rows padded by 16 bytes
 // (conflict-free ldmatrix), a 3-stage ring private to each warp: no block barrier in the token loop.
 // Accumulation is fp32; the token-sum S uses the same bf16-rounded weights as the numerator.
+#include <stdlib.h>
+
 #include "slot_math.cuh"
 
 namespace ocrl {
 
-template <int D, int KP, int NPW_>
+template <int D, int KP, int NPW_, int GT_ = 16>
 struct TcCfg {
   static constexpr int NPW = NPW_;              // warps that stream tokens (each owns a tile ring)
   static constexpr int NW = 8;                  // all warps take part in the slot update
   static constexpr int NT = NW * 32;
-  static constexpr int GT = 16;                 // tokens per warp group
+  static constexpr int GT = GT_;                // tokens per warp group (16, or 8 with twice the warps)
   static constexpr int PITCH = D * 2 + 16;      // bytes per padded bf16 row
   static constexpr int TILE_BYTES = GT * PITCH; // k or v of one group
   static constexpr int STAGE_BYTES = 2 * TILE_BYTES;
-  static constexpr int STAGES = (KP > 8 && D >= 192) ? 2 : 3;
+  static constexpr int STAGES = (GT_ == 8) ? 2 : ((KP > 8 && D >= 192) ? 2 : 3);
   static constexpr int NKS = D / 16;            // k-steps of the logits / m-tiles of U^T
   static constexpr int NSL = KP / 8;            // slot n-tiles (1 or 2)
   static constexpr int RB = (KP <= 8) ? 4 : 2;  // rows per batch in the slot-update matvecs
@@ -33,9 +35,9 @@ struct TcCfg {
   static_assert(D % 64 == 0, "D must be a multiple of 64");
 };
 
-template <int D, int KP, int NWT>
-__global__ void __launch_bounds__(TcCfg<D, KP, NWT>::NT, 1) sa_iter_fwd_tc_kernel(const IterFwdArgs a) {
-  using Cfg = TcCfg<D, KP, NWT>;
+template <int D, int KP, int NWT, int GTT>
+__global__ void __launch_bounds__(TcCfg<D, KP, NWT, GTT>::NT, 1) sa_iter_fwd_tc_kernel(const IterFwdArgs a) {
+  using Cfg = TcCfg<D, KP, NWT, GTT>;
   constexpr int NW = Cfg::NW, NPW = Cfg::NPW, NT = Cfg::NT, GT = Cfg::GT, PITCH = Cfg::PITCH, STAGES = Cfg::STAGES;
   constexpr int NKS = Cfg::NKS, NSL = Cfg::NSL, RB = Cfg::RB, NC = D / 64;
   typedef __nv_bfloat16 bf16;
@@ -81,11 +83,23 @@ __global__ void __launch_bounds__(TcCfg<D, KP, NWT>::NT, 1) sa_iter_fwd_tc_kerne
   uint64_t* wbar = reinterpret_cast<uint64_t*>(sp);  // weights landed: 0 = GRU, 1 = W1, 2 = W2, 3 = Wq
   // the CTA's weight slices fit in the idle ring -> stream them with bulk copies under the exchanges
   const size_t gru_floats = (size_t)DS * D, w1_floats = (size_t)HS * D, w2_floats = (size_t)DS * H;
-  const bool w_smem = sizeof(float) * (6 * gru_floats + w1_floats + w2_floats) <= ring_bytes;
+  const bool w_smem = (a.wb16 == nullptr) && sizeof(float) * (6 * gru_floats + w1_floats + w2_floats) <= ring_bytes;
   float* ws_gru = wstage;                 // [ih_r, ih_z, ih_n, hh_r, hh_z, hh_n][DS][D]
   float* ws_w1 = ws_gru + 6 * gru_floats; // [HS][D]
   float* ws_w2 = ws_w1 + w1_floats;       // [DS][H]
   float* ws_wq = wstage;                  // [DS][D], re-uses the first GRU block once the GRU is done
+  // tensor-core slot update: bf16 weights straight from L2, bf16 hi/lo vector pairs staged in the idle ring
+  const bool use_mma = (a.wb16 != nullptr);
+  const int LP = LMAX + 8;
+  bf16* vst0h = reinterpret_cast<bf16*>(ring);
+  bf16* vst0l = vst0h + KP * LP;
+  bf16* vst1h = vst0l + KP * LP;
+  bf16* vst1l = vst1h + KP * LP;
+  const bf16* wb_q = a.wb16;
+  const bf16* wb_ih = wb_q + (size_t)D * D;
+  const bf16* wb_hh = wb_ih + (size_t)3 * D * D;
+  const bf16* wb_1 = wb_hh + (size_t)3 * D * D;
+  const bf16* wb_2 = wb_1 + (size_t)H * D;
 
   const bf16* kimg = reinterpret_cast<const bf16*>(a.k) + (size_t)img * N * D;
   const bf16* vimg = reinterpret_cast<const bf16*>(a.v) + (size_t)img * N * D;
@@ -144,7 +158,11 @@ __global__ void __launch_bounds__(TcCfg<D, KP, NWT>::NT, 1) sa_iter_fwd_tc_kerne
     d.vec0 = d.vec1 = lnb; d.out0 = gates;
     d.njobs = 1; d.split = 1; d.split_mod = 1; d.row_stride = 0; d.nrows = DS;
     d.out_stride = 0; d.ldo = DS;
-    if (w_smem) {
+    if (use_mma) {
+      stage_vec_hilo(lnb, K, KP, D, vst0h, vst0l, LP, tid, NT);
+      __syncthreads();
+      rows_mma_jobs<KP, D / 32>(wb_q, rank * DS, 0, 1, DS, vst0h, vst0l, LP, gates, 0, DS, warp, lane, NW);
+    } else if (w_smem) {
       mbar_wait(&wbar[3], (uint32_t)(tq & 1));
       d.W0 = d.W1 = ws_wq; d.row_base = 0;
       rows_dot_desc<KP, RB, NC, 2, false>(d, warp, lane, NW);
@@ -171,20 +189,39 @@ __global__ void __launch_bounds__(TcCfg<D, KP, NWT>::NT, 1) sa_iter_fwd_tc_kerne
   compute_q(0);
 
   unsigned char* my_ring = ring + (size_t)warp * STAGES * Cfg::STAGE_BYTES;
+  // softmax scratch of a pass warp lives in its own (still unused) slice of the partial-U buffer
+  float* my_lg = ured + (size_t)(warp < NPW ? warp : 0) * KP * D;  // logits [16 tokens][KP] fp32
+  bf16* my_wb = reinterpret_cast<bf16*>(my_lg + GT * KP);            // weights [KP][16 tokens] bf16
 
-  // all 32 lanes copy one 16-token group of k and v into ring stage `st` (zero-fill past N)
+  // all 32 lanes copy one 16-token group of k and v into ring stage `st` (zero-fill past N).
+  // Token rows are contiguous in global memory, so chunk c of the tile sits at byte 16*c; in shared
+  // memory every row is padded by 16 bytes (conflict-free ldmatrix).
+  int dst_off[GT * Cfg::CHUNKS_PER_ROW / 32];
+#pragma unroll
+  for (int i = 0; i < GT * Cfg::CHUNKS_PER_ROW / 32; ++i) {
+    const int c = lane + 32 * i;
+    dst_off[i] = c * 16 + (c / Cfg::CHUNKS_PER_ROW) * 16;
+  }
   auto issue = [&](int local_group, int st) {
     const int tok0 = (g_begin + warp + local_group * NPW) * GT;
     unsigned char* kd = my_ring + (size_t)st * Cfg::STAGE_BYTES;
     unsigned char* vd = kd + Cfg::TILE_BYTES;
+    const unsigned char* ks = reinterpret_cast<const unsigned char*>(kimg + (size_t)tok0 * D) + lane * 16;
+    const unsigned char* vs = reinterpret_cast<const unsigned char*>(vimg + (size_t)tok0 * D) + lane * 16;
+    if (tok0 + GT <= N) {
 #pragma unroll
-    for (int i = 0; i < GT * Cfg::CHUNKS_PER_ROW / 32; ++i) {
-      const int c = lane + 32 * i;
-      const int row = c / Cfg::CHUNKS_PER_ROW, col = c % Cfg::CHUNKS_PER_ROW;
-      const bool ok = (tok0 + row) < N;
-      const size_t src = (size_t)(ok ? tok0 + row : 0) * D + col * 8;
-      cp_async16(kd + row * PITCH + col * 16, kimg + src, ok ? 16 : 0);
-      cp_async16(vd + row * PITCH + col * 16, vimg + src, ok ? 16 : 0);
+      for (int i = 0; i < GT * Cfg::CHUNKS_PER_ROW / 32; ++i) {
+        cp_async16(kd + dst_off[i], ks + 512 * i, 16);
+        cp_async16(vd + dst_off[i], vs + 512 * i, 16);
+      }
+    } else {  // ragged tail: rows past N are zero-filled
+#pragma unroll
+      for (int i = 0; i < GT * Cfg::CHUNKS_PER_ROW / 32; ++i) {
+        const int row = (lane + 32 * i) / Cfg::CHUNKS_PER_ROW;
+        const bool ok = (tok0 + row) < N;
+        cp_async16(kd + dst_off[i], ok ? ks + 512 * i : reinterpret_cast<const unsigned char*>(kimg), ok ? 16 : 0);
+        cp_async16(vd + dst_off[i], ok ? vs + 512 * i : reinterpret_cast<const unsigned char*>(vimg), ok ? 16 : 0);
+      }
     }
   };
 
@@ -207,7 +244,7 @@ __global__ void __launch_bounds__(TcCfg<D, KP, NWT>::NT, 1) sa_iter_fwd_tc_kerne
       for (int mt = 0; mt < NKS; ++mt)
 #pragma unroll
         for (int i = 0; i < 4; ++i) UT[sl][mt][i] = 0.f;
-    float Sl[NSL] = {};  // sum of the (bf16-rounded) weights of slot 8*sl + g8 seen by this lane
+    float Sl[KP] = {};  // lanes 0-15: sum over this lane's tokens of the (bf16-rounded) weights of every slot
     {
       uint32_t qa[NKS][4];  // A fragments of q (16 slot rows x D)
       {
@@ -218,6 +255,8 @@ __global__ void __launch_bounds__(TcCfg<D, KP, NWT>::NT, 1) sa_iter_fwd_tc_kerne
       }
       // per-lane byte offset inside a k / v tile for the x4 loads (same for both operands)
       const int frag_off = ((lane & 7) + (lane >> 4) * 8) * PITCH + ((lane >> 3) & 1) * 16;
+      const int frag_off8 = (lane & 7) * PITCH + ((lane >> 3) & 1) * 16;  // x2 loads of an 8-token tile
+      (void)frag_off; (void)frag_off8;
 
       for (int p = 0; p < STAGES - 1; ++p) {
         if (p < warp_groups) issue(p, p % STAGES);
@@ -229,91 +268,105 @@ __global__ void __launch_bounds__(TcCfg<D, KP, NWT>::NT, 1) sa_iter_fwd_tc_kerne
           if (nxt < warp_groups) issue(nxt, nxt % STAGES);
           cp_async_commit();
         }
+        const bool ptrace = (a.trace != nullptr && blockIdx.x == 0 && tid == 0 && t == 0 && lg < 6);
+        if (ptrace) a.trace[128 + lg * 5 + 0] = clock64();
         cp_async_wait<STAGES - 1>();
         __syncwarp();
+        if (ptrace) a.trace[128 + lg * 5 + 1] = clock64();
         const unsigned char* kb = my_ring + (size_t)(lg % STAGES) * Cfg::STAGE_BYTES;
         const unsigned char* vb = kb + Cfg::TILE_BYTES;
         const int tok0 = (g_begin + warp + lg * NPW) * GT;
 
-        // logits^T: two 8-token blocks, two interleaved accumulator chains each for ILP
-        float lgA[2][4] = {}, lgB[2][4] = {};
+        // logits^T: 8-token blocks (two per 16-token group), four interleaved accumulator chains for ILP
+        constexpr int NBLK = GT / 8;
+        float lgc[4][NBLK][4] = {};
 #pragma unroll
         for (int ks = 0; ks < NKS; ++ks) {
-          uint32_t kf[4];
-          ldmatrix_x4(kf, kb + frag_off + ks * 32);
-          if (ks & 1) {
-            mma_bf16_16816(lgB[0], qa[ks], kf[0], kf[1]);
-            mma_bf16_16816(lgB[1], qa[ks], kf[2], kf[3]);
+          if constexpr (GT == 16) {
+            uint32_t kf[4];
+            ldmatrix_x4(kf, kb + frag_off + ks * 32);
+            mma_bf16_16816(lgc[ks & 3][0], qa[ks], kf[0], kf[1]);
+            mma_bf16_16816(lgc[ks & 3][1], qa[ks], kf[2], kf[3]);
           } else {
-            mma_bf16_16816(lgA[0], qa[ks], kf[0], kf[1]);
-            mma_bf16_16816(lgA[1], qa[ks], kf[2], kf[3]);
+            uint32_t kf[2];
+            ldmatrix_x2(kf, kb + frag_off8 + ks * 32);
+            mma_bf16_16816(lgc[ks & 3][0], qa[ks], kf[0], kf[1]);
           }
         }
-        // K-way softmax over the slot axis (rows of the fragment): lanes with equal t4 hold a column
-        uint32_t wb[NSL][2];  // B fragments of w^T for the U^T product: [slot tile][token half]
+        if (ptrace) a.trace[128 + lg * 5 + 2] = clock64();
+        // K-way softmax over the slot axis.  The accumulator fragments are transposed through a small
+        // per-warp scratch so that one lane owns one token: max / exp / sum need no shuffles.
 #pragma unroll
-        for (int nb = 0; nb < 2; ++nb) {
+        for (int nb = 0; nb < NBLK; ++nb) {
           float x[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) x[i] = lgA[nb][i] + lgB[nb][i];
-          const bool lo_ok = g8 < K, hi_ok = (NSL > 1) && (g8 + 8 < K);
-          float m0 = lo_ok ? x[0] : -INFINITY, m1 = lo_ok ? x[1] : -INFINITY;
-          if (hi_ok) { m0 = fmaxf(m0, x[2]); m1 = fmaxf(m1, x[3]); }
-#pragma unroll
-          for (int o = 4; o < 32; o <<= 1) {
-            m0 = fmaxf(m0, __shfl_xor_sync(FULL, m0, o));
-            m1 = fmaxf(m1, __shfl_xor_sync(FULL, m1, o));
-          }
-          float e[4];
-          e[0] = lo_ok ? __expf(x[0] - m0) : 0.f;
-          e[1] = lo_ok ? __expf(x[1] - m1) : 0.f;
-          e[2] = hi_ok ? __expf(x[2] - m0) : 0.f;
-          e[3] = hi_ok ? __expf(x[3] - m1) : 0.f;
-          float s0 = e[0] + e[2], s1 = e[1] + e[3];
-#pragma unroll
-          for (int o = 4; o < 32; o <<= 1) {
-            s0 += __shfl_xor_sync(FULL, s0, o);
-            s1 += __shfl_xor_sync(FULL, s1, o);
-          }
-          const float i0 = 1.f / s0, i1 = 1.f / s1;
-          const int tk0 = tok0 + nb * 8 + 2 * t4;  // tokens of this lane's two columns
-          const bool v0 = tk0 < N, v1 = (tk0 + 1) < N;
-          float av[4] = {e[0] * i0, e[1] * i1, e[2] * i0, e[3] * i1};
-          if (last && a.attn_out) {
-            float* ao = a.attn_out + ((size_t)img * N + tk0) * K;
-            if (lo_ok) {
-              if (v0) ao[g8] = av[0];
-              if (v1) ao[K + g8] = av[1];
-            }
-            if (hi_ok) {
-              if (v0) ao[g8 + 8] = av[2];
-              if (v1) ao[K + g8 + 8] = av[3];
-            }
-          }
-          // weights a + eps, rounded to bf16 once and used for both the numerator and the token sum
-          const __nv_bfloat162 wlo = __floats2bfloat162_rn((lo_ok && v0) ? av[0] + a.eps : 0.f,
-                                                          (lo_ok && v1) ? av[1] + a.eps : 0.f);
-          wb[0][nb] = *reinterpret_cast<const uint32_t*>(&wlo);
-          Sl[0] += __low2float(wlo) + __high2float(wlo);
+          for (int i = 0; i < 4; ++i) x[i] = (lgc[0][nb][i] + lgc[1][nb][i]) + (lgc[2][nb][i] + lgc[3][nb][i]);
+          const int tk = nb * 8 + 2 * t4;
+          my_lg[tk * KP + g8] = x[0];
+          my_lg[(tk + 1) * KP + g8] = x[1];
           if constexpr (NSL > 1) {
-            const __nv_bfloat162 whi = __floats2bfloat162_rn((hi_ok && v0) ? av[2] + a.eps : 0.f,
-                                                            (hi_ok && v1) ? av[3] + a.eps : 0.f);
-            wb[1][nb] = *reinterpret_cast<const uint32_t*>(&whi);
-            Sl[1] += __low2float(whi) + __high2float(whi);
+            my_lg[tk * KP + g8 + 8] = x[2];
+            my_lg[(tk + 1) * KP + g8 + 8] = x[3];
           }
         }
+        __syncwarp();
+        if (lane < GT) {
+          float l[KP];
+#pragma unroll
+          for (int j4 = 0; j4 < KP / 4; ++j4) {
+            const float4 v4 = *reinterpret_cast<const float4*>(my_lg + lane * KP + 4 * j4);
+            l[4 * j4] = v4.x; l[4 * j4 + 1] = v4.y; l[4 * j4 + 2] = v4.z; l[4 * j4 + 3] = v4.w;
+          }
+          float m = l[0];
+#pragma unroll
+          for (int j = 1; j < KP; ++j) m = (j < K) ? fmaxf(m, l[j]) : m;
+          float sum = 0.f;
+#pragma unroll
+          for (int j = 0; j < KP; ++j) {
+            l[j] = (j < K) ? __expf(l[j] - m) : 0.f;
+            sum += l[j];
+          }
+          const float inv = __fdividef(1.f, sum);
+          const bool tok_ok = (tok0 + lane) < N;
+          float* ao = (last && a.attn_out && tok_ok) ? a.attn_out + ((size_t)img * N + tok0 + lane) * K : nullptr;
+#pragma unroll
+          for (int j = 0; j < KP; ++j) {
+            const float av = l[j] * inv;
+            if (ao != nullptr && j < K) ao[j] = av;
+            // weight a + eps, rounded to bf16 once and used for both the numerator and the token sum
+            const bf16 wq = __float2bfloat16_rn((tok_ok && j < K) ? av + a.eps : 0.f);
+            my_wb[j * GT + lane] = wq;
+            Sl[j] += __bfloat162float(wq);
+          }
+        }
+        __syncwarp();
+        uint32_t wb[NSL][2];  // B fragments of w^T for the U^T product: [slot tile][token half]
+#pragma unroll
+        for (int sl = 0; sl < NSL; ++sl) {
+          wb[sl][0] = *reinterpret_cast<const uint32_t*>(my_wb + (8 * sl + g8) * GT + 2 * t4);
+          wb[sl][1] = (GT == 16) ? *reinterpret_cast<const uint32_t*>(my_wb + (8 * sl + g8) * GT + (GT - 8) + 2 * t4) : 0u;
+        }
+        if (ptrace) a.trace[128 + lg * 5 + 3] = clock64();
         // U^T += v_tile^T . w^T
 #pragma unroll
         for (int mt = 0; mt < NKS; ++mt) {
-          uint32_t vf[4];
-          ldmatrix_x4_trans(vf, vb + frag_off + mt * 32);
-          // ldmatrix order: [tok 0-7, d 0-7], [tok 0-7, d 8-15], [tok 8-15, d 0-7], [tok 8-15, d 8-15]
-          // mma A order:    a0 = (d 0-7, tok 0-7), a1 = (d 8-15, tok 0-7), a2 = (d 0-7, tok 8-15), a3 = (d 8-15, tok 8-15)
-          const uint32_t af[4] = {vf[0], vf[1], vf[2], vf[3]};
+          if constexpr (GT == 16) {
+            uint32_t vf[4];
+            ldmatrix_x4_trans(vf, vb + frag_off + mt * 32);
+            // ldmatrix order: [tok 0-7, d 0-7], [tok 0-7, d 8-15], [tok 8-15, d 0-7], [tok 8-15, d 8-15]
+            // mma A order:    a0 = (d 0-7, tok 0-7), a1 = (d 8-15, tok 0-7), a2 = (d 0-7, tok 8-15), a3 = (d 8-15, tok 8-15)
+            const uint32_t af[4] = {vf[0], vf[1], vf[2], vf[3]};
 #pragma unroll
-          for (int sl = 0; sl < NSL; ++sl) mma_bf16_16816(UT[sl][mt], af, wb[sl][0], wb[sl][1]);
+            for (int sl = 0; sl < NSL; ++sl) mma_bf16_16816(UT[sl][mt], af, wb[sl][0], wb[sl][1]);
+          } else {
+            uint32_t vf[2];  // [tok 0-7, d 0-7], [tok 0-7, d 8-15]: the k = 8 form of the MMA
+            ldmatrix_x2_trans(vf, vb + frag_off8 + mt * 32);
+#pragma unroll
+            for (int sl = 0; sl < NSL; ++sl) mma_bf16_1688(UT[sl][mt], vf[0], vf[1], wb[sl][0]);
+          }
         }
         __syncwarp();  // every lane is done with this stage before it is refilled
+        if (ptrace) a.trace[128 + lg * 5 + 4] = clock64();
       }
       cp_async_wait<0>();
     }
@@ -334,11 +387,11 @@ __global__ void __launch_bounds__(TcCfg<D, KP, NWT>::NT, 1) sa_iter_fwd_tc_kerne
         u[(s0 + 1) * D + d0 + 8] = UT[sl][mt][3];
       }
 #pragma unroll
-    for (int sl = 0; sl < NSL; ++sl) {
-      float s = Sl[sl];
-      s += __shfl_xor_sync(FULL, s, 1);
-      s += __shfl_xor_sync(FULL, s, 2);
-      if (t4 == 0) sred[warp * KP + sl * 8 + g8] = s;
+    for (int j = 0; j < KP; ++j) {
+      float s = Sl[j];
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+      if (lane == 0) sred[warp * KP + j] = s;
     }
     }
     __syncthreads();  // partial sums visible; every warp is done with the ring
@@ -394,7 +447,14 @@ __global__ void __launch_bounds__(TcCfg<D, KP, NWT>::NT, 1) sa_iter_fwd_tc_kerne
       DotDesc d;
       d.vec0 = upd_full; d.vec1 = s_prev; d.out0 = gates;
       d.njobs = 6; d.split = 3; d.split_mod = 3; d.nrows = DS; d.out_stride = KP * DS; d.ldo = DS;
-      if (w_smem) {
+      if (use_mma) {
+        stage_vec_hilo(upd_full, K, KP, D, vst0h, vst0l, LP, tid, NT);
+        stage_vec_hilo(s_prev, K, KP, D, vst1h, vst1l, LP, tid, NT);
+        __syncthreads();
+        rows_mma_jobs<KP, D / 32>(wb_ih, rank * DS, D, 3, DS, vst0h, vst0l, LP, gates, KP * DS, DS, warp, lane, NW);
+        rows_mma_jobs<KP, D / 32>(wb_hh, rank * DS, D, 3, DS, vst1h, vst1l, LP, gates + 3 * KP * DS, KP * DS, DS,
+                                  (warp + 4) % NW, lane, NW);
+      } else if (w_smem) {
         mbar_wait(&wbar[0], (uint32_t)(t & 1));
         d.W0 = ws_gru; d.W1 = ws_gru + 3 * gru_floats; d.row_base = 0; d.row_stride = DS;
         rows_dot_desc<KP, RB, NC, 2, false>(d, warp, lane, NW);
@@ -442,7 +502,11 @@ __global__ void __launch_bounds__(TcCfg<D, KP, NWT>::NT, 1) sa_iter_fwd_tc_kerne
       DotDesc d;
       d.vec0 = d.vec1 = lnb; d.out0 = gates;
       d.njobs = 1; d.split = 1; d.split_mod = 1; d.row_stride = 0; d.nrows = HS; d.out_stride = 0; d.ldo = HS;
-      if (w_smem) {
+      if (use_mma) {
+        stage_vec_hilo(lnb, K, KP, D, vst0h, vst0l, LP, tid, NT);
+        __syncthreads();
+        rows_mma_jobs<KP, D / 32>(wb_1, rank * HS, 0, 1, HS, vst0h, vst0l, LP, gates, 0, HS, warp, lane, NW);
+      } else if (w_smem) {
         mbar_wait(&wbar[1], (uint32_t)(t & 1));
         d.W0 = d.W1 = ws_w1; d.row_base = 0;
         rows_dot_desc<KP, RB, NC, 2, false>(d, warp, lane, NW);
@@ -465,7 +529,11 @@ __global__ void __launch_bounds__(TcCfg<D, KP, NWT>::NT, 1) sa_iter_fwd_tc_kerne
       DotDesc d;
       d.vec0 = d.vec1 = hid_full; d.out0 = gates;
       d.njobs = 1; d.split = 1; d.split_mod = 1; d.row_stride = 0; d.nrows = DS; d.out_stride = 0; d.ldo = DS;
-      if (w_smem) {
+      if (use_mma) {
+        stage_vec_hilo(hid_full, K, KP, H, vst0h, vst0l, LP, tid, NT);
+        __syncthreads();
+        rows_mma_jobs_len<KP>(H, wb_2, rank * DS, 0, 1, DS, vst0h, vst0l, LP, gates, 0, DS, warp, lane, NW);
+      } else if (w_smem) {
         mbar_wait(&wbar[2], (uint32_t)(t & 1));
         d.W0 = d.W1 = ws_w2; d.row_base = 0;
         rows_dot_desc_len<KP, RB, 2, false>(d, H, warp, lane, NW);
@@ -491,9 +559,9 @@ __global__ void __launch_bounds__(TcCfg<D, KP, NWT>::NT, 1) sa_iter_fwd_tc_kerne
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <int D, int KP, int NWT>
+template <int D, int KP, int NWT, int GTT>
 static size_t tc_smem_bytes(int H, int CL) {
-  using Cfg = TcCfg<D, KP, NWT>;
+  using Cfg = TcCfg<D, KP, NWT, GTT>;
   const size_t ring_bytes = (size_t)Cfg::NPW * Cfg::STAGES * Cfg::STAGE_BYTES;
   const size_t ured_bytes = (size_t)Cfg::NPW * KP * D * sizeof(float);
   const int LMAX = D > H ? D : H;
@@ -506,11 +574,11 @@ static size_t tc_smem_bytes(int H, int CL) {
   return b + 128;
 }
 
-template <int D, int KP, int NWT>
+template <int D, int KP, int NWT, int GTT>
 static int launch_tc(const IterFwdArgs& a, cudaStream_t stream) {
-  using Cfg = TcCfg<D, KP, NWT>;
-  auto kern = sa_iter_fwd_tc_kernel<D, KP, NWT>;
-  const size_t smem = tc_smem_bytes<D, KP, NWT>(a.H, a.CL);
+  using Cfg = TcCfg<D, KP, NWT, GTT>;
+  auto kern = sa_iter_fwd_tc_kernel<D, KP, NWT, GTT>;
+  const size_t smem = tc_smem_bytes<D, KP, NWT, GTT>(a.H, a.CL);
   if (smem > 227 * 1024) {
     set_error("sa_iter_fwd(tensor): shared memory %zu B exceeds 227 KB (D=%d K=%d H=%d)", smem, D, a.K, a.H);
     return OCRL_E_SHAPE;
@@ -535,9 +603,45 @@ static int launch_tc(const IterFwdArgs& a, cudaStream_t stream) {
 
 template <int D>
 static int tc_dispatch_k(const IterFwdArgs& a, cudaStream_t s) {
-  constexpr int NW = (D >= 192) ? 4 : 8;  // token-pass warps: ring = NPW * stages * 2 * 16 * (2D+16) bytes
-  if (a.K <= 8) return launch_tc<D, 8, NW>(a, s);
-  return launch_tc<D, 16, NW>(a, s);
+  // token-pass warps x tokens per group: ring = NPW * stages * 2 * GT * (2D+16) bytes.  Eight warps on
+  // 8-token groups hide the in-order latencies of the softmax / MMA chain better than four on 16.
+  const char* e = getenv("OCRL_SA_GT");
+  const int gt = e ? atoi(e) : 16;
+  if (D >= 192) {
+    if (a.K <= 8) return gt == 16 ? launch_tc<D, 8, 4, 16>(a, s) : launch_tc<D, 8, 8, 8>(a, s);
+    return launch_tc<D, 16, 4, 16>(a, s);
+  } else {
+    if (a.K <= 8) return launch_tc<D, 8, 8, 16>(a, s);
+    return launch_tc<D, 16, 8, 16>(a, s);
+  }
+}
+
+// fp32 -> bf16 copies of the slot-update weights, laid out [wq | w_ih | w_hh | w1 | w2]
+__global__ void iter_tc_prep_kernel(ocrl_sa_weights w, __nv_bfloat16* out, int D, int H) {
+  const int n_q = D * D, n_g = 3 * D * D, n_1 = H * D;
+  const int total = n_q + 2 * n_g + 2 * n_1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    float v;
+    if (i < n_q) v = w.wq[i];
+    else if (i < n_q + n_g) v = w.w_ih[i - n_q];
+    else if (i < n_q + 2 * n_g) v = w.w_hh[i - n_q - n_g];
+    else if (i < n_q + 2 * n_g + n_1) v = w.w1[i - n_q - 2 * n_g];
+    else v = w.w2[i - n_q - 2 * n_g - n_1];
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+size_t sa_iter_tc_workspace(const ocrl_sa_dims* d) {
+  return sizeof(__nv_bfloat16) * ((size_t)7 * d->D * d->D + (size_t)2 * d->H_mlp * d->D) + 256 + 4096;
+}
+
+// converts the weights into `workspace`; returns the bf16 pointer (256-byte aligned) or null
+const __nv_bfloat16* sa_iter_tc_prepare(const ocrl_sa_dims* d, const ocrl_sa_weights* w, void* workspace,
+                                        cudaStream_t stream) {
+  if (workspace == nullptr) return nullptr;
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+  iter_tc_prep_kernel<<<148, 256, 0, stream>>>(*w, out, d->D, d->H_mlp);
+  return out;
 }
 
 int sa_iter_fwd_tc_dispatch(const IterFwdArgs& a, cudaStream_t s) {

@@ -33,6 +33,7 @@ struct IterFwdArgs {
   int B, N, D, H, K, T, CL;
   float eps, ln_eps;
   long long* trace;  // optional: clock64() at phase boundaries of CTA 0 (development aid), else null
+  const __nv_bfloat16* wb16;  // optional bf16 copies [wq | w_ih | w_hh | w1 | w2] for the tensor-core slot update
 };
 
 // out[j*ldo + out_off + row] = dot(W[row0+row, 0:L], vec[j, 0:L]) for row < nrows, j < KP.
@@ -259,6 +260,113 @@ __device__ __forceinline__ void ln_rows_fast(const float* src, const float* gw_s
       *reinterpret_cast<float2*>(dst + j * D + 64 * c + 2 * lane) =
           make_float2(x[c].x * rstd * g.x + b.x, x[c].y * rstd * g.y + b.y);
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tensor-core form of the slot-update matvecs (bf16 mode).
+//   out[j][row] = sum_l W[row][l] * vec[j][l]      W: bf16 in global memory (L2-resident), 16 rows per MMA
+//   vec is given as a bf16 hi/lo pair (hi + lo reproduces the fp32 value to ~2^-17), so only the weights
+//   carry bf16 rounding.  A fragments are 128-bit global loads (the contraction index is permuted so that a
+//   lane's 8 consecutive weights feed two k16 steps), B fragments are hoisted for the whole call.
+// Jobs are flattened over the warps: job u covers rows [row_base + u*row_stride, +nrows), writes
+// out0 + u*out_job_stride.  vhi / vlo: shared memory [KP][LP] bf16 (rows >= K zero).
+// ---------------------------------------------------------------------------------------------
+template <int KP, int NCH32>
+__device__ __noinline__ void rows_mma_jobs(const __nv_bfloat16* __restrict__ W, int row_base, int row_stride,
+                                              int njobs, int nrows, const __nv_bfloat16* vhi,
+                                              const __nv_bfloat16* vlo, int LP, float* out0, int out_job_stride,
+                                              int ldo, int warp, int lane, int nwarps) {
+  constexpr int L = 32 * NCH32, NSL = KP / 8;
+  const int g8 = lane >> 2, t4 = lane & 3;
+  uint2 bh[NSL][NCH32][2], bl[NSL][NCH32][2];
+#pragma unroll
+  for (int sl = 0; sl < NSL; ++sl)
+#pragma unroll
+    for (int c = 0; c < NCH32; ++c)
+#pragma unroll
+      for (int st = 0; st < 2; ++st) {
+        const int off = (8 * sl + g8) * LP + 32 * c + 8 * t4 + 4 * st;
+        bh[sl][c][st] = *reinterpret_cast<const uint2*>(vhi + off);
+        bl[sl][c][st] = *reinterpret_cast<const uint2*>(vlo + off);
+      }
+  const int tpj = (nrows + 15) / 16;
+  const int total = njobs * tpj;
+  uint4 a0[NCH32], a1[NCH32];
+  auto load_tile = [&](int u, uint4(&x0)[NCH32], uint4(&x1)[NCH32]) {
+    const int job = u / tpj, mt = u % tpj;
+    const int r0 = min(mt * 16 + g8, nrows - 1), r1 = min(mt * 16 + g8 + 8, nrows - 1);
+    const __nv_bfloat16* base = W + (size_t)(row_base + job * row_stride) * L + 8 * t4;
+#pragma unroll
+    for (int c = 0; c < NCH32; ++c) {
+      x0[c] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)r0 * L + 32 * c));
+      x1[c] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)r1 * L + 32 * c));
+    }
+  };
+  int u = warp;
+  if (u < total) load_tile(u, a0, a1);
+#pragma unroll 1
+  for (; u < total; u += nwarps) {
+    uint4 n0[NCH32], n1[NCH32];
+    const bool more = (u + nwarps) < total;
+    if (more) load_tile(u + nwarps, n0, n1);
+    float acc[NSL][4];
+#pragma unroll
+    for (int sl = 0; sl < NSL; ++sl)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[sl][i] = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH32; ++c) {
+      const uint32_t f0[4] = {a0[c].x, a1[c].x, a0[c].y, a1[c].y};
+      const uint32_t f1[4] = {a0[c].z, a1[c].z, a0[c].w, a1[c].w};
+#pragma unroll
+      for (int sl = 0; sl < NSL; ++sl) {
+        mma_bf16_16816(acc[sl], f0, bh[sl][c][0].x, bh[sl][c][0].y);
+        mma_bf16_16816(acc[sl], f0, bl[sl][c][0].x, bl[sl][c][0].y);
+        mma_bf16_16816(acc[sl], f1, bh[sl][c][1].x, bh[sl][c][1].y);
+        mma_bf16_16816(acc[sl], f1, bl[sl][c][1].x, bl[sl][c][1].y);
+      }
+    }
+    const int job = u / tpj, mt = u % tpj;
+    float* out = out0 + job * out_job_stride;
+    const int r0 = mt * 16 + g8, r1 = r0 + 8;
+#pragma unroll
+    for (int sl = 0; sl < NSL; ++sl) {
+      const int j0 = 8 * sl + 2 * t4;
+      if (r0 < nrows) { out[j0 * ldo + r0] = acc[sl][0]; out[(j0 + 1) * ldo + r0] = acc[sl][1]; }
+      if (r1 < nrows) { out[j0 * ldo + r1] = acc[sl][2]; out[(j0 + 1) * ldo + r1] = acc[sl][3]; }
+    }
+    if (more) {
+#pragma unroll
+      for (int c = 0; c < NCH32; ++c) { a0[c] = n0[c]; a1[c] = n1[c]; }
+    }
+  }
+}
+
+template <int KP>
+__device__ __forceinline__ void rows_mma_jobs_len(int L, const __nv_bfloat16* W, int row_base, int row_stride, int njobs,
+                                                  int nrows, const __nv_bfloat16* vhi, const __nv_bfloat16* vlo, int LP,
+                                                  float* out0, int out_job_stride, int ldo, int warp, int lane,
+                                                  int nwarps) {
+  switch (L / 32) {
+    case 2: rows_mma_jobs<KP, 2>(W, row_base, row_stride, njobs, nrows, vhi, vlo, LP, out0, out_job_stride, ldo, warp, lane, nwarps); break;
+    case 4: rows_mma_jobs<KP, 4>(W, row_base, row_stride, njobs, nrows, vhi, vlo, LP, out0, out_job_stride, ldo, warp, lane, nwarps); break;
+    case 6: rows_mma_jobs<KP, 6>(W, row_base, row_stride, njobs, nrows, vhi, vlo, LP, out0, out_job_stride, ldo, warp, lane, nwarps); break;
+    default: rows_mma_jobs<KP, 8>(W, row_base, row_stride, njobs, nrows, vhi, vlo, LP, out0, out_job_stride, ldo, warp, lane, nwarps); break;
+  }
+}
+
+// fp32 vectors [K][L] in shared memory -> bf16 hi / lo pair [KP][LP] (rows >= K zero)
+__device__ __forceinline__ void stage_vec_hilo(const float* src, int K, int KPr, int L, __nv_bfloat16* hi,
+                                               __nv_bfloat16* lo, int LP, int tid, int nthreads) {
+  for (int e = tid; e < KPr * (L / 2); e += nthreads) {
+    const int j = e / (L / 2), l2 = e % (L / 2);
+    float2 x = make_float2(0.f, 0.f);
+    if (j < K) x = *reinterpret_cast<const float2*>(src + j * L + 2 * l2);
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x.x, x.y);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(x.x - __low2float(h), x.y - __high2float(h));
+    *reinterpret_cast<__nv_bfloat162*>(hi + j * LP + 2 * l2) = h;
+    *reinterpret_cast<__nv_bfloat162*>(lo + j * LP + 2 * l2) = l;
   }
 }
 

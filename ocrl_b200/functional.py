@@ -149,6 +149,9 @@ def iterate(k: Tensor, v: Tensor, slots0: Tensor, p: Dict[str, Tensor], num_iter
         _, _, saved_bytes = abi.query_workspace(dims)
         saved = torch.empty(saved_bytes // 4, device=k.device, dtype=torch.float32)
     w = _sa_weights(pw)
+    if _workspace is None and dims.math_mode == abi.MATH_TENSOR:  # bf16 weight copies for the tensor-core slot update
+        fwd_ws, _, _ = abi.query_workspace(dims)
+        _workspace = torch.empty(fwd_ws, device=k.device, dtype=torch.uint8)
     with _timed("sa_iter_fwd"):
         abi.check(abi.lib().ocrl_sa_iter_fwd(ctypes.byref(dims), abi.ptr(k), abi.ptr(v), abi.ptr(slots0),
                                              ctypes.byref(w), abi.ptr(slots), abi.ptr(attn), abi.ptr(saved),
