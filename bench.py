@@ -270,7 +270,7 @@ def roofline_of(a, mode, events):
     tk_avg = sum(tk_ms) / max(1, len(tk_ms))
     achieved = a.batch * bytes_img / (it_avg * 1e-3) / 1e9 if it_ms else None
     tok_achieved = a.batch * tok_bytes_img / (tk_avg * 1e-3) / 1e9 if tk_ms else None
-    return {"kernel": "sa_iter_fwd_tc_kernel (mma.sync bf16)" if mode == "bf16" else "sa_iter_fwd_kernel (fp32 FFMA)",
+    return {"kernel": "sa_iter_fwd_pipe_kernel (two-engine persistent clusters, TMA ring, mma.sync bf16)" if mode == "bf16" else "sa_iter_fwd_kernel (fp32 FFMA)",
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": (achieved / peak if achieved else None), "traffic": None, "peak_source": peak_src,
             "algorithmic_bytes_per_image": bytes_img, "avg_launch_ms": it_avg, "launches_timed": len(it_ms),

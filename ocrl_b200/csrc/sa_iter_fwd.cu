@@ -10,6 +10,7 @@ extern template int sa_iter_fwd_dispatch<float>(const IterFwdArgs&, cudaStream_t
 extern template int sa_iter_fwd_dispatch<__nv_bfloat16>(const IterFwdArgs&, cudaStream_t);
 int sa_iter_fwd_tc_dispatch(const IterFwdArgs& a, cudaStream_t s);
 int sa_iter_fwd_pc_dispatch(const IterFwdArgs& a, cudaStream_t s);
+int sa_iter_fwd_pipe_dispatch(const IterFwdArgs& a, cudaStream_t s);
 size_t sa_iter_tc_workspace(const ocrl_sa_dims* d);
 const __nv_bfloat16* sa_iter_tc_prepare(const ocrl_sa_dims* d, const ocrl_sa_weights* w, void* workspace,
                                         cudaStream_t stream);
@@ -30,6 +31,12 @@ int sa_iter_fwd_launch(const ocrl_sa_dims* d, const void* k, const void* v, cons
   if (d->kv_dtype == OCRL_DT_BF16) {
     if (d->math_mode == OCRL_MATH_TENSOR) {
       // persistent clusters with weight-stationary slot update (K <= 8, inference); OCRL_SA_PC=-1 disables
+      // two-engine pipeline (pass of one image under the slot update of another); OCRL_SA_PIPE=-1 disables
+      const char* ppv = getenv("OCRL_SA_PIPE");
+      if (ppv == nullptr || atoi(ppv) >= 0) {
+        const int rc = sa_iter_fwd_pipe_dispatch(a, stream);
+        if (rc != OCRL_E_SHAPE) return rc;
+      }
       const char* pcv = getenv("OCRL_SA_PC");
       if (pcv == nullptr || atoi(pcv) >= 0) {
         const int rc = sa_iter_fwd_pc_dispatch(a, stream);

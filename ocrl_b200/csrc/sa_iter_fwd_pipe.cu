@@ -1,0 +1,761 @@
+// Two-engine persistent-cluster form of the fused T-iteration loop (slot_attn.py:64-102) for bf16 k/v.
+//
+// A cluster of CL CTAs works on TWO images at a time ("lanes").  Every CTA runs
+//   * a PASS engine  (warps 0-7: 4 logit warps + 4 U warps) that streams k/v tiles of its token share through a
+//     TMA ring and produces the partial sum_n w v and sum_n w of one (image, iteration), and
+//   * an UPDATE engine (warps 8-15) that runs the slot update of the other lane: reduce-scatter over the
+//     cluster, GRU, residual MLP, next q -- six DSMEM exchange rounds with tensor-core matrix-vector products
+//     against the CTA's weight slice, which stays in shared memory for the whole kernel.
+// The engines alternate lanes (pass A0 | pass B0 + update A0 | pass A1 + update B0 | ...), so the
+// latency-bound update of one image hides behind the bandwidth-bound pass of the other and the ring never
+// drains: tiles of the next pass are already in flight when a pass ends.  Hand-offs are shared-memory
+// mbarriers (u_ready / u_free / q_ready); the cluster exchange is st.async + complete_tx, double-buffered
+// by round parity (see pc_common.cuh / sa_iter_fwd_pc.cu for the single-engine form and the protocol).
+// Only 2 * (#clusters) images are in flight, so passes 2..T read k/v from L2.
+#include "pc_common.cuh"
+
+namespace ocrl {
+namespace pipe {
+
+using namespace pc;
+
+#ifndef TRACE_OP
+#define TRACE_OP 2
+#endif
+
+template <int D_, int H_, int CL_, int S_>
+struct Cfg {
+  static constexpr int D = D_, H = H_, CL = CL_, S = S_;
+  static constexpr int KP = 8, NT = 512, TOK = 16;
+  static constexpr int PITCH = D * 2 + 16, PITCHH = H * 2 + 16;
+  static constexpr int LX = D > H ? D : H;
+  static constexpr int PITCHX = LX * 2 + 16;
+  static constexpr int TILE_BYTES = TOK * D * 2, STAGE_BYTES = 2 * TILE_BYTES, WT_BYTES = 256;
+  static constexpr int DS = D / CL, HS = H / CL;
+  static constexpr int NMU = D / 16, NMG = (3 * DS + 15) / 16, NM1 = (HS + 15) / 16, NM2 = (DS + 15) / 16, NKC = 4;
+  static constexpr int UP = D + 4;
+  static_assert(D % 64 == 0 && H % 64 == 0 && DS % 4 == 0 && HS % 4 == 0, "shape");
+  static_assert(TILE_BYTES % 1024 == 0, "swizzle atoms are 1024 bytes");
+
+  static constexpr int OFF_RING = 0;
+  static constexpr int OFF_WT = OFF_RING + S * STAGE_BYTES;
+  static constexpr int OFF_WIH = OFF_WT + S * WT_BYTES;
+  static constexpr int OFF_WHH = OFF_WIH + 3 * DS * PITCH;
+  static constexpr int OFF_W1 = OFF_WHH + 3 * DS * PITCH;
+  static constexpr int OFF_W2 = OFF_W1 + HS * PITCH;
+  static constexpr int OFF_WQ = OFF_W2 + DS * PITCHH;
+  static constexpr int OFF_ZROW = OFF_WQ + DS * PITCH;
+  static constexpr int OFF_LNP = OFF_ZROW + PITCHX;
+  static constexpr int OFF_BIAS = OFF_LNP + 4 * D * 4;
+  static constexpr int XBUF_BYTES = KP * LX * 4 + 32 * CL;
+  static constexpr int OFF_XBUF = (OFF_BIAS + (7 * DS + HS) * 4 + 15) & ~15;
+  static constexpr int OFF_ACT = OFF_XBUF + 2 * XBUF_BYTES;        // activation staging, bf16 (update engine)
+  static constexpr int P_ROWS = (2 * NMG > NKC * (NM1 > NM2 ? NM1 : NM2)) ? 2 * NMG * 16 : NKC * (NM1 > NM2 ? NM1 : NM2) * 16;
+  static constexpr int OFF_P = OFF_ACT + KP * PITCHX;              // MMA partial outputs
+  static constexpr int OFF_UST = OFF_P + P_ROWS * 32;              // U staging a, b (pass -> update hand-off)
+  static constexpr int OFF_SRED = OFF_UST + 2 * KP * UP * 4;       // [4][8] token sums of the logit warps
+  static constexpr int OFF_LANE = OFF_SRED + 128;                  // per lane: slots hi/lo, q (bf16), own slice (fp32)
+  static constexpr int LANE_BYTES = KP * PITCH + KP * PITCH + KP * DS * 4;
+  static constexpr int OFF_BAR = (OFF_LANE + 2 * LANE_BYTES + 15) & ~15;  // full[S] w_ready[S] xbar[2] u_ready u_free q_ready[2]
+  static constexpr int OFF_ISSUED = OFF_BAR + (2 * S + 6) * 8;
+  static constexpr int SMEM_BYTES = OFF_ISSUED + S * 4 + 1024;     // + slack for the manual 1024-byte alignment
+};
+
+__device__ __forceinline__ void upd_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+template <int D, int H, int CL, int S>
+__global__ void __launch_bounds__(512, 1)
+sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v) {
+  using C = Cfg<D, H, CL, S>;
+  constexpr int KP = C::KP, PITCH = C::PITCH, PITCHH = C::PITCHH, PITCHX = C::PITCHX, DS = C::DS, HS = C::HS;
+  constexpr int NMU = C::NMU, NMG = C::NMG, NM1 = C::NM1, NM2 = C::NM2, NKC = C::NKC, UP = C::UP, TOK = C::TOK;
+  constexpr float LOG2E = 1.4426950408889634f;
+
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int cid = blockIdx.x / CL, ncl = gridDim.x / CL;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g8 = lane >> 2, t4 = lane & 3;
+  const int K = a.K, N = a.N, T = a.T, B = a.B;
+  const bool tracer = (a.trace != nullptr && blockIdx.x == 0);
+#define PP_TRACE(i) do { if (tracer) a.trace[(i)] = clock64(); } while (0)
+
+  unsigned char* ring = sm + C::OFF_RING;
+  unsigned char* wtiles = sm + C::OFF_WT;
+  unsigned char* s_wih = sm + C::OFF_WIH;
+  unsigned char* s_whh = sm + C::OFF_WHH;
+  unsigned char* s_w1 = sm + C::OFF_W1;
+  unsigned char* s_w2 = sm + C::OFF_W2;
+  unsigned char* s_wq = sm + C::OFF_WQ;
+  unsigned char* s_zrow = sm + C::OFF_ZROW;
+  float* s_lnp = reinterpret_cast<float*>(sm + C::OFF_LNP);
+  float* s_bias = reinterpret_cast<float*>(sm + C::OFF_BIAS);
+  const float* s_bih = s_bias;
+  const float* s_bhh = s_bias + 3 * DS;
+  const float* s_b1 = s_bias + 6 * DS;
+  const float* s_b2 = s_bias + 6 * DS + HS;
+  unsigned char* xbuf = sm + C::OFF_XBUF;
+  unsigned char* act_hi = sm + C::OFF_ACT;
+  unsigned char* act_lo = nullptr;  // activations are single bf16 in this kernel (the legacy HMMA pipe is the scarce unit)
+  float* P = reinterpret_cast<float*>(sm + C::OFF_P);
+  float* ustage_a = reinterpret_cast<float*>(sm + C::OFF_UST);
+  float* ustage_b = ustage_a + KP * UP;
+  float* sred = reinterpret_cast<float*>(sm + C::OFF_SRED);
+  auto slh_hi = [&](int l) { return sm + C::OFF_LANE + l * C::LANE_BYTES; };
+  auto slh_lo = [&](int) { return (unsigned char*)nullptr; };
+  auto qbuf = [&](int l) { return sm + C::OFF_LANE + l * C::LANE_BYTES + KP * PITCH; };
+  auto own_of = [&](int l) { return reinterpret_cast<float*>(sm + C::OFF_LANE + l * C::LANE_BYTES + 2 * KP * PITCH); };
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
+  uint64_t* full = bars;
+  uint64_t* w_ready = bars + S;
+  uint64_t* xbar = bars + 2 * S;
+  uint64_t* u_ready = bars + 2 * S + 2;
+  uint64_t* u_free = bars + 2 * S + 3;
+  uint64_t* q_ready = bars + 2 * S + 4;
+  volatile int* issued = reinterpret_cast<volatile int*>(sm + C::OFF_ISSUED);
+
+  // ------------------------------------------------------------------ work assignment (two lanes per cluster)
+  const int G = ncl * 2;
+  int nimg[2];
+#pragma unroll
+  for (int l = 0; l < 2; ++l) {
+    const int gi = cid * 2 + l;
+    nimg[l] = (B > gi) ? (B - gi + G - 1) / G : 0;
+  }
+  const int nops0 = nimg[0] * T, nops1 = nimg[1] * T;  // nops0 >= nops1
+  const int total_ops = nops0 + nops1;
+  auto op_of = [&](int n, int& l, int& c) {
+    if (n < 2 * nops1) { l = n & 1; c = n >> 1; } else { l = 0; c = n - nops1; }
+  };
+  auto image_of = [&](int l, int m) { return B - 1 - ((cid * 2 + l) + m * G); };  // newest first (still in L2)
+  const int ntiles = (N + TOK - 1) / TOK;
+  const int TPC = (ntiles + CL - 1) / CL;
+  const int tile0 = rank * TPC;
+  const int TP = max(0, min(TPC, ntiles - tile0));
+
+  // one elected lane: stage (j % S) <- tile j = n * TP + tile of the CTA's tile sequence (pass ops in stream order)
+  auto issue_tile = [&](int n, int tile) {
+    const int j = n * TP + tile;
+    const int s = j % S;
+    int l, c;
+    op_of(n, l, c);
+    const int row0 = image_of(l, c / T) * N + (tile0 + tile) * TOK;
+    unsigned char* kd = ring + (size_t)s * C::STAGE_BYTES;
+    mbar_expect_tx(&full[s], (uint32_t)C::STAGE_BYTES);
+    tma_load_3d(kd, &tm_k, 0, 0, row0, &full[s]);
+    tma_load_3d(kd + C::TILE_BYTES, &tm_v, 0, 0, row0, &full[s]);
+    __threadfence_block();
+    issued[s] = j;
+  };
+  // tile (n, tile) + S in stream order, or n = -1 past the end
+  auto advance = [&](int& n, int& tile) {
+    tile += S;
+    while (tile >= TP) { tile -= TP; ++n; }
+    if (n >= total_ops) n = -1;
+  };
+
+  // ------------------------------------------------------------------ one-time setup
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&w_ready[s], 1);
+      issued[s] = -1;
+    }
+    mbar_init(&xbar[0], 1);
+    mbar_init(&xbar[1], 1);
+    mbar_init(u_ready, 8);
+    mbar_init(u_free, 8);
+    mbar_init(&q_ready[0], 1);
+    mbar_init(&q_ready[1], 1);
+    mbar_fence_init();
+    // first tiles: their HBM latency overlaps the weight load below
+    if (TP > 0)
+      for (int p = 0; p < S; ++p)
+        if (p / TP < total_ops) issue_tile(p / TP, p % TP);
+  }
+  {
+    // the CTA's weight slices, fp32 global -> bf16 shared; eight independent 16-byte loads in flight per thread
+    auto load_rows = [&](unsigned char* dst, int pitch, const float* src, int L, int nrows) {
+      const int total = nrows * (L / 4);
+      for (int i0 = tid; i0 < total; i0 += 8 * C::NT) {
+        float4 x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u * C::NT;
+          if (i < total) x[u] = __ldg(reinterpret_cast<const float4*>(src) + i);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u * C::NT;
+          if (i < total) {
+            const int r = i / (L / 4), c4 = i % (L / 4);
+            *reinterpret_cast<uint2*>(dst + r * pitch + 8 * c4) =
+                make_uint2(pack_bf16x2(x[u].x, x[u].y), pack_bf16x2(x[u].z, x[u].w));
+          }
+        }
+      }
+    };
+    for (int gate = 0; gate < 3; ++gate) {
+      load_rows(s_wih + gate * DS * PITCH, PITCH, a.w.w_ih + ((size_t)gate * D + rank * DS) * D, D, DS);
+      load_rows(s_whh + gate * DS * PITCH, PITCH, a.w.w_hh + ((size_t)gate * D + rank * DS) * D, D, DS);
+    }
+    load_rows(s_w1, PITCH, a.w.w1 + (size_t)rank * HS * D, D, HS);
+    load_rows(s_w2, PITCHH, a.w.w2 + (size_t)rank * DS * H, H, DS);
+    load_rows(s_wq, PITCH, a.w.wq + (size_t)rank * DS * D, D, DS);
+    for (int i = tid; i < PITCHX / 4; i += C::NT) reinterpret_cast<uint32_t*>(s_zrow)[i] = 0u;
+    for (int i = tid; i < D; i += C::NT) {
+      s_lnp[i] = a.w.ln_slots_w[i];
+      s_lnp[D + i] = a.w.ln_slots_b[i];
+      s_lnp[2 * D + i] = a.w.ln_mlp_w[i];
+      s_lnp[3 * D + i] = a.w.ln_mlp_b[i];
+    }
+    for (int i = tid; i < 3 * DS; i += C::NT) {
+      const int gate = i / DS, dl = i % DS;
+      s_bias[i] = a.w.b_ih[gate * D + rank * DS + dl];
+      s_bias[3 * DS + i] = a.w.b_hh[gate * D + rank * DS + dl];
+    }
+    for (int i = tid; i < HS; i += C::NT) s_bias[6 * DS + i] = a.w.b1[rank * HS + i];
+    for (int i = tid; i < DS; i += C::NT) s_bias[6 * DS + HS + i] = a.w.b2[rank * DS + i];
+    // staging rows of the padded slots are never written by the conversions; keep them finite
+    for (int i = tid; i < (KP * PITCHX) / 4; i += C::NT) reinterpret_cast<uint32_t*>(act_hi)[i] = 0u;
+    for (int i = tid; i < (2 * C::LANE_BYTES) / 4; i += C::NT) reinterpret_cast<uint32_t*>(sm + C::OFF_LANE)[i] = 0u;
+  }
+  __syncthreads();
+  cluster.sync();  // every CTA's barriers are initialised before any peer signals them
+  if (tid == 0) PP_TRACE(0);
+
+  if (warp < 8) {
+    // ==================================================================================== PASS ENGINE
+    for (int n = 0; n < total_ops; ++n) {
+      int l, c;
+      op_of(n, l, c);
+      const int t = c % T, img = image_of(l, c / T);
+      const bool last = (t == T - 1);
+      const int jbase = n * TP;
+      if (warp < 4) {
+        // ---- logit warp
+        mbar_wait(&q_ready[l], (uint32_t)(c & 1));
+        if (tid == 0 && n < 40) PP_TRACE(8 + n * 8);
+        const unsigned char* qsrc = qbuf(l);
+        uint32_t qb[D / 16][2];
+#pragma unroll
+        for (int ks = 0; ks < D / 16; ++ks) {
+          qb[ks][0] = *reinterpret_cast<const uint32_t*>(qsrc + g8 * PITCH + ks * 32 + 4 * t4);
+          qb[ks][1] = *reinterpret_cast<const uint32_t*>(qsrc + g8 * PITCH + ks * 32 + 16 + 4 * t4);
+        }
+        const int c0 = 2 * t4, c1 = 2 * t4 + 1;
+        const bool ok0 = c0 < K, ok1 = c1 < K;
+        float Sl0 = 0.f, Sl1 = 0.f;
+        const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lhalf = (lane >> 4) * 16;
+        for (int tile = warp; tile < TP; tile += 4) {
+          const int j = jbase + tile;
+          const int s = j % S;
+          const uint32_t ph = (uint32_t)((j / S) & 1);
+          const unsigned char* kt = ring + (size_t)s * C::STAGE_BYTES;
+          uint32_t* wt = reinterpret_cast<uint32_t*>(wtiles + s * C::WT_BYTES);
+          const bool tt = tracer && tid == 0 && n == TRACE_OP && tile < 32;  // tile stamps of chain 0 in a steady-state op
+          if (tt) a.trace[340 + (tile >> 2) * 8 + 0] = clock64();
+          while (issued[s] < j) __nanosleep(32);  // the barrier has entered this tile's phase (parity waits alias)
+          mbar_wait(&full[s], ph);
+          if (tt) a.trace[340 + (tile >> 2) * 8 + 1] = clock64();
+          float ca[4] = {0.f, 0.f, 0.f, 0.f}, cb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int ks = 0; ks < D / 16; ++ks) {
+            uint32_t kf[4];
+            ldmatrix_x4(kf, kt + swz_off<D>(lrow, ks * 32 + lhalf));
+            if (ks & 1) mma_bf16_16816(cb, kf, qb[ks][0], qb[ks][1]);
+            else mma_bf16_16816(ca, kf, qb[ks][0], qb[ks][1]);
+          }
+          if (tt) a.trace[340 + (tile >> 2) * 8 + 2] = clock64();
+          // softmax over the slot axis: a token's 8 logits live in the 4 lanes of a quad (2 each).  Both token rows
+          // of the fragment go through the reductions together (straight-line code, the two chains interleave);
+          // the divergent attn_vis stores come afterwards.
+          const int tok = (tile0 + tile) * TOK + g8;
+          float x0[2], x1[2], mx[2], e0[2], e1[2], sum[2];
+#pragma unroll
+          for (int hrow = 0; hrow < 2; ++hrow) {
+            x0[hrow] = ok0 ? ca[2 * hrow] + cb[2 * hrow] : -INFINITY;
+            x1[hrow] = ok1 ? ca[2 * hrow + 1] + cb[2 * hrow + 1] : -INFINITY;
+            mx[hrow] = fmaxf(x0[hrow], x1[hrow]);
+          }
+#pragma unroll
+          for (int o = 1; o <= 2; o <<= 1) {
+            const float m0 = __shfl_xor_sync(FULL, mx[0], o), m1 = __shfl_xor_sync(FULL, mx[1], o);
+            mx[0] = fmaxf(mx[0], m0);
+            mx[1] = fmaxf(mx[1], m1);
+          }
+#pragma unroll
+          for (int hrow = 0; hrow < 2; ++hrow) {
+            e0[hrow] = ex2f(x0[hrow] - mx[hrow]);
+            e1[hrow] = ex2f(x1[hrow] - mx[hrow]);
+            sum[hrow] = e0[hrow] + e1[hrow];
+          }
+#pragma unroll
+          for (int o = 1; o <= 2; o <<= 1) {
+            const float s0 = __shfl_xor_sync(FULL, sum[0], o), s1 = __shfl_xor_sync(FULL, sum[1], o);
+            sum[0] += s0;
+            sum[1] += s1;
+          }
+          float w[4];
+          float av[4];
+#pragma unroll
+          for (int hrow = 0; hrow < 2; ++hrow) {
+            const float inv = __fdividef(1.f, sum[hrow]);
+            av[2 * hrow] = e0[hrow] * inv;
+            av[2 * hrow + 1] = e1[hrow] * inv;
+            const bool tok_ok = (tok + 8 * hrow) < N;
+            w[2 * hrow] = (tok_ok && ok0) ? av[2 * hrow] + a.eps : 0.f;
+            w[2 * hrow + 1] = (tok_ok && ok1) ? av[2 * hrow + 1] + a.eps : 0.f;
+          }
+          if (last && a.attn_out != nullptr) {
+#pragma unroll
+            for (int hrow = 0; hrow < 2; ++hrow) {
+              const int tk = tok + 8 * hrow;
+              if (tk < N) {
+                float* ao = a.attn_out + ((size_t)img * N + tk) * K;
+                if ((K & 1) == 0) {
+                  if (ok0) *reinterpret_cast<float2*>(ao + c0) = make_float2(av[2 * hrow], av[2 * hrow + 1]);
+                } else {
+                  if (ok0) ao[c0] = av[2 * hrow];
+                  if (ok1) ao[c1] = av[2 * hrow + 1];
+                }
+              }
+            }
+          }
+          if (tt) a.trace[420 + (tile >> 2) * 4 + 0] = clock64();
+          // weights rounded to bf16 once; the same rounded values feed the numerator and the token sum
+          const __nv_bfloat162 p0 = __floats2bfloat162_rn(w[0], w[1]);
+          const __nv_bfloat162 p1 = __floats2bfloat162_rn(w[2], w[3]);
+          Sl0 += __low2float(p0) + __low2float(p1);
+          Sl1 += __high2float(p0) + __high2float(p1);
+          wt[lane] = movmatrix_trans(*reinterpret_cast<const uint32_t*>(&p0));
+          wt[32 + lane] = movmatrix_trans(*reinterpret_cast<const uint32_t*>(&p1));
+          if (tt) a.trace[420 + (tile >> 2) * 4 + 1] = clock64();
+          __syncwarp();
+          if (tt) a.trace[420 + (tile >> 2) * 4 + 2] = clock64();
+          if (lane == 0) mbar_arrive(&w_ready[s]);
+          if (tt) a.trace[340 + (tile >> 2) * 8 + 3] = clock64();
+        }
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          Sl0 += __shfl_xor_sync(FULL, Sl0, o);
+          Sl1 += __shfl_xor_sync(FULL, Sl1, o);
+        }
+        if (n > 0) mbar_wait(u_free, (uint32_t)((n - 1) & 1));  // the previous update has read sred / the U staging
+        if (g8 == 0) {
+          sred[warp * 8 + c0] = Sl0;
+          sred[warp * 8 + c1] = Sl1;
+        }
+        if (tid == 0 && n < 40) PP_TRACE(8 + n * 8 + 1);
+      } else {
+        // ---- U warp: all D features of its tiles
+        const int uw = warp - 4;
+        float acc[NMU][4];
+#pragma unroll
+        for (int i = 0; i < NMU; ++i)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[i][e] = 0.f;
+        const int urow = (lane & 7) + (lane >> 4) * 8, uhalf = ((lane >> 3) & 1) * 16;
+        for (int tile = uw; tile < TP; tile += 4) {
+          const int j = jbase + tile;
+          const int s = j % S;
+          const uint32_t ph = (uint32_t)((j / S) & 1);
+          const unsigned char* vt = ring + (size_t)s * C::STAGE_BYTES + C::TILE_BYTES;
+          const uint32_t* wt = reinterpret_cast<const uint32_t*>(wtiles + s * C::WT_BYTES);
+          const bool tt = tracer && tid == 128 && n == TRACE_OP && tile < 32;
+          if (tt) a.trace[340 + (tile >> 2) * 8 + 4] = clock64();
+          while (issued[s] < j) __nanosleep(32);
+          mbar_wait(&w_ready[s], ph);  // implies full[s]: the logit warp waited for k and v together
+          if (tt) a.trace[340 + (tile >> 2) * 8 + 5] = clock64();
+          const uint32_t b0 = wt[lane], b1 = wt[32 + lane];
+#pragma unroll
+          for (int i = 0; i < NMU; ++i) {
+            uint32_t vf[4];
+            ldmatrix_x4_trans(vf, vt + swz_off<D>(urow, uhalf + i * 32));
+            mma_bf16_16816(acc[i], vf, b0, b1);
+          }
+          __syncwarp();  // every lane is done with the stage (this warp is its only remaining reader)
+          if (tt) a.trace[340 + (tile >> 2) * 8 + 6] = clock64();
+          if (lane == 0) {
+            int nn = n, tn = tile;
+            advance(nn, tn);
+            if (nn >= 0) issue_tile(nn, tn);
+          }
+          if (tt) a.trace[340 + (tile >> 2) * 8 + 7] = clock64();
+        }
+        if (n > 0) mbar_wait(u_free, (uint32_t)((n - 1) & 1));
+        // combine the four partial sums: warps 4, 5 write the two staging buffers, warps 6, 7 add into them
+        float* ust = (uw & 1) ? ustage_b : ustage_a;
+        if (uw >= 2) asm volatile("bar.sync 2, 128;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < NMU; ++i) {
+          const int d0 = 16 * i + g8;
+          float* u0 = ust + (2 * t4) * UP + d0;
+          float* u1 = ust + (2 * t4 + 1) * UP + d0;
+          if (uw >= 2) {
+            u0[0] += acc[i][0]; u1[0] += acc[i][1]; u0[8] += acc[i][2]; u1[8] += acc[i][3];
+          } else {
+            u0[0] = acc[i][0]; u1[0] = acc[i][1]; u0[8] = acc[i][2]; u1[8] = acc[i][3];
+          }
+        }
+        if (uw < 2) asm volatile("bar.sync 2, 128;" ::: "memory");
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(u_ready);
+    }
+  } else {
+    // ==================================================================================== UPDATE ENGINE
+    const int utid = tid - 256, uwarp = warp - 8;
+    uint32_t round = 0;
+    auto xb = [&](uint32_t r) { return xbuf + (r & 1) * C::XBUF_BYTES; };
+    auto arm = [&](uint32_t r, uint32_t bytes) {
+      if (utid == 0) mbar_expect_tx(&xbar[r & 1], bytes);
+    };
+    auto xwait = [&](uint32_t r) { mbar_wait_cluster(&xbar[r & 1], (r >> 1) & 1); };
+    // All-gather push without staging: thread i < K*SL holds element (slot = i / SL, f = i % SL) of the CTA's
+    // slice.  The four lanes of a quad assemble the float4 of features 4*(f/4).. and each sends it to CL/4 CTAs.
+    auto quad_push = [&](uint32_t r, float val, int i, int SL, int pitchf) {
+      const int qb = lane & ~3;
+      float4 v4;
+      v4.x = __shfl_sync(FULL, val, qb);
+      v4.y = __shfl_sync(FULL, val, qb + 1);
+      v4.z = __shfl_sync(FULL, val, qb + 2);
+      v4.w = __shfl_sync(FULL, val, qb + 3);
+      if (i < K * SL) {
+        const int slot = i / SL, f4 = (i % SL) & ~3;
+        const uint32_t lbuf = smem_u32(xb(r)) + (uint32_t)((slot * pitchf + rank * SL + f4) * 4);
+        const uint32_t lbar = smem_u32(&xbar[r & 1]);
+#pragma unroll
+        for (int q = 0; q < CL / 4; ++q) {
+          const int dest = (lane & 3) + 4 * q;
+          st_async_v4(mapa_u32(lbuf, dest), v4, mapa_u32(lbar, dest));
+        }
+      }
+    };
+    auto to_hilo = [&](const float* src, int L, unsigned char* hi, unsigned char* lo, int ap) {
+      for (int i = utid; i < K * (L / 2); i += 256) {
+        const int slot = i / (L / 2), c2 = i % (L / 2);
+        const float2 x = *reinterpret_cast<const float2*>(src + slot * L + 2 * c2);
+        *reinterpret_cast<uint32_t*>(hi + slot * ap + 4 * c2) = pack_bf16x2(x.x, x.y);
+        (void)lo;
+      }
+    };
+    auto ln_to_hilo = [&](const float* src, const float* gw, const float* gbias, unsigned char* hi, unsigned char* lo,
+                          unsigned char* raw_hi, unsigned char* raw_lo) {
+      constexpr int NCH = D / 64;
+      if (uwarp < K) {
+        float2 x[NCH];
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          x[c] = *reinterpret_cast<const float2*>(src + uwarp * D + 64 * c + 2 * lane);
+          s += x[c].x + x[c].y;
+          if (raw_hi != nullptr)
+            *reinterpret_cast<uint32_t*>(raw_hi + uwarp * PITCH + (64 * c + 2 * lane) * 2) = pack_bf16x2(x[c].x, x[c].y);
+          (void)raw_lo;
+        }
+        const float mean = warp_sum(s) * (1.f / D);
+        float q = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          x[c].x -= mean;
+          x[c].y -= mean;
+          q = fmaf(x[c].x, x[c].x, fmaf(x[c].y, x[c].y, q));
+        }
+        const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + a.ln_eps);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const float2 g = *reinterpret_cast<const float2*>(gw + 64 * c + 2 * lane);
+          const float2 b = *reinterpret_cast<const float2*>(gbias + 64 * c + 2 * lane);
+          *reinterpret_cast<uint32_t*>(hi + uwarp * PITCHX + (64 * c + 2 * lane) * 2) =
+              pack_bf16x2(x[c].x * rstd * g.x + b.x, x[c].y * rstd * g.y + b.y);
+          (void)lo;
+        }
+      }
+    };
+    // q = W_q . LN(slots) of lane l for the CTA's slice, all-gathered as bf16 (times log2 e) into every CTA's qbuf[l]
+    auto q_phase = [&](int l, const float* slots_full /* [K][D], shared or global */) {
+      arm(round, (uint32_t)(K * D * 2));
+      ln_to_hilo(slots_full, s_lnp, s_lnp + D, act_hi, act_lo, slh_hi(l), slh_lo(l));
+      upd_sync();
+      for (int job = uwarp; job < NM2 * NKC; job += 8) {
+        const int mt = job / NKC, kc = job % NKC;
+        mma_job<false>(s_wq, PITCH, DS, s_zrow, mt, kc * (D / 16) / NKC, (kc + 1) * (D / 16) / NKC, act_hi, act_lo, PITCHX,
+                P + kc * NM2 * 128, lane);
+      }
+      upd_sync();
+      const int nel = K * DS;
+      for (int i0 = uwarp * 32; i0 < nel; i0 += 256) {
+        const int i = i0 + lane;
+        float val = 0.f;
+        if (i < nel) {
+          const int slot = i / DS, dl = i % DS;
+#pragma unroll
+          for (int kc = 0; kc < NKC; ++kc) val += P[(kc * NM2 * 16 + dl) * 8 + slot];
+          val *= LOG2E;
+        }
+        const int qb = lane & ~3;
+        const float v0 = __shfl_sync(FULL, val, qb), v1 = __shfl_sync(FULL, val, qb + 1);
+        const float v2 = __shfl_sync(FULL, val, qb + 2), v3 = __shfl_sync(FULL, val, qb + 3);
+        if (i < nel) {
+          const int slot = i / DS, f4 = (i % DS) & ~3;
+          const uint32_t lbuf = smem_u32(qbuf(l)) + (uint32_t)(slot * PITCH + (rank * DS + f4) * 2);
+          const uint32_t lbar = smem_u32(&xbar[round & 1]);
+          const uint32_t lo = pack_bf16x2(v0, v1), hi = pack_bf16x2(v2, v3);
+#pragma unroll
+          for (int q = 0; q < CL / 4; ++q) {
+            const int dest = (lane & 3) + 4 * q;
+            st_async_v2(mapa_u32(lbuf, dest), lo, hi, mapa_u32(lbar, dest));
+          }
+        }
+      }
+      xwait(round);
+      ++round;
+      if (utid == 0) mbar_arrive(&q_ready[l]);  // the logit warps of lane l may load their q fragments
+    };
+    auto load_own = [&](int l, int img) {
+      float* own = own_of(l);
+      for (int i = utid; i < K * DS; i += 256) own[i] = a.slots0[((size_t)img * K + i / DS) * D + rank * DS + i % DS];
+    };
+
+    // initial queries of both lanes
+    for (int l = 0; l < 2; ++l)
+      if (nimg[l] > 0) {
+        load_own(l, image_of(l, 0));
+        q_phase(l, a.slots0 + (size_t)image_of(l, 0) * K * D);
+      }
+
+    for (int n = 0; n < total_ops; ++n) {
+      int l, c;
+      op_of(n, l, c);
+      const int t = c % T, m = c / T, img = image_of(l, m);
+      const bool last = (t == T - 1);
+      float* own = own_of(l);
+      const bool tr_on = tracer && utid == 0 && n < 40;
+#define PP_T(i) do { if (tr_on) a.trace[8 + n * 8 + (i)] = clock64(); } while (0)
+      // ============================================================ R1: reduce-scatter of sum w v, all-reduce of sum w
+      arm(round, (uint32_t)(K * D * 4 + 32 * CL));
+      mbar_wait(u_ready, (uint32_t)(n & 1));
+      PP_T(2);
+      {
+        const uint32_t lbuf = smem_u32(xb(round)), lbar = smem_u32(&xbar[round & 1]);
+        constexpr int QPR = D / 4;
+        for (int i = utid; i < K * QPR; i += 256) {
+          const int slot = i / QPR, d = 4 * (i % QPR);
+          const int dest = d / DS, dl = d % DS;
+          const float4 xa = *reinterpret_cast<const float4*>(ustage_a + slot * UP + d);
+          const float4 xb4 = *reinterpret_cast<const float4*>(ustage_b + slot * UP + d);
+          const float4 val = make_float4(xa.x + xb4.x, xa.y + xb4.y, xa.z + xb4.z, xa.w + xb4.w);
+          const uint32_t off = (uint32_t)(((rank * KP + slot) * DS + dl) * 4);
+          st_async_v4(mapa_u32(lbuf + off, dest), val, mapa_u32(lbar, dest));
+        }
+        if (utid < 8 * CL) {
+          const int slot = utid & 7, dest = utid >> 3;
+          const float s = sred[slot] + sred[8 + slot] + sred[16 + slot] + sred[24 + slot];
+          const uint32_t off = (uint32_t)(KP * D * 4 + (rank * 8 + slot) * 4);
+          st_async_b32(mapa_u32(lbuf + off, dest), __float_as_uint(s), mapa_u32(lbar, dest));
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(u_free);  // the pass engine may overwrite the staging buffers
+      xwait(round);
+      PP_T(3);
+      // ============================================================ R2: all-gather updates = sum over CTAs / token sum
+      arm(round + 1, (uint32_t)(K * D * 4));
+      {
+        const float* rs = reinterpret_cast<const float*>(xb(round));
+        const float* ss = rs + KP * D;
+        for (int i0 = uwarp * 32; i0 < K * DS; i0 += 256) {
+          const int i = i0 + lane;
+          float val = 0.f;
+          if (i < K * DS) {
+            const int slot = i / DS, dl = i % DS;
+            float u = 0.f, s = 0.f;
+#pragma unroll
+            for (int src = 0; src < CL; ++src) {
+              u += rs[(src * KP + slot) * DS + dl];
+              s += ss[src * 8 + slot];
+            }
+            val = u / s;
+          }
+          quad_push(round + 1, val, i, DS, D);
+        }
+      }
+      ++round;
+      xwait(round);
+      to_hilo(reinterpret_cast<const float*>(xb(round)), D, act_hi, act_lo, PITCHX);
+      ++round;
+      upd_sync();
+      // ---- GRU: gi = W_ih u, gh = W_hh h
+      for (int job = uwarp; job < 2 * NMG; job += 8) {
+        const bool hh = job >= NMG;
+        const int mt = hh ? job - NMG : job;
+        mma_job<false>(hh ? s_whh : s_wih, PITCH, 3 * DS, s_zrow, mt, 0, D / 16, hh ? slh_hi(l) : act_hi, hh ? slh_lo(l) : act_lo,
+                hh ? PITCH : PITCHX, P + (hh ? NMG * 128 : 0), lane);
+      }
+      arm(round, (uint32_t)(K * D * 4));
+      upd_sync();
+      PP_T(4);
+      // ============================================================ R3: all-gather h'
+      for (int i0 = uwarp * 32; i0 < K * DS; i0 += 256) {
+        const int i = i0 + lane;
+        float hp = 0.f;
+        if (i < K * DS) {
+          const int slot = i / DS, dl = i % DS;
+          const float* Pi = P;
+          const float* Ph = P + NMG * 128;
+          const float gir = Pi[(dl) * 8 + slot] + s_bih[dl], ghr = Ph[(dl) * 8 + slot] + s_bhh[dl];
+          const float giz = Pi[(DS + dl) * 8 + slot] + s_bih[DS + dl], ghz = Ph[(DS + dl) * 8 + slot] + s_bhh[DS + dl];
+          const float gin = Pi[(2 * DS + dl) * 8 + slot] + s_bih[2 * DS + dl];
+          const float ghn = Ph[(2 * DS + dl) * 8 + slot] + s_bhh[2 * DS + dl];
+          const float r = sigmoidf_(gir + ghr), z = sigmoidf_(giz + ghz);
+          const float nn = tanhf(gin + r * ghn);
+          hp = (1.f - z) * nn + z * own[i];
+          own[i] = hp;
+        }
+        quad_push(round, hp, i, DS, D);
+      }
+      xwait(round);
+      ln_to_hilo(reinterpret_cast<const float*>(xb(round)), s_lnp + 2 * D, s_lnp + 3 * D, act_hi, act_lo, nullptr, nullptr);
+      ++round;
+      upd_sync();
+      for (int job = uwarp; job < NM1 * NKC; job += 8) {
+        const int mt = job / NKC, kc = job % NKC;
+        mma_job<false>(s_w1, PITCH, HS, s_zrow, mt, kc * (D / 16) / NKC, (kc + 1) * (D / 16) / NKC, act_hi, act_lo, PITCHX,
+                P + kc * NM1 * 128, lane);
+      }
+      arm(round, (uint32_t)(K * H * 4));
+      upd_sync();
+      PP_T(5);
+      // ============================================================ R4: all-gather the MLP hidden layer
+      for (int i0 = uwarp * 32; i0 < K * HS; i0 += 256) {
+        const int i = i0 + lane;
+        float hid = 0.f;
+        if (i < K * HS) {
+          const int slot = i / HS, hl = i % HS;
+          float sum = s_b1[hl];
+#pragma unroll
+          for (int kc = 0; kc < NKC; ++kc) sum += P[(kc * NM1 * 16 + hl) * 8 + slot];
+          hid = fmaxf(sum, 0.f);
+        }
+        quad_push(round, hid, i, HS, H);
+      }
+      xwait(round);
+      to_hilo(reinterpret_cast<const float*>(xb(round)), H, act_hi, act_lo, PITCHX);
+      ++round;
+      upd_sync();
+      for (int job = uwarp; job < NM2 * NKC; job += 8) {
+        const int mt = job / NKC, kc = job % NKC;
+        mma_job<false>(s_w2, PITCHH, DS, s_zrow, mt, kc * (H / 16) / NKC, (kc + 1) * (H / 16) / NKC, act_hi, act_lo, PITCHX,
+                P + kc * NM2 * 128, lane);
+      }
+      if (!last) arm(round, (uint32_t)(K * D * 4));
+      upd_sync();
+      PP_T(6);
+      // ============================================================ R5: all-gather the new slots (or write them out)
+      const bool more = last && (m + 1 < nimg[l]);
+      for (int i0 = uwarp * 32; i0 < K * DS; i0 += 256) {
+        const int i = i0 + lane;
+        float sn = 0.f;
+        if (i < K * DS) {
+          const int slot = i / DS, dl = i % DS;
+          float sum = s_b2[dl];
+#pragma unroll
+          for (int kc = 0; kc < NKC; ++kc) sum += P[(kc * NM2 * 16 + dl) * 8 + slot];
+          sn = own[i] + sum;
+          own[i] = sn;
+          if (last) {
+            a.slots_out[((size_t)img * K + slot) * D + rank * DS + dl] = sn;
+            if (more) own[i] = a.slots0[((size_t)image_of(l, m + 1) * K + slot) * D + rank * DS + dl];
+          }
+        }
+        if (!last) quad_push(round, sn, i, DS, D);
+      }
+      if (!last) {
+        xwait(round);
+        const float* sfull = reinterpret_cast<const float*>(xb(round));
+        ++round;
+        q_phase(l, sfull);  // R6: q of the lane's next iteration
+      } else if (more) {
+        q_phase(l, a.slots0 + (size_t)image_of(l, m + 1) * K * D);  // q of the lane's next image
+      } else {
+        upd_sync();  // P is rewritten by the next op
+      }
+      PP_T(7);
+    }
+  }
+  __syncthreads();
+  cluster.sync();  // no CTA leaves while a peer may still address its shared memory
+}
+
+template <int D, int H, int CL, int S>
+static int launch_pipe(const IterFwdArgs& a, cudaStream_t stream) {
+  using C = Cfg<D, H, CL, S>;
+  auto kern = sa_iter_fwd_pipe_kernel<D, H, CL, S>;
+  static_assert(C::SMEM_BYTES <= 227 * 1024, "shared memory budget");
+  CUtensorMap tm_k, tm_v;
+  if (!make_kv_map(&tm_k, a.k, (long long)a.B * a.N, D, C::TOK) || !make_kv_map(&tm_v, a.v, (long long)a.B * a.N, D, C::TOK)) {
+    set_error("sa_iter_fwd(pipeline): cuTensorMapEncodeTiled failed");
+    return OCRL_E_LAUNCH;
+  }
+  OCRL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  if (CL > 8) OCRL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(C::NT);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  static int max_clusters = -1;
+  if (max_clusters < 0) {
+    cfg.gridDim = dim3(CL * 148);
+    int n = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+    if (e != cudaSuccess || n <= 0) {
+      (void)cudaGetLastError();
+      set_error("sa_iter_fwd(pipeline): cluster size %d with %d B of shared memory cannot be scheduled", CL, C::SMEM_BYTES);
+      return OCRL_E_SHAPE;
+    }
+    max_clusters = n;
+    if (getenv("OCRL_SA_PC_VERBOSE"))
+      fprintf(stderr, "[ocrl] pipe kernel CL=%d S=%d smem=%d B: max active clusters %d\n", CL, S, C::SMEM_BYTES, n);
+  }
+  int ncl = max_clusters;
+  if (const char* e = getenv("OCRL_SA_PC_CLUSTERS")) ncl = max(1, min(ncl, atoi(e)));
+  const int want = (a.B + 1) / 2;  // two lanes per cluster
+  if (ncl > want) ncl = want;
+  cfg.gridDim = dim3((unsigned)(ncl * CL));
+  OCRL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, a, tm_k, tm_v));
+  return OCRL_OK;
+}
+
+}  // namespace pipe
+
+// Returns OCRL_E_SHAPE (without launching) for shapes this kernel does not cover; the caller falls back.
+int sa_iter_fwd_pipe_dispatch(const IterFwdArgs& a, cudaStream_t s) {
+  if (a.K > 8 || a.saved != nullptr) {
+    set_error("sa_iter_fwd(pipeline): K <= 8, inference only");
+    return OCRL_E_SHAPE;
+  }
+  int variant = 0;
+  if (const char* e = getenv("OCRL_SA_PIPE")) variant = atoi(e);
+  if (a.D == 192 && a.H == 192) {
+    switch (variant) {
+      case 1: return pipe::launch_pipe<192, 192, 8, 4>(a, s);
+      case 2: return pipe::launch_pipe<192, 192, 16, 8>(a, s);
+      case 3: return pipe::launch_pipe<192, 192, 8, 6>(a, s);
+      default: return pipe::launch_pipe<192, 192, 8, 7>(a, s);
+    }
+  }
+  set_error("sa_iter_fwd(pipeline): D=%d H=%d not instantiated", a.D, a.H);
+  return OCRL_E_SHAPE;
+}
+
+}  // namespace ocrl

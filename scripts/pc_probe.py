@@ -16,8 +16,21 @@ def cuda(d):
     return {k: v.cuda() for k, v in d.items()}
 
 
+def set_variant(v):
+    """'pipeN' two-engine kernel variant N; 'pcN' single-engine variant N; 'old' the per-image cluster kernel"""
+    v = str(v)
+    if v.startswith("pipe"):
+        os.environ["OCRL_SA_PIPE"] = v[4:] or "0"
+    elif v.startswith("pc"):
+        os.environ["OCRL_SA_PIPE"] = "-1"
+        os.environ["OCRL_SA_PC"] = v[2:] or "0"
+    else:
+        os.environ["OCRL_SA_PIPE"] = "-1"
+        os.environ["OCRL_SA_PC"] = "-1"
+
+
 def parity(variant):
-    os.environ["OCRL_SA_PC"] = str(variant)
+    set_variant(variant)
     for name in ("sa_slate_grad", "sa_sharp", "sa_small_grad"):
         meta, g = load_case(name)
         if meta["K"] > 8 or g["p"]["project_q.weight"].shape[0] != 192:
@@ -68,7 +81,7 @@ def timing(variants, shapes):
         bytes_img = 2 * N * 192 * 2 + N * K * 4 + 2 * K * 192 * 4
         flush = torch.empty(256 << 20, device="cuda", dtype=torch.uint8)
         for var in variants:
-            os.environ["OCRL_SA_PC"] = str(var)
+            set_variant(var)
             ms = timeit(lambda: F.iterate(k, v, s0, p, T, _workspace=ws))
             # cold: L2 flushed before every launch (k/v come from HBM in the first pass)
 
@@ -84,7 +97,7 @@ def timing(variants, shapes):
 if __name__ == "__main__":
     mode = sys.argv[1]
     if mode == "parity":
-        parity(int(sys.argv[2]))
+        parity(sys.argv[2])
     else:
-        variants = [int(x) for x in sys.argv[2].split(",")]
+        variants = sys.argv[2].split(",")
         timing(variants, [(64, 4096, 6, 3)] if mode == "time" else [(64, 4096, 6, 3), (256, 4096, 6, 3), (32, 16384, 6, 3), (64, 4096, 8, 7)])

@@ -6,6 +6,7 @@ import sys
 import torch
 
 os.environ["OCRL_SA_TRACE"] = "1"
+os.environ["OCRL_SA_PIPE"] = "-1"
 os.environ["OCRL_SA_PC"] = sys.argv[1] if len(sys.argv) > 1 else "0"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ocrl_b200 import abi, functional as F  # noqa: E402
