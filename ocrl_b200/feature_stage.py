@@ -25,6 +25,49 @@ class SlotAttnCNNEncoder(nn.Module):
         return self._encoder(obs)
 
 
+class FusedBf16Encoder:
+    """Inference fast path of SlotAttnCNNEncoder in bf16 (library calls, cuDNN): channels-last tensors, bias and
+    ReLU fused into the convolutions (``cudnn_convolution_relu``), weights cast once and cached until a parameter
+    changes, the 3 input channels zero-padded to 8 so that the first layer also takes a tensor-core kernel.  The
+    last layer's bias is not applied here: ``last_bias`` is folded into the position table by the caller
+    (the token-stage kernel adds that table anyway).  Same arithmetic as the module under autocast(bf16)."""
+
+    def __init__(self, enc: "SlotAttnCNNEncoder"):
+        self._enc = enc
+        self._key = None
+        self._w = None
+        self._b = None
+
+    def _refresh(self):
+        convs = [self._enc._encoder[i].m for i in range(3)] + [self._enc._encoder[3]]
+        key = tuple((c.weight.data_ptr(), c.weight._version, c.bias.data_ptr(), c.bias._version) for c in convs)
+        if key == self._key:
+            return
+        ws, bs = [], []
+        for i, c in enumerate(convs):
+            w = c.weight.detach()
+            if i == 0 and w.shape[1] % 8:
+                w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, 8 - w.shape[1] % 8))
+            ws.append(w.to(torch.bfloat16).contiguous(memory_format=torch.channels_last))
+            bs.append(c.bias.detach().to(torch.bfloat16) if i < 3 else c.bias.detach().float())
+        self._w, self._b, self._key = ws, bs, key
+
+    @property
+    def last_bias(self):
+        self._refresh()
+        return self._b[3]
+
+    def __call__(self, obs):
+        self._refresh()
+        B, C, H, W = obs.shape
+        cin = self._w[0].shape[1]
+        x = torch.zeros(B, cin, H, W, device=obs.device, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        x[:, :C] = obs
+        for i in range(3):
+            x = torch.cudnn_convolution_relu(x, self._w[i], self._b[i], [1, 1], [2, 2], [1, 1], 1)
+        return torch.conv2d(x, self._w[3], None, 1, 2)
+
+
 class PositionalEmbedding(nn.Module):
     def __init__(self, obs_size: int, obs_channels: int):
         super().__init__()

@@ -17,7 +17,7 @@ from torch import nn
 
 from .adjacent import (BosToken, BroadCastDecoder, LearnedPositionalEncoding, OneHotDictionary,
                        TransformerDecoder, cosine_anneal, dVAE, gumbel_softmax)
-from .feature_stage import PositionalEmbedding, SlotAttnCNNEncoder
+from .feature_stage import FusedBf16Encoder, PositionalEmbedding, SlotAttnCNNEncoder
 from .networks import linear
 from .slot_attn import SlotAttentionEncoder
 
@@ -142,6 +142,13 @@ class SLATE_Module(nn.Module):
         if not self._hot_needs_grad(obs):
             # inference: position add + (transpose) + token MLP + projections fused into one kernel
             with torch.no_grad():
+                if self._conv_mode() == "bf16" and os.environ.get("OCRL_CONV_FUSED", "1") != "0":
+                    # fused bias+ReLU convolutions; the last conv's bias rides on the position table
+                    fast = self.__dict__.get("_fast_enc")
+                    if fast is None:
+                        fast = self.__dict__["_fast_enc"] = FusedBf16Encoder(self._enc)
+                    table = self._enc_pos.table() + fast.last_bias.unsqueeze(1)
+                    return self._slotattn(fast(obs), _pos_table=table)
                 return self._slotattn(self._encode_features(obs), _pos_table=self._enc_pos.table())
         fmap = self._enc(obs)
         emb = self._enc_pos(fmap).permute(0, 2, 3, 1).flatten(start_dim=1, end_dim=2)

@@ -102,12 +102,15 @@ def test_bf16_mode_through_the_module(monkeypatch):
     assert rel_err(masks.cpu(), g["out"]["masks"]) < 2e-2
 
 
-@pytest.mark.parametrize("conv", ["tf32", "bf16"])
+@pytest.mark.parametrize("conv", ["tf32", "bf16", "bf16-unfused"])
 def test_bf16_mode_with_tensor_core_convs(monkeypatch, conv):
-    """bf16 mode end to end: channels-last cuDNN convs (TF32 or bf16) feeding the tcgen05 token stage
-    (bf16 tokens when the convs are bf16) and the tensor-core iteration kernel; 2e-2 tolerance."""
+    """bf16 mode end to end: channels-last cuDNN convs (TF32, bf16 with fused bias+ReLU and the last bias folded
+    into the position table, or plain bf16 autocast) feeding the tcgen05 token stage (bf16 tokens when the convs
+    are bf16) and the tensor-core iteration kernel; 2e-2 tolerance."""
     meta, g = load_case("slate_encode_64")
     monkeypatch.setenv("OCRL_KV_DTYPE", "bf16")
+    monkeypatch.setenv("OCRL_CONV_FUSED", "0" if conv.endswith("unfused") else "1")
+    conv = conv.split("-")[0]
     monkeypatch.setenv("OCRL_CONV_DTYPE", conv)
     model = ocrl_b200.SLATE(*slate_config())
     _load_hot(model._module, g["p"])
