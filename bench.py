@@ -266,17 +266,29 @@ def roofline_of(a, mode, events):
             peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured"
     except Exception:
         pass
+    # DRAM traffic per launch of the same kernels from the committed `ncu --set full` capture (profiles/, per mode);
+    # it is a property of the kernel build, not re-measured here (a number taken under a profiler is never timed)
+    traffic, tok_traffic = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1", f"traffic_{mode}.json")) as f:
+            tj = json.load(f)
+        if (a.batch, N, D, K, a.iters) == (64, 4096, 192, 6, 3):  # the capture's configuration
+            traffic = tj.get("sa_iter_fwd_pipe_kernel", {}).get("traffic_bytes")
+            tok_traffic = tj.get("kv_proj_tc_kernel", {}).get("traffic_bytes")
+    except Exception:
+        pass
     it_avg = sum(it_ms) / max(1, len(it_ms))
     tk_avg = sum(tk_ms) / max(1, len(tk_ms))
     achieved = a.batch * bytes_img / (it_avg * 1e-3) / 1e9 if it_ms else None
     tok_achieved = a.batch * tok_bytes_img / (tk_avg * 1e-3) / 1e9 if tk_ms else None
     return {"kernel": "sa_iter_fwd_pipe_kernel (two-engine persistent clusters, TMA ring, mma.sync bf16)" if mode == "bf16" else "sa_iter_fwd_kernel (fp32 FFMA)",
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": (achieved / peak if achieved else None), "traffic": None, "peak_source": peak_src,
+            "frac": (achieved / peak if achieved else None), "traffic": traffic, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": a.batch * bytes_img,
             "algorithmic_bytes_per_image": bytes_img, "avg_launch_ms": it_avg, "launches_timed": len(it_ms),
             "token_stage": {"kernel": "kv_proj_tc_kernel (tcgen05 + TMA)" if mode == "bf16" else "token_stage_kernel (fp32 FFMA)",
                             "avg_launch_ms": tk_avg, "achieved": tok_achieved, "unit": "GB/s",
-                            "frac": (tok_achieved / peak if tok_achieved else None),
+                            "frac": (tok_achieved / peak if tok_achieved else None), "traffic": tok_traffic,
                             "algorithmic_bytes_per_image": tok_bytes_img}}
 
 
@@ -328,7 +340,7 @@ def main():
                 "data": "synthetic",
                 "config": dict(workload(a), l2="k/v working set per step %.0f MB > 126 MB L2; frame pool of %d rotates"
                                % (a.batch * 2 * N * D * esz / 1e6, a.pool),
-                               cnn="cuDNN via torch (library call); token stage + iteration loop hand-written CUDA",
+                               cnn="cuDNN via torch (library call, fused bias+ReLU in bf16 mode); token stage + iteration loop hand-written CUDA",
                                launch="CUDA graph replay of SLATE.__call__" if main_res["graph"] else "eager launches"),
                 "clocks": clk,
                 "e2e": {"value": main_res["e2e_value"], "unit": UNIT, "ms_per_step": main_res["e2e_ms_per_step"],

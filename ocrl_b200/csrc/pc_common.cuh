@@ -13,13 +13,16 @@ namespace pc {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// wait with cluster-scope acquire: the data behind the barrier was written by peer CTAs (st.async)
+// Wait for an exchange round.  The data behind the barrier was written into THIS CTA's shared memory by peers'
+// st.async; its visibility is tied to the complete_tx the waiter observes, so the default CTA-scope acquire is
+// enough (a cluster-scope acquire makes ptxas emit an L1 invalidate, CCTL.IVALL, after every wait: ~10 % of the
+// kernel's stall samples in the first profile).
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "WAITC_%=:\n"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
       "@p bra DONEC_%=;\n"
       "bra WAITC_%=;\n"
       "DONEC_%=:\n"
@@ -55,12 +58,40 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, in
       "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
       : "memory");
 }
+// same, with an L2 eviction-priority hint (createpolicy): evict_last for tiles that are read again by the next
+// iteration, evict_first for the final pass
+__device__ __forceinline__ void tma_load_3d_hint(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(
+          smem_u32(dst)),
+      "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 // Byte offset of (row, dbyte) inside a [TOK][D] bf16 tile that the TMA unit wrote as [row][D/64][64] with the
 // 128-byte swizzle (16-byte chunk index xor-ed with the 128-byte line index mod 8); dbyte is a multiple of 16.
 template <int D>
 __device__ __forceinline__ int swz_off(int row, int dbyte) {
   const int line = row * (D / 64) + (dbyte >> 7);
   return line * 128 + ((((dbyte >> 4) & 7) ^ (line & 7)) << 4);
+}
+__device__ __forceinline__ int lds_volatile(const int* p) {
+  int v;
+  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_volatile(int* p, int v) {
+  asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
 __device__ __forceinline__ void group_sync(int grp) {
   asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory");

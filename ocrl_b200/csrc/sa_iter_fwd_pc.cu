@@ -99,7 +99,8 @@ sa_iter_fwd_pc_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap t
   constexpr float LOG2E = 1.4426950408889634f;
 
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align by pointer arithmetic on the __shared__ pointer (an integer round trip would turn every access generic)
+  unsigned char* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int cid = blockIdx.x / CL, ncl = gridDim.x / CL;

@@ -50,7 +50,7 @@ struct Cfg {
   static constexpr int XBUF_BYTES = KP * LX * 4 + 32 * CL;
   static constexpr int OFF_XBUF = (OFF_BIAS + (7 * DS + HS) * 4 + 15) & ~15;
   static constexpr int OFF_ACT = OFF_XBUF + 2 * XBUF_BYTES;        // activation staging, bf16 (update engine)
-  static constexpr int P_ROWS = (2 * NMG > NKC * (NM1 > NM2 ? NM1 : NM2)) ? 2 * NMG * 16 : NKC * (NM1 > NM2 ? NM1 : NM2) * 16;
+  static constexpr int P_ROWS = (3 * NMG > NKC * (NM1 > NM2 ? NM1 : NM2)) ? 3 * NMG * 16 : NKC * (NM1 > NM2 ? NM1 : NM2) * 16;
   static constexpr int OFF_P = OFF_ACT + KP * PITCHX;              // MMA partial outputs
   static constexpr int OFF_UST = OFF_P + P_ROWS * 32;              // U staging a, b (pass -> update hand-off)
   static constexpr int OFF_SRED = OFF_UST + 2 * KP * UP * 4;       // [4][8] token sums of the logit warps
@@ -72,7 +72,8 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
   constexpr float LOG2E = 1.4426950408889634f;
 
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align by pointer arithmetic on the __shared__ pointer (an integer round trip would turn every access generic)
+  unsigned char* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int cid = blockIdx.x / CL, ncl = gridDim.x / CL;
@@ -114,40 +115,103 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
   uint64_t* u_ready = bars + 2 * S + 2;
   uint64_t* u_free = bars + 2 * S + 3;
   uint64_t* q_ready = bars + 2 * S + 4;
-  volatile int* issued = reinterpret_cast<volatile int*>(sm + C::OFF_ISSUED);
+  int* issued = reinterpret_cast<int*>(sm + C::OFF_ISSUED);
 
   // ------------------------------------------------------------------ work assignment (two lanes per cluster)
-  const int G = ncl * 2;
+  // Images are dealt to clusters round-robin (newest first: the projection kernel left them in L2) and a cluster
+  // alternates its images between its two lanes, so every cluster gets floor or ceil of B / #clusters images.
+  const int ncimg = (B > cid) ? (B - cid + ncl - 1) / ncl : 0;
   int nimg[2];
-#pragma unroll
-  for (int l = 0; l < 2; ++l) {
-    const int gi = cid * 2 + l;
-    nimg[l] = (B > gi) ? (B - gi + G - 1) / G : 0;
-  }
+  nimg[0] = (ncimg + 1) / 2;
+  nimg[1] = ncimg / 2;
   const int nops0 = nimg[0] * T, nops1 = nimg[1] * T;  // nops0 >= nops1
   const int total_ops = nops0 + nops1;
   auto op_of = [&](int n, int& l, int& c) {
     if (n < 2 * nops1) { l = n & 1; c = n >> 1; } else { l = 0; c = n - nops1; }
   };
-  auto image_of = [&](int l, int m) { return B - 1 - ((cid * 2 + l) + m * G); };  // newest first (still in L2)
+  auto image_of = [&](int l, int m) { return B - 1 - (cid + (2 * m + l) * ncl); };
   const int ntiles = (N + TOK - 1) / TOK;
   const int TPC = (ntiles + CL - 1) / CL;
   const int tile0 = rank * TPC;
   const int TP = max(0, min(TPC, ntiles - tile0));
 
-  // one elected lane: stage (j % S) <- tile j = n * TP + tile of the CTA's tile sequence (pass ops in stream order)
+  // one elected lane: stage (j % S) <- tile j = n * TP + tile of the CTA's tile sequence (pass ops in stream order).
+  // L2 policy: tiles of iterations 0..T-2 are read again by the next pass (evict_last), the final pass's are dead
+  // afterwards (evict_first).  For the first pass of an image the tile `PFD` tiles further on is prefetched into L2
+  // at the same rate as tiles are consumed (a burst would queue in front of the demand loads).
+  const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
+  constexpr int PFD = 24;
   auto issue_tile = [&](int n, int tile) {
     const int j = n * TP + tile;
     const int s = j % S;
     int l, c;
     op_of(n, l, c);
+    const int t = c % T;
     const int row0 = image_of(l, c / T) * N + (tile0 + tile) * TOK;
     unsigned char* kd = ring + (size_t)s * C::STAGE_BYTES;
+    const uint64_t pol = (t == T - 1) ? pol_drop : pol_keep;
     mbar_expect_tx(&full[s], (uint32_t)C::STAGE_BYTES);
-    tma_load_3d(kd, &tm_k, 0, 0, row0, &full[s]);
-    tma_load_3d(kd + C::TILE_BYTES, &tm_v, 0, 0, row0, &full[s]);
-    __threadfence_block();
-    issued[s] = j;
+    tma_load_3d_hint(kd, &tm_k, 0, 0, row0, &full[s], pol);
+    tma_load_3d_hint(kd + C::TILE_BYTES, &tm_v, 0, 0, row0, &full[s], pol);
+    sts_volatile(&issued[s], j);  // after the expect_tx above in program order: the barrier is in this tile's phase
+    // paced L2 prefetch, only where the data is cold (first pass of an image)
+    int pn = n, pt = tile + PFD;
+    while (pt >= TP && pn < total_ops) { pt -= TP; ++pn; }
+    if (pn < total_ops) {
+      int pl, pc;
+      op_of(pn, pl, pc);
+      if (pc % T == 0) {
+        const size_t off = ((size_t)image_of(pl, pc / T) * N + (size_t)(tile0 + pt) * TOK) * D * 2;
+        if (off + C::TILE_BYTES <= (size_t)B * N * D * 2) {
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(a.k) + off), "r"(C::TILE_BYTES) : "memory");
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(a.v) + off), "r"(C::TILE_BYTES) : "memory");
+        }
+      }
+    }
+  };
+  // Per-op constants of the refill path (row base of the CTA's share, L2 policy, cold = first pass of an image),
+  // computed once per op so that the per-tile refill is a handful of instructions.
+  struct OpInfo { int row_base; int cold; int valid; uint64_t pol; };
+  auto op_info = [&](int n) {
+    OpInfo o;
+    o.valid = (n < total_ops);
+    o.row_base = 0; o.cold = 0; o.pol = pol_keep;
+    if (o.valid) {
+      int l, c;
+      op_of(n, l, c);
+      const int t = c % T;
+      o.row_base = image_of(l, c / T) * N + tile0 * TOK;
+      o.cold = (t == 0);
+      o.pol = (t == T - 1) ? pol_drop : pol_keep;
+    }
+    return o;
+  };
+  // refill of stage j % S with tile (op, tile) and paced prefetch; `cur` / `nxt` describe ops n and n + 1
+  auto refill_fast = [&](int n, int tile, const OpInfo& cur, const OpInfo& nxt) {
+    int tn = tile + S;
+    const OpInfo& o = (tn < TP) ? cur : nxt;
+    const int nn = (tn < TP) ? n : n + 1;
+    if (tn >= TP) tn -= TP;
+    if (o.valid) {
+      const int j = nn * TP + tn;
+      const int s = j % S;
+      const int row0 = o.row_base + tn * TOK;
+      unsigned char* kd = ring + (size_t)s * C::STAGE_BYTES;
+      mbar_expect_tx(&full[s], (uint32_t)C::STAGE_BYTES);
+      tma_load_3d_hint(kd, &tm_k, 0, 0, row0, &full[s], o.pol);
+      tma_load_3d_hint(kd + C::TILE_BYTES, &tm_v, 0, 0, row0, &full[s], o.pol);
+      sts_volatile(&issued[s], j);
+    }
+    int pt = tile + PFD;
+    const OpInfo& po = (pt < TP) ? cur : nxt;
+    if (pt >= TP) pt -= TP;
+    if (po.valid && po.cold) {
+      const size_t off = (size_t)(po.row_base + pt * TOK) * (D * 2);
+      if (off + C::TILE_BYTES <= (size_t)B * N * D * 2) {
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(a.k) + off), "r"(C::TILE_BYTES) : "memory");
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(a.v) + off), "r"(C::TILE_BYTES) : "memory");
+      }
+    }
   };
   // tile (n, tile) + S in stream order, or n = -1 past the end
   auto advance = [&](int& n, int& tile) {
@@ -161,7 +225,7 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
     for (int s = 0; s < S; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&w_ready[s], 1);
-      issued[s] = -1;
+      sts_volatile(&issued[s], -1);
     }
     mbar_init(&xbar[0], 1);
     mbar_init(&xbar[1], 1);
@@ -170,10 +234,13 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
     mbar_init(&q_ready[0], 1);
     mbar_init(&q_ready[1], 1);
     mbar_fence_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_k) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_v) : "memory");
     // first tiles: their HBM latency overlaps the weight load below
     if (TP > 0)
       for (int p = 0; p < S; ++p)
         if (p / TP < total_ops) issue_tile(p / TP, p % TP);
+
   }
   {
     // the CTA's weight slices, fp32 global -> bf16 shared; eight independent 16-byte loads in flight per thread
@@ -257,7 +324,7 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
           uint32_t* wt = reinterpret_cast<uint32_t*>(wtiles + s * C::WT_BYTES);
           const bool tt = tracer && tid == 0 && n == TRACE_OP && tile < 32;  // tile stamps of chain 0 in a steady-state op
           if (tt) a.trace[340 + (tile >> 2) * 8 + 0] = clock64();
-          while (issued[s] < j) __nanosleep(32);  // the barrier has entered this tile's phase (parity waits alias)
+          while (lds_volatile(&issued[s]) < j) __nanosleep(20);  // the barrier has entered this tile's phase (parity waits alias)
           mbar_wait(&full[s], ph);
           if (tt) a.trace[340 + (tile >> 2) * 8 + 1] = clock64();
           float ca[4] = {0.f, 0.f, 0.f, 0.f}, cb[4] = {0.f, 0.f, 0.f, 0.f};
@@ -316,7 +383,7 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
               if (tk < N) {
                 float* ao = a.attn_out + ((size_t)img * N + tk) * K;
                 if ((K & 1) == 0) {
-                  if (ok0) *reinterpret_cast<float2*>(ao + c0) = make_float2(av[2 * hrow], av[2 * hrow + 1]);
+                  if (ok0) __stcs(reinterpret_cast<float2*>(ao + c0), make_float2(av[2 * hrow], av[2 * hrow + 1]));
                 } else {
                   if (ok0) ao[c0] = av[2 * hrow];
                   if (ok1) ao[c1] = av[2 * hrow + 1];
@@ -358,6 +425,8 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
 #pragma unroll
           for (int e = 0; e < 4; ++e) acc[i][e] = 0.f;
         const int urow = (lane & 7) + (lane >> 4) * 8, uhalf = ((lane >> 3) & 1) * 16;
+        const bool fast = (S <= TP) && (PFD <= TP);
+        const OpInfo oi_cur = op_info(n), oi_nxt = op_info(n + 1);
         for (int tile = uw; tile < TP; tile += 4) {
           const int j = jbase + tile;
           const int s = j % S;
@@ -366,7 +435,7 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
           const uint32_t* wt = reinterpret_cast<const uint32_t*>(wtiles + s * C::WT_BYTES);
           const bool tt = tracer && tid == 128 && n == TRACE_OP && tile < 32;
           if (tt) a.trace[340 + (tile >> 2) * 8 + 4] = clock64();
-          while (issued[s] < j) __nanosleep(32);
+          while (lds_volatile(&issued[s]) < j) __nanosleep(20);
           mbar_wait(&w_ready[s], ph);  // implies full[s]: the logit warp waited for k and v together
           if (tt) a.trace[340 + (tile >> 2) * 8 + 5] = clock64();
           const uint32_t b0 = wt[lane], b1 = wt[32 + lane];
@@ -379,9 +448,13 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
           __syncwarp();  // every lane is done with the stage (this warp is its only remaining reader)
           if (tt) a.trace[340 + (tile >> 2) * 8 + 6] = clock64();
           if (lane == 0) {
-            int nn = n, tn = tile;
-            advance(nn, tn);
-            if (nn >= 0) issue_tile(nn, tn);
+            if (fast) {
+              refill_fast(n, tile, oi_cur, oi_nxt);
+            } else {
+              int nn = n, tn = tile;
+              advance(nn, tn);
+              if (nn >= 0) issue_tile(nn, tn);
+            }
           }
           if (tt) a.trace[340 + (tile >> 2) * 8 + 7] = clock64();
         }
@@ -560,6 +633,9 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(u_free);  // the pass engine may overwrite the staging buffers
+      // gh = W_hh h only needs the slots that entered the iteration: computed under the R1 round trip
+      for (int job = uwarp; job < NMG; job += 8)
+        mma_job<false>(s_whh, PITCH, 3 * DS, s_zrow, job, 0, D / 16, slh_hi(l), slh_lo(l), PITCH, P + NMG * 128, lane);
       xwait(round);
       PP_T(3);
       // ============================================================ R2: all-gather updates = sum over CTAs / token sum
@@ -588,12 +664,11 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
       to_hilo(reinterpret_cast<const float*>(xb(round)), D, act_hi, act_lo, PITCHX);
       ++round;
       upd_sync();
-      // ---- GRU: gi = W_ih u, gh = W_hh h
+      // ---- GRU: gi = W_ih u (k split in two halves: 2 * NMG jobs keep all 8 warps busy; halves summed in the epilogue)
       for (int job = uwarp; job < 2 * NMG; job += 8) {
-        const bool hh = job >= NMG;
-        const int mt = hh ? job - NMG : job;
-        mma_job<false>(hh ? s_whh : s_wih, PITCH, 3 * DS, s_zrow, mt, 0, D / 16, hh ? slh_hi(l) : act_hi, hh ? slh_lo(l) : act_lo,
-                hh ? PITCH : PITCHX, P + (hh ? NMG * 128 : 0), lane);
+        const int mt = job >> 1, half = job & 1;
+        mma_job<false>(s_wih, PITCH, 3 * DS, s_zrow, mt, half * (D / 32), (half + 1) * (D / 32), act_hi, act_lo, PITCHX,
+                       P + (half ? 2 * NMG * 128 : 0), lane);
       }
       arm(round, (uint32_t)(K * D * 4));
       upd_sync();
@@ -605,10 +680,12 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
         if (i < K * DS) {
           const int slot = i / DS, dl = i % DS;
           const float* Pi = P;
+          const float* Pj = P + 2 * NMG * 128;  // second k half of W_ih u
           const float* Ph = P + NMG * 128;
-          const float gir = Pi[(dl) * 8 + slot] + s_bih[dl], ghr = Ph[(dl) * 8 + slot] + s_bhh[dl];
-          const float giz = Pi[(DS + dl) * 8 + slot] + s_bih[DS + dl], ghz = Ph[(DS + dl) * 8 + slot] + s_bhh[DS + dl];
-          const float gin = Pi[(2 * DS + dl) * 8 + slot] + s_bih[2 * DS + dl];
+          const float gir = Pi[(dl) * 8 + slot] + Pj[(dl) * 8 + slot] + s_bih[dl], ghr = Ph[(dl) * 8 + slot] + s_bhh[dl];
+          const float giz = Pi[(DS + dl) * 8 + slot] + Pj[(DS + dl) * 8 + slot] + s_bih[DS + dl];
+          const float ghz = Ph[(DS + dl) * 8 + slot] + s_bhh[DS + dl];
+          const float gin = Pi[(2 * DS + dl) * 8 + slot] + Pj[(2 * DS + dl) * 8 + slot] + s_bih[2 * DS + dl];
           const float ghn = Ph[(2 * DS + dl) * 8 + slot] + s_bhh[2 * DS + dl];
           const float r = sigmoidf_(gir + ghr), z = sigmoidf_(giz + ghz);
           const float nn = tanhf(gin + r * ghn);
@@ -731,6 +808,10 @@ static int launch_pipe(const IterFwdArgs& a, cudaStream_t stream) {
   if (const char* e = getenv("OCRL_SA_PC_CLUSTERS")) ncl = max(1, min(ncl, atoi(e)));
   const int want = (a.B + 1) / 2;  // two lanes per cluster
   if (ncl > want) ncl = want;
+  {  // fewest clusters that keep the same number of image rounds (frees SMs for concurrent work)
+    const int per = (a.B + ncl - 1) / ncl;
+    ncl = (a.B + per - 1) / per;
+  }
   cfg.gridDim = dim3((unsigned)(ncl * CL));
   OCRL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, a, tm_k, tm_v));
   return OCRL_OK;
