@@ -97,7 +97,7 @@ def time_cpu(a, frames_u8, steps, warmup):
     return a.batch * steps / dt, dt / steps * 1e3, cores
 
 
-def run_reference(a, rank):
+def run_reference(a, rank, out=sys.stdout):
     """--impl reference: the reference's CPU path for the same metric and config."""
     if rank != 0:
         return
@@ -113,7 +113,7 @@ def run_reference(a, rank):
             "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -292,13 +292,23 @@ def roofline_of(a, mode, events):
                             "algorithmic_bytes_per_image": tok_bytes_img}}
 
 
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Native libraries (NCCL prints its version banner with C stdio)
+    write to file descriptor 1 too, so fd 1 is pointed at stderr and the JSON line goes to a private duplicate."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
     a = parse()
+    out = _claim_stdout()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     if a.impl == "reference":
-        run_reference(a, rank)
+        run_reference(a, rank, out)
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the ocrl_b200 path has no CPU fallback; use --impl reference)")
@@ -360,7 +370,7 @@ def main():
             line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{csteps} batches of {a.batch} frames ({cms:.0f} ms each), oracle port "
                                               f"of the reference path with torch CPU ops, fp32"}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out, flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
