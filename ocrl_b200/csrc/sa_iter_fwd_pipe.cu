@@ -23,9 +23,9 @@ using namespace pc;
 #define TRACE_OP 2
 #endif
 
-template <int D_, int H_, int CL_, int S_>
+template <int D_, int H_, int CL_, int S_, int NL_>
 struct Cfg {
-  static constexpr int D = D_, H = H_, CL = CL_, S = S_;
+  static constexpr int D = D_, H = H_, CL = CL_, S = S_, NL = NL_;  // NL image lanes per cluster
   static constexpr int KP = 8, NT = 512, TOK = 16;
   static constexpr int PITCH = D * 2 + 16, PITCHH = H * 2 + 16;
   static constexpr int LX = D > H ? D : H;
@@ -45,28 +45,29 @@ struct Cfg {
   static constexpr int OFF_W2 = OFF_W1 + HS * PITCH;
   static constexpr int OFF_WQ = OFF_W2 + DS * PITCHH;
   static constexpr int OFF_ZROW = OFF_WQ + DS * PITCH;
-  static constexpr int OFF_LNP = OFF_ZROW + PITCHX;
-  static constexpr int OFF_BIAS = OFF_LNP + 4 * D * 4;
-  static constexpr int XBUF_BYTES = KP * LX * 4 + 32 * CL;
-  static constexpr int OFF_XBUF = (OFF_BIAS + (7 * DS + HS) * 4 + 15) & ~15;
-  static constexpr int OFF_ACT = OFF_XBUF + 2 * XBUF_BYTES;        // activation staging, bf16 (update engine)
+  static constexpr int OFF_BIAS = (OFF_ZROW + PITCHX + 15) & ~15;  // (the LayerNorm affine parameters are folded into W1', Wq')
+  // fp32 constants: b_ih[3DS] b_hh[3DS] b1'[HS] b2[DS] c1[HS] cq[DS] bq'[DS] + LayerNorm stats mean[8] rstd[8]
+  static constexpr int NCONST = 9 * DS + 2 * HS + 16;
+  static constexpr int XBUF_BYTES = KP * D * 4 + 32 * CL;          // R1 receive buffer (fp32 partial sums), single
+  static constexpr int OFF_XBUF = (OFF_BIAS + NCONST * 4 + 15) & ~15;
+  static constexpr int OFF_ACT = OFF_XBUF + XBUF_BYTES;            // bf16 all-gather targets, by round parity
   static constexpr int P_ROWS = (3 * NMG > NKC * (NM1 > NM2 ? NM1 : NM2)) ? 3 * NMG * 16 : NKC * (NM1 > NM2 ? NM1 : NM2) * 16;
-  static constexpr int OFF_P = OFF_ACT + KP * PITCHX;              // MMA partial outputs
+  static constexpr int OFF_P = OFF_ACT + 2 * KP * PITCHX;          // MMA partial outputs
   static constexpr int OFF_UST = OFF_P + P_ROWS * 32;              // U staging a, b (pass -> update hand-off)
   static constexpr int OFF_SRED = OFF_UST + 2 * KP * UP * 4;       // [4][8] token sums of the logit warps
   static constexpr int OFF_LANE = OFF_SRED + 128;                  // per lane: slots hi/lo, q (bf16), own slice (fp32)
   static constexpr int LANE_BYTES = KP * PITCH + KP * PITCH + KP * DS * 4;
-  static constexpr int OFF_BAR = (OFF_LANE + 2 * LANE_BYTES + 15) & ~15;  // full[S] w_ready[S] xbar[2] u_ready u_free q_ready[2]
-  static constexpr int OFF_ISSUED = OFF_BAR + (2 * S + 6) * 8;
+  static constexpr int OFF_BAR = (OFF_LANE + NL * LANE_BYTES + 15) & ~15;  // full[S] w_ready[S] xbar[2] u_ready u_free q_ready[NL]
+  static constexpr int OFF_ISSUED = OFF_BAR + (2 * S + 4 + NL) * 8;
   static constexpr int SMEM_BYTES = OFF_ISSUED + S * 4 + 1024;     // + slack for the manual 1024-byte alignment
 };
 
 __device__ __forceinline__ void upd_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-template <int D, int H, int CL, int S>
+template <int D, int H, int CL, int S, int NL>
 __global__ void __launch_bounds__(512, 1)
 sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v) {
-  using C = Cfg<D, H, CL, S>;
+  using C = Cfg<D, H, CL, S, NL>;
   constexpr int KP = C::KP, PITCH = C::PITCH, PITCHH = C::PITCHH, PITCHX = C::PITCHX, DS = C::DS, HS = C::HS;
   constexpr int NMU = C::NMU, NMG = C::NMG, NM1 = C::NM1, NM2 = C::NM2, NKC = C::NKC, UP = C::UP, TOK = C::TOK;
   constexpr float LOG2E = 1.4426950408889634f;
@@ -91,21 +92,23 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
   unsigned char* s_w2 = sm + C::OFF_W2;
   unsigned char* s_wq = sm + C::OFF_WQ;
   unsigned char* s_zrow = sm + C::OFF_ZROW;
-  float* s_lnp = reinterpret_cast<float*>(sm + C::OFF_LNP);
   float* s_bias = reinterpret_cast<float*>(sm + C::OFF_BIAS);
   const float* s_bih = s_bias;
   const float* s_bhh = s_bias + 3 * DS;
-  const float* s_b1 = s_bias + 6 * DS;
+  float* s_b1f = s_bias + 6 * DS;            // b1 + W1 . beta_mlp
   const float* s_b2 = s_bias + 6 * DS + HS;
+  float* s_c1 = s_bias + 7 * DS + HS;        // row sums of the folded bf16 W1'
+  float* s_cq = s_bias + 7 * DS + 2 * HS;    // row sums of the folded bf16 Wq'
+  float* s_bqf = s_bias + 8 * DS + 2 * HS;   // Wq . beta_slots
+  float* s_mean = s_bias + 9 * DS + 2 * HS;  // LayerNorm statistics of the round in flight
+  float* s_rstd = s_mean + 8;
   unsigned char* xbuf = sm + C::OFF_XBUF;
-  unsigned char* act_hi = sm + C::OFF_ACT;
-  unsigned char* act_lo = nullptr;  // activations are single bf16 in this kernel (the legacy HMMA pipe is the scarce unit)
+  auto act = [&](uint32_t r) { return sm + C::OFF_ACT + (r & 1) * (KP * PITCHX); };  // bf16 [8][PITCHX]
   float* P = reinterpret_cast<float*>(sm + C::OFF_P);
   float* ustage_a = reinterpret_cast<float*>(sm + C::OFF_UST);
   float* ustage_b = ustage_a + KP * UP;
   float* sred = reinterpret_cast<float*>(sm + C::OFF_SRED);
   auto slh_hi = [&](int l) { return sm + C::OFF_LANE + l * C::LANE_BYTES; };
-  auto slh_lo = [&](int) { return (unsigned char*)nullptr; };
   auto qbuf = [&](int l) { return sm + C::OFF_LANE + l * C::LANE_BYTES + KP * PITCH; };
   auto own_of = [&](int l) { return reinterpret_cast<float*>(sm + C::OFF_LANE + l * C::LANE_BYTES + 2 * KP * PITCH); };
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
@@ -121,15 +124,42 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
   // Images are dealt to clusters round-robin (newest first: the projection kernel left them in L2) and a cluster
   // alternates its images between its two lanes, so every cluster gets floor or ceil of B / #clusters images.
   const int ncimg = (B > cid) ? (B - cid + ncl - 1) / ncl : 0;
-  int nimg[2];
-  nimg[0] = (ncimg + 1) / 2;
-  nimg[1] = ncimg / 2;
-  const int nops0 = nimg[0] * T, nops1 = nimg[1] * T;  // nops0 >= nops1
-  const int total_ops = nops0 + nops1;
+  // Lane l takes the cluster's images l, l + NL, ...; ops (one pass + one update of one lane) are streamed row by row:
+  // row c holds op c of every lane that still has one, lanes in order (lane counts are non-increasing in l and
+  // differ by at most one image).  With NL = 3 an update has two pass slots to finish in, so the stream advances at
+  // the pace of the pass engine alone.
+  int nops[NL], row_start[NL + 1], row_width[NL + 1], seg_base[NL + 1];
+  auto nimg_of = [&](int l) { return (ncimg > l) ? (ncimg - l + NL - 1) / NL : 0; };
+#pragma unroll
+  for (int l = 0; l < NL; ++l) nops[l] = nimg_of(l) * T;
+  // segments of rows with constant width: width NL while c < nops[NL-1], NL-1 while c < nops[NL-2], ...
+  int total_ops = 0;
+  {
+    int prev = 0;
+#pragma unroll
+    for (int g = 0; g < NL; ++g) {
+      const int w = NL - g;               // active lanes in this segment
+      const int upto = nops[w - 1];       // rows [prev, upto)
+      row_start[g] = prev;
+      row_width[g] = w;
+      seg_base[g] = total_ops;
+      total_ops += (upto - prev) * w;
+      prev = upto;
+    }
+    row_start[NL] = prev; row_width[NL] = 1; seg_base[NL] = total_ops;
+  }
   auto op_of = [&](int n, int& l, int& c) {
-    if (n < 2 * nops1) { l = n & 1; c = n >> 1; } else { l = 0; c = n - nops1; }
+    l = 0; c = 0;
+#pragma unroll
+    for (int g = 0; g < NL; ++g) {
+      if (n >= seg_base[g] && n < seg_base[g + 1]) {
+        const int r = n - seg_base[g];
+        c = row_start[g] + r / row_width[g];
+        l = r % row_width[g];
+      }
+    }
   };
-  auto image_of = [&](int l, int m) { return B - 1 - (cid + (2 * m + l) * ncl); };
+  auto image_of = [&](int l, int m) { return B - 1 - (cid + (NL * m + l) * ncl); };
   const int ntiles = (N + TOK - 1) / TOK;
   const int TPC = (ntiles + CL - 1) / CL;
   const int tile0 = rank * TPC;
@@ -231,8 +261,7 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
     mbar_init(&xbar[1], 1);
     mbar_init(u_ready, 8);
     mbar_init(u_free, 8);
-    mbar_init(&q_ready[0], 1);
-    mbar_init(&q_ready[1], 1);
+    for (int l = 0; l < NL; ++l) mbar_init(&q_ready[l], 1);
     mbar_fence_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_k) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_v) : "memory");
@@ -268,26 +297,48 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
       load_rows(s_wih + gate * DS * PITCH, PITCH, a.w.w_ih + ((size_t)gate * D + rank * DS) * D, D, DS);
       load_rows(s_whh + gate * DS * PITCH, PITCH, a.w.w_hh + ((size_t)gate * D + rank * DS) * D, D, DS);
     }
-    load_rows(s_w1, PITCH, a.w.w1 + (size_t)rank * HS * D, D, HS);
     load_rows(s_w2, PITCHH, a.w.w2 + (size_t)rank * DS * H, H, DS);
-    load_rows(s_wq, PITCH, a.w.wq + (size_t)rank * DS * D, D, DS);
-    for (int i = tid; i < PITCHX / 4; i += C::NT) reinterpret_cast<uint32_t*>(s_zrow)[i] = 0u;
-    for (int i = tid; i < D; i += C::NT) {
-      s_lnp[i] = a.w.ln_slots_w[i];
-      s_lnp[D + i] = a.w.ln_slots_b[i];
-      s_lnp[2 * D + i] = a.w.ln_mlp_w[i];
-      s_lnp[3 * D + i] = a.w.ln_mlp_b[i];
+    // LayerNorm folded into the product that follows it:  W LN(x) = rstd (W' x - mean c) + W beta,  W' = W diag(gamma),
+    // c = row sums of the (bf16-rounded) W'.  One warp per row.
+    {
+      constexpr int NCH = D / 64;
+      for (int r = warp; r < HS + DS; r += C::NT / 32) {
+        const bool is1 = r < HS;
+        const int rr = is1 ? r : r - HS;
+        const float* wrow = is1 ? a.w.w1 + ((size_t)rank * HS + rr) * D : a.w.wq + ((size_t)rank * DS + rr) * D;
+        const float* gam = is1 ? a.w.ln_mlp_w : a.w.ln_slots_w;
+        const float* bet = is1 ? a.w.ln_mlp_b : a.w.ln_slots_b;
+        unsigned char* drow = (is1 ? s_w1 : s_wq) + rr * PITCH;
+        float csum = 0.f, bsum = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int d = 64 * c + 2 * lane;
+          const float2 wv = __ldg(reinterpret_cast<const float2*>(wrow + d));
+          const float2 g = __ldg(reinterpret_cast<const float2*>(gam + d));
+          const float2 b = __ldg(reinterpret_cast<const float2*>(bet + d));
+          const __nv_bfloat162 wf = __floats2bfloat162_rn(wv.x * g.x, wv.y * g.y);
+          *reinterpret_cast<__nv_bfloat162*>(drow + d * 2) = wf;
+          csum += __low2float(wf) + __high2float(wf);
+          bsum = fmaf(wv.x, b.x, fmaf(wv.y, b.y, bsum));
+        }
+        csum = warp_sum(csum);
+        bsum = warp_sum(bsum);
+        if (lane == 0) {
+          if (is1) { s_c1[rr] = csum; s_b1f[rr] = bsum + a.w.b1[rank * HS + rr]; }
+          else { s_cq[rr] = csum; s_bqf[rr] = bsum; }
+        }
+      }
     }
+    for (int i = tid; i < PITCHX / 4; i += C::NT) reinterpret_cast<uint32_t*>(s_zrow)[i] = 0u;
     for (int i = tid; i < 3 * DS; i += C::NT) {
       const int gate = i / DS, dl = i % DS;
       s_bias[i] = a.w.b_ih[gate * D + rank * DS + dl];
       s_bias[3 * DS + i] = a.w.b_hh[gate * D + rank * DS + dl];
     }
-    for (int i = tid; i < HS; i += C::NT) s_bias[6 * DS + i] = a.w.b1[rank * HS + i];
     for (int i = tid; i < DS; i += C::NT) s_bias[6 * DS + HS + i] = a.w.b2[rank * DS + i];
     // staging rows of the padded slots are never written by the conversions; keep them finite
-    for (int i = tid; i < (KP * PITCHX) / 4; i += C::NT) reinterpret_cast<uint32_t*>(act_hi)[i] = 0u;
-    for (int i = tid; i < (2 * C::LANE_BYTES) / 4; i += C::NT) reinterpret_cast<uint32_t*>(sm + C::OFF_LANE)[i] = 0u;
+    for (int i = tid; i < (2 * KP * PITCHX) / 4; i += C::NT) reinterpret_cast<uint32_t*>(sm + C::OFF_ACT)[i] = 0u;
+    for (int i = tid; i < (NL * C::LANE_BYTES) / 4; i += C::NT) reinterpret_cast<uint32_t*>(sm + C::OFF_LANE)[i] = 0u;
   }
   __syncthreads();
   cluster.sync();  // every CTA's barriers are initialised before any peer signals them
@@ -480,124 +531,102 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
     }
   } else {
     // ==================================================================================== UPDATE ENGINE
+    // Every exchange round is  push -> wait -> tensor-core product -> one barrier -> epilogue (= next push):
+    // all-gather payloads travel as bf16 straight into the receivers' MMA staging buffers (act[parity], slh[lane],
+    // qbuf[lane]); the LayerNorms are folded into the products that follow them (statistics from the received rows).
     const int utid = tid - 256, uwarp = warp - 8;
     uint32_t round = 0;
-    auto xb = [&](uint32_t r) { return xbuf + (r & 1) * C::XBUF_BYTES; };
+    unsigned char* xb = xbuf;
     auto arm = [&](uint32_t r, uint32_t bytes) {
       if (utid == 0) mbar_expect_tx(&xbar[r & 1], bytes);
     };
     auto xwait = [&](uint32_t r) { mbar_wait_cluster(&xbar[r & 1], (r >> 1) & 1); };
-    // All-gather push without staging: thread i < K*SL holds element (slot = i / SL, f = i % SL) of the CTA's
-    // slice.  The four lanes of a quad assemble the float4 of features 4*(f/4).. and each sends it to CL/4 CTAs.
-    auto quad_push = [&](uint32_t r, float val, int i, int SL, int pitchf) {
+    // All-gather push: thread i < K*SL holds element (slot = i / SL, f = i % SL) of the CTA's slice.  The four lanes
+    // of a quad assemble 4 features (8 bytes of bf16) and each sends them to CL/4 CTAs, into `dst` ([8][pitch] bf16).
+    auto quad_push = [&](uint32_t r, float val, int i, int SL, unsigned char* dst, int pitch) {
       const int qb = lane & ~3;
-      float4 v4;
-      v4.x = __shfl_sync(FULL, val, qb);
-      v4.y = __shfl_sync(FULL, val, qb + 1);
-      v4.z = __shfl_sync(FULL, val, qb + 2);
-      v4.w = __shfl_sync(FULL, val, qb + 3);
+      const float v0 = __shfl_sync(FULL, val, qb), v1 = __shfl_sync(FULL, val, qb + 1);
+      const float v2 = __shfl_sync(FULL, val, qb + 2), v3 = __shfl_sync(FULL, val, qb + 3);
       if (i < K * SL) {
         const int slot = i / SL, f4 = (i % SL) & ~3;
-        const uint32_t lbuf = smem_u32(xb(r)) + (uint32_t)((slot * pitchf + rank * SL + f4) * 4);
+        const uint32_t lbuf = smem_u32(dst) + (uint32_t)(slot * pitch + (rank * SL + f4) * 2);
         const uint32_t lbar = smem_u32(&xbar[r & 1]);
+        const uint32_t lo = pack_bf16x2(v0, v1), hi = pack_bf16x2(v2, v3);
 #pragma unroll
         for (int q = 0; q < CL / 4; ++q) {
           const int dest = (lane & 3) + 4 * q;
-          st_async_v4(mapa_u32(lbuf, dest), v4, mapa_u32(lbar, dest));
+          st_async_v2(mapa_u32(lbuf, dest), lo, hi, mapa_u32(lbar, dest));
         }
       }
     };
-    auto to_hilo = [&](const float* src, int L, unsigned char* hi, unsigned char* lo, int ap) {
-      for (int i = utid; i < K * (L / 2); i += 256) {
-        const int slot = i / (L / 2), c2 = i % (L / 2);
-        const float2 x = *reinterpret_cast<const float2*>(src + slot * L + 2 * c2);
-        *reinterpret_cast<uint32_t*>(hi + slot * ap + 4 * c2) = pack_bf16x2(x.x, x.y);
-        (void)lo;
-      }
-    };
-    auto ln_to_hilo = [&](const float* src, const float* gw, const float* gbias, unsigned char* hi, unsigned char* lo,
-                          unsigned char* raw_hi, unsigned char* raw_lo) {
+    // mean / rstd of the K rows (bf16, length D) that just arrived: one warp per row
+    auto row_stats = [&](const unsigned char* rows, int pitch) {
       constexpr int NCH = D / 64;
       if (uwarp < K) {
         float2 x[NCH];
         float s = 0.f;
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
-          x[c] = *reinterpret_cast<const float2*>(src + uwarp * D + 64 * c + 2 * lane);
+          const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(rows + uwarp * pitch + (64 * c + 2 * lane) * 2);
+          x[c] = make_float2(__low2float(v), __high2float(v));
           s += x[c].x + x[c].y;
-          if (raw_hi != nullptr)
-            *reinterpret_cast<uint32_t*>(raw_hi + uwarp * PITCH + (64 * c + 2 * lane) * 2) = pack_bf16x2(x[c].x, x[c].y);
-          (void)raw_lo;
         }
         const float mean = warp_sum(s) * (1.f / D);
         float q = 0.f;
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
-          x[c].x -= mean;
-          x[c].y -= mean;
-          q = fmaf(x[c].x, x[c].x, fmaf(x[c].y, x[c].y, q));
+          const float dx = x[c].x - mean, dy = x[c].y - mean;
+          q = fmaf(dx, dx, fmaf(dy, dy, q));
         }
         const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + a.ln_eps);
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          const float2 g = *reinterpret_cast<const float2*>(gw + 64 * c + 2 * lane);
-          const float2 b = *reinterpret_cast<const float2*>(gbias + 64 * c + 2 * lane);
-          *reinterpret_cast<uint32_t*>(hi + uwarp * PITCHX + (64 * c + 2 * lane) * 2) =
-              pack_bf16x2(x[c].x * rstd * g.x + b.x, x[c].y * rstd * g.y + b.y);
-          (void)lo;
-        }
+        if (lane == 0) { s_mean[uwarp] = mean; s_rstd[uwarp] = rstd; }
       }
     };
-    // q = W_q . LN(slots) of lane l for the CTA's slice, all-gathered as bf16 (times log2 e) into every CTA's qbuf[l]
-    auto q_phase = [&](int l, const float* slots_full /* [K][D], shared or global */) {
-      arm(round, (uint32_t)(K * D * 2));
-      ln_to_hilo(slots_full, s_lnp, s_lnp + D, act_hi, act_lo, slh_hi(l), slh_lo(l));
+    // slots of image `img` (fp32, global) -> this CTA's bf16 copy slh[l] and the fp32 own slice
+    auto load_slots0 = [&](int l, int img) {
+      const float* src = a.slots0 + (size_t)img * K * D;
+      unsigned char* dst = slh_hi(l);
+      for (int i = utid; i < K * (D / 2); i += 256) {
+        const int slot = i / (D / 2), c2 = i % (D / 2);
+        const float2 x = __ldg(reinterpret_cast<const float2*>(src + slot * D + 2 * c2));
+        *reinterpret_cast<uint32_t*>(dst + slot * PITCH + 4 * c2) = pack_bf16x2(x.x, x.y);
+      }
+      float* own = own_of(l);
+      for (int i = utid; i < K * DS; i += 256) own[i] = __ldg(src + (i / DS) * D + rank * DS + i % DS);
       upd_sync();
+    };
+    // q = W_q LN(slots) of lane l for the CTA's slice (slots = slh[l], bf16), all-gathered (times log2 e) into qbuf[l]
+    auto q_phase = [&](int l) {
       for (int job = uwarp; job < NM2 * NKC; job += 8) {
         const int mt = job / NKC, kc = job % NKC;
-        mma_job<false>(s_wq, PITCH, DS, s_zrow, mt, kc * (D / 16) / NKC, (kc + 1) * (D / 16) / NKC, act_hi, act_lo, PITCHX,
-                P + kc * NM2 * 128, lane);
+        mma_job<false>(s_wq, PITCH, DS, s_zrow, mt, kc * (D / 16) / NKC, (kc + 1) * (D / 16) / NKC, slh_hi(l), nullptr, PITCH,
+                       P + kc * NM2 * 128, lane);
       }
+      row_stats(slh_hi(l), PITCH);
+      arm(round, (uint32_t)(K * D * 2));
       upd_sync();
-      const int nel = K * DS;
-      for (int i0 = uwarp * 32; i0 < nel; i0 += 256) {
+      for (int i0 = uwarp * 32; i0 < K * DS; i0 += 256) {
         const int i = i0 + lane;
         float val = 0.f;
-        if (i < nel) {
+        if (i < K * DS) {
           const int slot = i / DS, dl = i % DS;
+          float acc = 0.f;
 #pragma unroll
-          for (int kc = 0; kc < NKC; ++kc) val += P[(kc * NM2 * 16 + dl) * 8 + slot];
-          val *= LOG2E;
+          for (int kc = 0; kc < NKC; ++kc) acc += P[(kc * NM2 * 16 + dl) * 8 + slot];
+          val = (s_rstd[slot] * (acc - s_mean[slot] * s_cq[dl]) + s_bqf[dl]) * LOG2E;
         }
-        const int qb = lane & ~3;
-        const float v0 = __shfl_sync(FULL, val, qb), v1 = __shfl_sync(FULL, val, qb + 1);
-        const float v2 = __shfl_sync(FULL, val, qb + 2), v3 = __shfl_sync(FULL, val, qb + 3);
-        if (i < nel) {
-          const int slot = i / DS, f4 = (i % DS) & ~3;
-          const uint32_t lbuf = smem_u32(qbuf(l)) + (uint32_t)(slot * PITCH + (rank * DS + f4) * 2);
-          const uint32_t lbar = smem_u32(&xbar[round & 1]);
-          const uint32_t lo = pack_bf16x2(v0, v1), hi = pack_bf16x2(v2, v3);
-#pragma unroll
-          for (int q = 0; q < CL / 4; ++q) {
-            const int dest = (lane & 3) + 4 * q;
-            st_async_v2(mapa_u32(lbuf, dest), lo, hi, mapa_u32(lbar, dest));
-          }
-        }
+        quad_push(round, val, i, DS, qbuf(l), PITCH);
       }
       xwait(round);
       ++round;
       if (utid == 0) mbar_arrive(&q_ready[l]);  // the logit warps of lane l may load their q fragments
     };
-    auto load_own = [&](int l, int img) {
-      float* own = own_of(l);
-      for (int i = utid; i < K * DS; i += 256) own[i] = a.slots0[((size_t)img * K + i / DS) * D + rank * DS + i % DS];
-    };
 
     // initial queries of both lanes
-    for (int l = 0; l < 2; ++l)
-      if (nimg[l] > 0) {
-        load_own(l, image_of(l, 0));
-        q_phase(l, a.slots0 + (size_t)image_of(l, 0) * K * D);
+    for (int l = 0; l < NL; ++l)
+      if (nops[l] > 0) {
+        load_slots0(l, image_of(l, 0));
+        q_phase(l);
       }
 
     for (int n = 0; n < total_ops; ++n) {
@@ -613,7 +642,7 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
       mbar_wait(u_ready, (uint32_t)(n & 1));
       PP_T(2);
       {
-        const uint32_t lbuf = smem_u32(xb(round)), lbar = smem_u32(&xbar[round & 1]);
+        const uint32_t lbuf = smem_u32(xb), lbar = smem_u32(&xbar[round & 1]);
         constexpr int QPR = D / 4;
         for (int i = utid; i < K * QPR; i += 256) {
           const int slot = i / QPR, d = 4 * (i % QPR);
@@ -635,42 +664,40 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
       if (lane == 0) mbar_arrive(u_free);  // the pass engine may overwrite the staging buffers
       // gh = W_hh h only needs the slots that entered the iteration: computed under the R1 round trip
       for (int job = uwarp; job < NMG; job += 8)
-        mma_job<false>(s_whh, PITCH, 3 * DS, s_zrow, job, 0, D / 16, slh_hi(l), slh_lo(l), PITCH, P + NMG * 128, lane);
+        mma_job<false>(s_whh, PITCH, 3 * DS, s_zrow, job, 0, D / 16, slh_hi(l), nullptr, PITCH, P + NMG * 128, lane);
       xwait(round);
+      ++round;
       PP_T(3);
       // ============================================================ R2: all-gather updates = sum over CTAs / token sum
-      arm(round + 1, (uint32_t)(K * D * 4));
+      arm(round, (uint32_t)(K * D * 2));
       {
-        const float* rs = reinterpret_cast<const float*>(xb(round));
+        const float* rs = reinterpret_cast<const float*>(xb);
         const float* ss = rs + KP * D;
         for (int i0 = uwarp * 32; i0 < K * DS; i0 += 256) {
           const int i = i0 + lane;
           float val = 0.f;
           if (i < K * DS) {
             const int slot = i / DS, dl = i % DS;
-            float u = 0.f, s = 0.f;
+            float u = 0.f, sw = 0.f;
 #pragma unroll
             for (int src = 0; src < CL; ++src) {
               u += rs[(src * KP + slot) * DS + dl];
-              s += ss[src * 8 + slot];
+              sw += ss[src * 8 + slot];
             }
-            val = u / s;
+            val = u / sw;
           }
-          quad_push(round + 1, val, i, DS, D);
+          quad_push(round, val, i, DS, act(round), PITCHX);
         }
       }
-      ++round;
       xwait(round);
-      to_hilo(reinterpret_cast<const float*>(xb(round)), D, act_hi, act_lo, PITCHX);
-      ++round;
-      upd_sync();
       // ---- GRU: gi = W_ih u (k split in two halves: 2 * NMG jobs keep all 8 warps busy; halves summed in the epilogue)
       for (int job = uwarp; job < 2 * NMG; job += 8) {
         const int mt = job >> 1, half = job & 1;
-        mma_job<false>(s_wih, PITCH, 3 * DS, s_zrow, mt, half * (D / 32), (half + 1) * (D / 32), act_hi, act_lo, PITCHX,
+        mma_job<false>(s_wih, PITCH, 3 * DS, s_zrow, mt, half * (D / 32), (half + 1) * (D / 32), act(round), nullptr, PITCHX,
                        P + (half ? 2 * NMG * 128 : 0), lane);
       }
-      arm(round, (uint32_t)(K * D * 4));
+      ++round;
+      arm(round, (uint32_t)(K * D * 2));
       upd_sync();
       PP_T(4);
       // ============================================================ R3: all-gather h'
@@ -692,18 +719,18 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
           hp = (1.f - z) * nn + z * own[i];
           own[i] = hp;
         }
-        quad_push(round, hp, i, DS, D);
+        quad_push(round, hp, i, DS, act(round), PITCHX);
       }
       xwait(round);
-      ln_to_hilo(reinterpret_cast<const float*>(xb(round)), s_lnp + 2 * D, s_lnp + 3 * D, act_hi, act_lo, nullptr, nullptr);
-      ++round;
-      upd_sync();
+      // ---- MLP layer 1 on the raw h' (LayerNorm folded), statistics alongside
       for (int job = uwarp; job < NM1 * NKC; job += 8) {
         const int mt = job / NKC, kc = job % NKC;
-        mma_job<false>(s_w1, PITCH, HS, s_zrow, mt, kc * (D / 16) / NKC, (kc + 1) * (D / 16) / NKC, act_hi, act_lo, PITCHX,
-                P + kc * NM1 * 128, lane);
+        mma_job<false>(s_w1, PITCH, HS, s_zrow, mt, kc * (D / 16) / NKC, (kc + 1) * (D / 16) / NKC, act(round), nullptr, PITCHX,
+                       P + kc * NM1 * 128, lane);
       }
-      arm(round, (uint32_t)(K * H * 4));
+      row_stats(act(round), PITCHX);
+      ++round;
+      arm(round, (uint32_t)(K * H * 2));
       upd_sync();
       PP_T(5);
       // ============================================================ R4: all-gather the MLP hidden layer
@@ -712,27 +739,25 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
         float hid = 0.f;
         if (i < K * HS) {
           const int slot = i / HS, hl = i % HS;
-          float sum = s_b1[hl];
+          float acc = 0.f;
 #pragma unroll
-          for (int kc = 0; kc < NKC; ++kc) sum += P[(kc * NM1 * 16 + hl) * 8 + slot];
-          hid = fmaxf(sum, 0.f);
+          for (int kc = 0; kc < NKC; ++kc) acc += P[(kc * NM1 * 16 + hl) * 8 + slot];
+          hid = fmaxf(s_rstd[slot] * (acc - s_mean[slot] * s_c1[hl]) + s_b1f[hl], 0.f);
         }
-        quad_push(round, hid, i, HS, H);
+        quad_push(round, hid, i, HS, act(round), PITCHX);
       }
       xwait(round);
-      to_hilo(reinterpret_cast<const float*>(xb(round)), H, act_hi, act_lo, PITCHX);
-      ++round;
-      upd_sync();
       for (int job = uwarp; job < NM2 * NKC; job += 8) {
         const int mt = job / NKC, kc = job % NKC;
-        mma_job<false>(s_w2, PITCHH, DS, s_zrow, mt, kc * (H / 16) / NKC, (kc + 1) * (H / 16) / NKC, act_hi, act_lo, PITCHX,
-                P + kc * NM2 * 128, lane);
+        mma_job<false>(s_w2, PITCHH, DS, s_zrow, mt, kc * (H / 16) / NKC, (kc + 1) * (H / 16) / NKC, act(round), nullptr, PITCHX,
+                       P + kc * NM2 * 128, lane);
       }
-      if (!last) arm(round, (uint32_t)(K * D * 4));
+      ++round;
+      if (!last) arm(round, (uint32_t)(K * D * 2));
       upd_sync();
       PP_T(6);
       // ============================================================ R5: all-gather the new slots (or write them out)
-      const bool more = last && (m + 1 < nimg[l]);
+      const bool more = last && (m + 1 < nimg_of(l));
       for (int i0 = uwarp * 32; i0 < K * DS; i0 += 256) {
         const int i = i0 + lane;
         float sn = 0.f;
@@ -743,20 +768,18 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
           for (int kc = 0; kc < NKC; ++kc) sum += P[(kc * NM2 * 16 + dl) * 8 + slot];
           sn = own[i] + sum;
           own[i] = sn;
-          if (last) {
-            a.slots_out[((size_t)img * K + slot) * D + rank * DS + dl] = sn;
-            if (more) own[i] = a.slots0[((size_t)image_of(l, m + 1) * K + slot) * D + rank * DS + dl];
-          }
+          if (last) a.slots_out[((size_t)img * K + slot) * D + rank * DS + dl] = sn;
         }
-        if (!last) quad_push(round, sn, i, DS, D);
+        if (!last) quad_push(round, sn, i, DS, slh_hi(l), PITCH);
       }
       if (!last) {
         xwait(round);
-        const float* sfull = reinterpret_cast<const float*>(xb(round));
         ++round;
-        q_phase(l, sfull);  // R6: q of the lane's next iteration
+        q_phase(l);  // R6: q of the lane's next iteration
       } else if (more) {
-        q_phase(l, a.slots0 + (size_t)image_of(l, m + 1) * K * D);  // q of the lane's next image
+        upd_sync();  // every warp is done with `own` and P
+        load_slots0(l, image_of(l, m + 1));
+        q_phase(l);  // q of the lane's next image
       } else {
         upd_sync();  // P is rewritten by the next op
       }
@@ -767,10 +790,10 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
   cluster.sync();  // no CTA leaves while a peer may still address its shared memory
 }
 
-template <int D, int H, int CL, int S>
+template <int D, int H, int CL, int S, int NL>
 static int launch_pipe(const IterFwdArgs& a, cudaStream_t stream) {
-  using C = Cfg<D, H, CL, S>;
-  auto kern = sa_iter_fwd_pipe_kernel<D, H, CL, S>;
+  using C = Cfg<D, H, CL, S, NL>;
+  auto kern = sa_iter_fwd_pipe_kernel<D, H, CL, S, NL>;
   static_assert(C::SMEM_BYTES <= 227 * 1024, "shared memory budget");
   CUtensorMap tm_k, tm_v;
   if (!make_kv_map(&tm_k, a.k, (long long)a.B * a.N, D, C::TOK) || !make_kv_map(&tm_v, a.v, (long long)a.B * a.N, D, C::TOK)) {
@@ -802,11 +825,11 @@ static int launch_pipe(const IterFwdArgs& a, cudaStream_t stream) {
     }
     max_clusters = n;
     if (getenv("OCRL_SA_PC_VERBOSE"))
-      fprintf(stderr, "[ocrl] pipe kernel CL=%d S=%d smem=%d B: max active clusters %d\n", CL, S, C::SMEM_BYTES, n);
+      fprintf(stderr, "[ocrl] pipe kernel CL=%d S=%d NL=%d smem=%d B: max active clusters %d\n", CL, S, NL, C::SMEM_BYTES, n);
   }
   int ncl = max_clusters;
   if (const char* e = getenv("OCRL_SA_PC_CLUSTERS")) ncl = max(1, min(ncl, atoi(e)));
-  const int want = (a.B + 1) / 2;  // two lanes per cluster
+  const int want = (a.B + NL - 1) / NL;  // NL lanes per cluster
   if (ncl > want) ncl = want;
   {  // fewest clusters that keep the same number of image rounds (frees SMs for concurrent work)
     const int per = (a.B + ncl - 1) / ncl;
@@ -829,10 +852,11 @@ int sa_iter_fwd_pipe_dispatch(const IterFwdArgs& a, cudaStream_t s) {
   if (const char* e = getenv("OCRL_SA_PIPE")) variant = atoi(e);
   if (a.D == 192 && a.H == 192) {
     switch (variant) {
-      case 1: return pipe::launch_pipe<192, 192, 8, 4>(a, s);
-      case 2: return pipe::launch_pipe<192, 192, 16, 8>(a, s);
-      case 3: return pipe::launch_pipe<192, 192, 8, 6>(a, s);
-      default: return pipe::launch_pipe<192, 192, 8, 7>(a, s);
+      case 1: return pipe::launch_pipe<192, 192, 8, 4, 2>(a, s);
+      case 2: return pipe::launch_pipe<192, 192, 16, 8, 2>(a, s);
+      case 3: return pipe::launch_pipe<192, 192, 8, 7, 2>(a, s);
+      case 4: return pipe::launch_pipe<192, 192, 8, 6, 3>(a, s);
+      default: return pipe::launch_pipe<192, 192, 8, 7, 3>(a, s);
     }
   }
   set_error("sa_iter_fwd(pipeline): D=%d H=%d not instantiated", a.D, a.H);
