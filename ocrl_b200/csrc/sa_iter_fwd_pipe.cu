@@ -23,9 +23,10 @@ using namespace pc;
 #define TRACE_OP 2
 #endif
 
-template <int D_, int H_, int CL_, int S_, int NL_>
+template <int D_, int H_, int CL_, int S_, int NL_, int KB_>
 struct Cfg {
-  static constexpr int D = D_, H = H_, CL = CL_, S = S_, NL = NL_;  // NL image lanes per cluster
+  // NL image lanes per cluster; KB rows in the slot-indexed buffers (6 when K <= 6: room for one more ring stage)
+  static constexpr int D = D_, H = H_, CL = CL_, S = S_, NL = NL_, KB = KB_;
   static constexpr int KP = 8, NT = 512, TOK = 16;
   static constexpr int PITCH = D * 2 + 16, PITCHH = H * 2 + 16;
   static constexpr int LX = D > H ? D : H;
@@ -48,33 +49,34 @@ struct Cfg {
   static constexpr int OFF_BIAS = (OFF_ZROW + PITCHX + 15) & ~15;  // (the LayerNorm affine parameters are folded into W1', Wq')
   // fp32 constants: b_ih[3DS] b_hh[3DS] b1'[HS] b2[DS] c1[HS] cq[DS] bq'[DS] + LayerNorm stats mean[8] rstd[8]
   static constexpr int NCONST = 9 * DS + 2 * HS + 16;
-  static constexpr int XBUF_BYTES = KP * D * 4 + 32 * CL;          // R1 receive buffer (fp32 partial sums), single
+  static constexpr int XBUF_BYTES = KB * D * 4 + 32 * CL;          // R1 receive buffer (fp32 partial sums), single
   static constexpr int OFF_XBUF = (OFF_BIAS + NCONST * 4 + 15) & ~15;
   static constexpr int OFF_ACT = OFF_XBUF + XBUF_BYTES;            // bf16 all-gather targets, by round parity
   static constexpr int P_ROWS = (3 * NMG > NKC * (NM1 > NM2 ? NM1 : NM2)) ? 3 * NMG * 16 : NKC * (NM1 > NM2 ? NM1 : NM2) * 16;
-  static constexpr int OFF_P = OFF_ACT + 2 * KP * PITCHX;          // MMA partial outputs
-  static constexpr int OFF_UST = OFF_P + P_ROWS * 32;              // U staging a, b (pass -> update hand-off)
-  static constexpr int OFF_SRED = OFF_UST + 2 * KP * UP * 4;       // [4][8] token sums of the logit warps
-  static constexpr int OFF_LANE = OFF_SRED + 128;                  // per lane: slots hi/lo, q (bf16), own slice (fp32)
-  static constexpr int LANE_BYTES = KP * PITCH + KP * PITCH + KP * DS * 4;
-  static constexpr int OFF_BAR = (OFF_LANE + NL * LANE_BYTES + 15) & ~15;  // full[S] w_ready[S] xbar[2] u_ready u_free q_ready[NL]
+  static constexpr int OFF_UST = OFF_ACT + 2 * KB * PITCHX;        // U staging a, b (pass -> update hand-off)
+  static constexpr int OFF_LANE = OFF_UST + 2 * KB * UP * 4;       // per lane: slots (bf16), q (bf16), own slice (fp32)
+  static constexpr int LANE_BYTES = KB * PITCH + KB * PITCH + KB * DS * 4;
+  // rows KB..7 of the slot-indexed buffers are read as (ignored) padding columns of the MMAs, so plain data follows
+  // them: the MMA partial outputs and the token sums close the list
+  static constexpr int OFF_P = (OFF_LANE + NL * LANE_BYTES + 15) & ~15;
+  static constexpr int OFF_SRED = OFF_P + P_ROWS * 32;             // [4][8] token sums of the logit warps
+  static constexpr int OFF_BAR = OFF_SRED + 128;  // full[S] w_ready[S] xbar[2] u_ready u_free q_ready[NL]
   static constexpr int OFF_ISSUED = OFF_BAR + (2 * S + 4 + NL) * 8;
-  static constexpr int SMEM_BYTES = OFF_ISSUED + S * 4 + 1024;     // + slack for the manual 1024-byte alignment
+  static constexpr int SMEM_BYTES = OFF_ISSUED + S * 4;
 };
 
 __device__ __forceinline__ void upd_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-template <int D, int H, int CL, int S, int NL>
+template <int D, int H, int CL, int S, int NL, int KB>
 __global__ void __launch_bounds__(512, 1)
 sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v) {
-  using C = Cfg<D, H, CL, S, NL>;
-  constexpr int KP = C::KP, PITCH = C::PITCH, PITCHH = C::PITCHH, PITCHX = C::PITCHX, DS = C::DS, HS = C::HS;
+  using C = Cfg<D, H, CL, S, NL, KB>;
+  constexpr int PITCH = C::PITCH, PITCHH = C::PITCHH, PITCHX = C::PITCHX, DS = C::DS, HS = C::HS;
   constexpr int NMU = C::NMU, NMG = C::NMG, NM1 = C::NM1, NM2 = C::NM2, NKC = C::NKC, UP = C::UP, TOK = C::TOK;
   constexpr float LOG2E = 1.4426950408889634f;
 
-  extern __shared__ unsigned char smem_raw[];
-  // align by pointer arithmetic on the __shared__ pointer (an integer round trip would turn every access generic)
-  unsigned char* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  extern __shared__ __align__(1024) unsigned char sm[];  // swizzled TMA tiles need 1024-byte alignment
+  if ((smem_u32(sm) & 1023u) != 0) __trap();
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int cid = blockIdx.x / CL, ncl = gridDim.x / CL;
@@ -103,14 +105,14 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
   float* s_mean = s_bias + 9 * DS + 2 * HS;  // LayerNorm statistics of the round in flight
   float* s_rstd = s_mean + 8;
   unsigned char* xbuf = sm + C::OFF_XBUF;
-  auto act = [&](uint32_t r) { return sm + C::OFF_ACT + (r & 1) * (KP * PITCHX); };  // bf16 [8][PITCHX]
+  auto act = [&](uint32_t r) { return sm + C::OFF_ACT + (r & 1) * (KB * PITCHX); };  // bf16 [KB][PITCHX]
   float* P = reinterpret_cast<float*>(sm + C::OFF_P);
   float* ustage_a = reinterpret_cast<float*>(sm + C::OFF_UST);
-  float* ustage_b = ustage_a + KP * UP;
+  float* ustage_b = ustage_a + KB * UP;
   float* sred = reinterpret_cast<float*>(sm + C::OFF_SRED);
   auto slh_hi = [&](int l) { return sm + C::OFF_LANE + l * C::LANE_BYTES; };
-  auto qbuf = [&](int l) { return sm + C::OFF_LANE + l * C::LANE_BYTES + KP * PITCH; };
-  auto own_of = [&](int l) { return reinterpret_cast<float*>(sm + C::OFF_LANE + l * C::LANE_BYTES + 2 * KP * PITCH); };
+  auto qbuf = [&](int l) { return sm + C::OFF_LANE + l * C::LANE_BYTES + KB * PITCH; };
+  auto own_of = [&](int l) { return reinterpret_cast<float*>(sm + C::OFF_LANE + l * C::LANE_BYTES + 2 * KB * PITCH); };
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
   uint64_t* full = bars;
   uint64_t* w_ready = bars + S;
@@ -337,7 +339,7 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
     }
     for (int i = tid; i < DS; i += C::NT) s_bias[6 * DS + HS + i] = a.w.b2[rank * DS + i];
     // staging rows of the padded slots are never written by the conversions; keep them finite
-    for (int i = tid; i < (2 * KP * PITCHX) / 4; i += C::NT) reinterpret_cast<uint32_t*>(sm + C::OFF_ACT)[i] = 0u;
+    for (int i = tid; i < (2 * KB * PITCHX) / 4; i += C::NT) reinterpret_cast<uint32_t*>(sm + C::OFF_ACT)[i] = 0u;
     for (int i = tid; i < (NL * C::LANE_BYTES) / 4; i += C::NT) reinterpret_cast<uint32_t*>(sm + C::OFF_LANE)[i] = 0u;
   }
   __syncthreads();
@@ -518,10 +520,12 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
           const int d0 = 16 * i + g8;
           float* u0 = ust + (2 * t4) * UP + d0;
           float* u1 = ust + (2 * t4 + 1) * UP + d0;
-          if (uw >= 2) {
-            u0[0] += acc[i][0]; u1[0] += acc[i][1]; u0[8] += acc[i][2]; u1[8] += acc[i][3];
-          } else {
-            u0[0] = acc[i][0]; u1[0] = acc[i][1]; u0[8] = acc[i][2]; u1[8] = acc[i][3];
+          if (2 * t4 < KB) {  // rows KB..7 are padding slots
+            if (uw >= 2) {
+              u0[0] += acc[i][0]; u1[0] += acc[i][1]; u0[8] += acc[i][2]; u1[8] += acc[i][3];
+            } else {
+              u0[0] = acc[i][0]; u1[0] = acc[i][1]; u0[8] = acc[i][2]; u1[8] = acc[i][3];
+            }
           }
         }
         if (uw < 2) asm volatile("bar.sync 2, 128;" ::: "memory");
@@ -650,13 +654,13 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
           const float4 xa = *reinterpret_cast<const float4*>(ustage_a + slot * UP + d);
           const float4 xb4 = *reinterpret_cast<const float4*>(ustage_b + slot * UP + d);
           const float4 val = make_float4(xa.x + xb4.x, xa.y + xb4.y, xa.z + xb4.z, xa.w + xb4.w);
-          const uint32_t off = (uint32_t)(((rank * KP + slot) * DS + dl) * 4);
+          const uint32_t off = (uint32_t)(((rank * KB + slot) * DS + dl) * 4);
           st_async_v4(mapa_u32(lbuf + off, dest), val, mapa_u32(lbar, dest));
         }
         if (utid < 8 * CL) {
           const int slot = utid & 7, dest = utid >> 3;
           const float s = sred[slot] + sred[8 + slot] + sred[16 + slot] + sred[24 + slot];
-          const uint32_t off = (uint32_t)(KP * D * 4 + (rank * 8 + slot) * 4);
+          const uint32_t off = (uint32_t)(KB * D * 4 + (rank * 8 + slot) * 4);
           st_async_b32(mapa_u32(lbuf + off, dest), __float_as_uint(s), mapa_u32(lbar, dest));
         }
       }
@@ -672,7 +676,7 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
       arm(round, (uint32_t)(K * D * 2));
       {
         const float* rs = reinterpret_cast<const float*>(xb);
-        const float* ss = rs + KP * D;
+        const float* ss = rs + KB * D;
         for (int i0 = uwarp * 32; i0 < K * DS; i0 += 256) {
           const int i = i0 + lane;
           float val = 0.f;
@@ -681,7 +685,7 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
             float u = 0.f, sw = 0.f;
 #pragma unroll
             for (int src = 0; src < CL; ++src) {
-              u += rs[(src * KP + slot) * DS + dl];
+              u += rs[(src * KB + slot) * DS + dl];
               sw += ss[src * 8 + slot];
             }
             val = u / sw;
@@ -790,10 +794,10 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
   cluster.sync();  // no CTA leaves while a peer may still address its shared memory
 }
 
-template <int D, int H, int CL, int S, int NL>
+template <int D, int H, int CL, int S, int NL, int KB>
 static int launch_pipe(const IterFwdArgs& a, cudaStream_t stream) {
-  using C = Cfg<D, H, CL, S, NL>;
-  auto kern = sa_iter_fwd_pipe_kernel<D, H, CL, S, NL>;
+  using C = Cfg<D, H, CL, S, NL, KB>;
+  auto kern = sa_iter_fwd_pipe_kernel<D, H, CL, S, NL, KB>;
   static_assert(C::SMEM_BYTES <= 227 * 1024, "shared memory budget");
   CUtensorMap tm_k, tm_v;
   if (!make_kv_map(&tm_k, a.k, (long long)a.B * a.N, D, C::TOK) || !make_kv_map(&tm_v, a.v, (long long)a.B * a.N, D, C::TOK)) {
@@ -825,7 +829,7 @@ static int launch_pipe(const IterFwdArgs& a, cudaStream_t stream) {
     }
     max_clusters = n;
     if (getenv("OCRL_SA_PC_VERBOSE"))
-      fprintf(stderr, "[ocrl] pipe kernel CL=%d S=%d NL=%d smem=%d B: max active clusters %d\n", CL, S, NL, C::SMEM_BYTES, n);
+      fprintf(stderr, "[ocrl] pipe kernel CL=%d S=%d NL=%d KB=%d smem=%d B: max active clusters %d\n", CL, S, NL, KB, C::SMEM_BYTES, n);
   }
   int ncl = max_clusters;
   if (const char* e = getenv("OCRL_SA_PC_CLUSTERS")) ncl = max(1, min(ncl, atoi(e)));
@@ -851,13 +855,15 @@ int sa_iter_fwd_pipe_dispatch(const IterFwdArgs& a, cudaStream_t s) {
   int variant = 0;
   if (const char* e = getenv("OCRL_SA_PIPE")) variant = atoi(e);
   if (a.D == 192 && a.H == 192) {
-    switch (variant) {
-      case 1: return pipe::launch_pipe<192, 192, 8, 4, 2>(a, s);
-      case 2: return pipe::launch_pipe<192, 192, 16, 8, 2>(a, s);
-      case 3: return pipe::launch_pipe<192, 192, 8, 7, 2>(a, s);
-      case 4: return pipe::launch_pipe<192, 192, 8, 6, 3>(a, s);
-      default: return pipe::launch_pipe<192, 192, 8, 7, 3>(a, s);
+    if (a.K <= 6) {  // six slot rows in the exchange / staging buffers leave room for an eighth ring stage
+      switch (variant) {
+        case 1: return pipe::launch_pipe<192, 192, 8, 4, 2, 6>(a, s);
+        case 2: return pipe::launch_pipe<192, 192, 8, 8, 2, 6>(a, s);
+        case 3: return pipe::launch_pipe<192, 192, 8, 7, 3, 6>(a, s);
+        default: return pipe::launch_pipe<192, 192, 8, 8, 3, 6>(a, s);
+      }
     }
+    return pipe::launch_pipe<192, 192, 8, 7, 3, 8>(a, s);
   }
   set_error("sa_iter_fwd(pipeline): D=%d H=%d not instantiated", a.D, a.H);
   return OCRL_E_SHAPE;

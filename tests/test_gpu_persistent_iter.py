@@ -15,7 +15,7 @@ from tests.golden_io import load_case, rel_err
 
 pytestmark = pytest.mark.gpu
 BF16_TOL = 2e-2
-VARIANTS = {"pipe": {"OCRL_SA_PIPE": "0"}, "pipe_s4": {"OCRL_SA_PIPE": "1"},
+VARIANTS = {"pipe": {"OCRL_SA_PIPE": "0"}, "pipe_2lanes_s4": {"OCRL_SA_PIPE": "1"},
             "single_engine": {"OCRL_SA_PIPE": "-1", "OCRL_SA_PC": "0"},
             "single_engine_cl16": {"OCRL_SA_PIPE": "-1", "OCRL_SA_PC": "1"}}
 
