@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define OCRL_ABI_VERSION 2
+#define OCRL_ABI_VERSION 3
 
 enum {
   OCRL_OK = 0,
@@ -147,6 +147,14 @@ int ocrl_sa_iter_bwd(const ocrl_sa_dims* dims, const void* k, const void* v, con
                      const ocrl_sa_weights* w, const float* d_slots, const float* d_attn_vis,
                      float* dk, float* dv, float* d_slots0, const ocrl_sa_weight_grads* dw,
                      void* workspace, void* stream);
+
+/* Element-wise pieces of the feature stage between the (library) convolutions, bf16 inference path.
+ *   ocrl_conv_bias_relu_bf16: y = relu(y + bias[c]) in place on a channels-last bf16 tensor [npixels, channels]
+ *     -- the bias + ReLU of Conv2dBlock (ocrs/common/networks.py:38-53); bias fp32 [channels].
+ *   ocrl_frames_to_nhwc_bf16: obs [B,C,H,W] fp32 in [0,1] (utils/datasets.py:17) -> out [B,H,W,CP] bf16 with the
+ *     channels zero-padded to CP = 8 (input of the first convolution, ocrs/common/models.py:99). */
+int ocrl_conv_bias_relu_bf16(void* y, const float* bias, long long npixels, int channels, void* stream);
+int ocrl_frames_to_nhwc_bf16(const float* obs, void* out, int B, int C, int H, int W, int CP, void* stream);
 
 #ifdef __cplusplus
 }

@@ -102,7 +102,7 @@ def test_bf16_mode_through_the_module(monkeypatch):
     assert rel_err(masks.cpu(), g["out"]["masks"]) < 2e-2
 
 
-@pytest.mark.parametrize("conv", ["tf32", "bf16", "bf16-unfused"])
+@pytest.mark.parametrize("conv", ["tf32", "bf16", "bf16-unfused", "bf16-ocrlepilogue"])
 def test_bf16_mode_with_tensor_core_convs(monkeypatch, conv):
     """bf16 mode end to end: channels-last cuDNN convs (TF32, bf16 with fused bias+ReLU and the last bias folded
     into the position table, or plain bf16 autocast) feeding the tcgen05 token stage (bf16 tokens when the convs
@@ -110,6 +110,7 @@ def test_bf16_mode_with_tensor_core_convs(monkeypatch, conv):
     meta, g = load_case("slate_encode_64")
     monkeypatch.setenv("OCRL_KV_DTYPE", "bf16")
     monkeypatch.setenv("OCRL_CONV_FUSED", "0" if conv.endswith("unfused") else "1")
+    monkeypatch.setenv("OCRL_CONV_EPILOGUE", "ocrl" if conv.endswith("ocrlepilogue") else "cudnn")
     conv = conv.split("-")[0]
     monkeypatch.setenv("OCRL_CONV_DTYPE", conv)
     model = ocrl_b200.SLATE(*slate_config())
