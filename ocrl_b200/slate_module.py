@@ -138,6 +138,18 @@ class SLATE_Module(nn.Module):
         finally:
             torch.backends.cudnn.allow_tf32 = prev
 
+    def _pos_table_with_bias(self, fast):
+        """Position table [C, S*S] plus the last convolution's bias, cached until one of their parameters changes
+        (the table is input-independent; the reference recomputes it per batch element, utils.py:28-33)."""
+        cm = self._enc_pos.channels_map
+        last = self._enc._encoder[3]
+        key = tuple((p.data_ptr(), p._version) for p in (cm.weight, cm.bias, last.bias))
+        cached = self.__dict__.get("_pos_table_cache")
+        if cached is None or cached[0] != key:
+            cached = (key, (self._enc_pos.table() + fast.last_bias.unsqueeze(1)).contiguous())
+            self.__dict__["_pos_table_cache"] = cached
+        return cached[1]
+
     def _slot_attention(self, obs):
         if not self._hot_needs_grad(obs):
             # inference: position add + (transpose) + token MLP + projections fused into one kernel
@@ -147,8 +159,7 @@ class SLATE_Module(nn.Module):
                     fast = self.__dict__.get("_fast_enc")
                     if fast is None:
                         fast = self.__dict__["_fast_enc"] = FusedBf16Encoder(self._enc)
-                    table = self._enc_pos.table() + fast.last_bias.unsqueeze(1)
-                    return self._slotattn(fast(obs), _pos_table=table)
+                    return self._slotattn(fast(obs), _pos_table=self._pos_table_with_bias(fast))
                 return self._slotattn(self._encode_features(obs), _pos_table=self._enc_pos.table())
         fmap = self._enc(obs)
         emb = self._enc_pos(fmap).permute(0, 2, 3, 1).flatten(start_dim=1, end_dim=2)
