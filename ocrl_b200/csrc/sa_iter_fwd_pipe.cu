@@ -540,6 +540,10 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
     // qbuf[lane]); the LayerNorms are folded into the products that follow them (statistics from the received rows).
     const int utid = tid - 256, uwarp = warp - 8;
     uint32_t round = 0;
+    // training: per-(image, iteration) state for the fused backward (SavedLayout, slot_math.cuh); every CTA writes
+    // its own feature slice
+    const SavedLayout SL(K, D, H);
+    auto saved_at = [&](int img, int t) { return a.saved + ((size_t)img * T + t) * SL.stride(); };
     unsigned char* xb = xbuf;
     auto arm = [&](uint32_t r, uint32_t bytes) {
       if (utid == 0) mbar_expect_tx(&xbar[r & 1], bytes);
@@ -600,7 +604,7 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
       upd_sync();
     };
     // q = W_q LN(slots) of lane l for the CTA's slice (slots = slh[l], bf16), all-gathered (times log2 e) into qbuf[l]
-    auto q_phase = [&](int l) {
+    auto q_phase = [&](int l, int q_img, int q_t) {
       for (int job = uwarp; job < NM2 * NKC; job += 8) {
         const int mt = job / NKC, kc = job % NKC;
         mma_job<false>(s_wq, PITCH, DS, s_zrow, mt, kc * (D / 16) / NKC, (kc + 1) * (D / 16) / NKC, slh_hi(l), nullptr, PITCH,
@@ -617,7 +621,9 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
           float acc = 0.f;
 #pragma unroll
           for (int kc = 0; kc < NKC; ++kc) acc += P[(kc * NM2 * 16 + dl) * 8 + slot];
-          val = (s_rstd[slot] * (acc - s_mean[slot] * s_cq[dl]) + s_bqf[dl]) * LOG2E;
+          const float qv = s_rstd[slot] * (acc - s_mean[slot] * s_cq[dl]) + s_bqf[dl];
+          if (a.saved != nullptr) saved_at(q_img, q_t)[SL.off_q() + slot * D + rank * DS + dl] = qv;
+          val = qv * LOG2E;
         }
         quad_push(round, val, i, DS, qbuf(l), PITCH);
       }
@@ -630,7 +636,7 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
     for (int l = 0; l < NL; ++l)
       if (nops[l] > 0) {
         load_slots0(l, image_of(l, 0));
-        q_phase(l);
+        q_phase(l, image_of(l, 0), 0);
       }
 
     for (int n = 0; n < total_ops; ++n) {
@@ -689,6 +695,12 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
               sw += ss[src * 8 + slot];
             }
             val = u / sw;
+            if (a.saved != nullptr) {
+              float* sv = saved_at(img, t);
+              sv[SL.off_h() + slot * D + rank * DS + dl] = own[i];  // slots entering the iteration
+              sv[SL.off_u() + slot * D + rank * DS + dl] = val;
+              if (rank == 0 && dl == 0) sv[SL.off_s() + slot] = sw;
+            }
           }
           quad_push(round, val, i, DS, act(round), PITCHX);
         }
@@ -722,6 +734,15 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
           const float nn = tanhf(gin + r * ghn);
           hp = (1.f - z) * nn + z * own[i];
           own[i] = hp;
+          if (a.saved != nullptr) {
+            float* sv = saved_at(img, t);
+            const int f = slot * D + rank * DS + dl;
+            sv[SL.off_r() + f] = r;
+            sv[SL.off_z() + f] = z;
+            sv[SL.off_n() + f] = nn;
+            sv[SL.off_ghn() + f] = ghn;
+            sv[SL.off_hp() + f] = hp;
+          }
         }
         quad_push(round, hp, i, DS, act(round), PITCHX);
       }
@@ -746,7 +767,9 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
           float acc = 0.f;
 #pragma unroll
           for (int kc = 0; kc < NKC; ++kc) acc += P[(kc * NM1 * 16 + hl) * 8 + slot];
-          hid = fmaxf(s_rstd[slot] * (acc - s_mean[slot] * s_c1[hl]) + s_b1f[hl], 0.f);
+          const float pre = s_rstd[slot] * (acc - s_mean[slot] * s_c1[hl]) + s_b1f[hl];
+          if (a.saved != nullptr) saved_at(img, t)[SL.off_pre() + slot * H + rank * HS + hl] = pre;
+          hid = fmaxf(pre, 0.f);
         }
         quad_push(round, hid, i, HS, act(round), PITCHX);
       }
@@ -779,11 +802,11 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
       if (!last) {
         xwait(round);
         ++round;
-        q_phase(l);  // R6: q of the lane's next iteration
+        q_phase(l, img, t + 1);  // R6: q of the lane's next iteration
       } else if (more) {
         upd_sync();  // every warp is done with `own` and P
         load_slots0(l, image_of(l, m + 1));
-        q_phase(l);  // q of the lane's next image
+        q_phase(l, image_of(l, m + 1), 0);  // q of the lane's next image
       } else {
         upd_sync();  // P is rewritten by the next op
       }
@@ -848,8 +871,8 @@ static int launch_pipe(const IterFwdArgs& a, cudaStream_t stream) {
 
 // Returns OCRL_E_SHAPE (without launching) for shapes this kernel does not cover; the caller falls back.
 int sa_iter_fwd_pipe_dispatch(const IterFwdArgs& a, cudaStream_t s) {
-  if (a.K > 8 || a.saved != nullptr) {
-    set_error("sa_iter_fwd(pipeline): K <= 8, inference only");
+  if (a.K > 8) {
+    set_error("sa_iter_fwd(pipeline): K <= 8");
     return OCRL_E_SHAPE;
   }
   int variant = 0;

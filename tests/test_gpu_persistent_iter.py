@@ -102,3 +102,23 @@ def test_argmax_masks_against_oracle_report_flip_rate():
     flips = (a.argmax(-1) != a_ref.argmax(-1))
     print(f"argmax flips {int(flips.sum())} / {flips.numel()}; with margin > 2e-2: {int((flips & clear).sum())}")
     assert not (flips & clear).any()
+
+
+def test_saved_state_matches_the_per_image_kernel(monkeypatch):
+    """Training: the per-(image, iteration) state the pipeline kernel keeps for the fused backward agrees with the
+    per-image cluster kernel's (same layout, SavedLayout in slot_math.cuh), and the gradients computed from it agree."""
+    from ocrl_b200 import functional as F
+
+    meta, g = load_case("sa_slate_grad")
+    p = _cuda(g["p"])
+    k_ref, v_ref = so.kv_project(g["in"]["inputs"], g["p"])
+    kb, vb, s0 = k_ref.bfloat16().cuda(), v_ref.bfloat16().cuda(), g["in"]["slots0"].cuda()
+    monkeypatch.setenv("OCRL_SA_PIPE", "0")
+    s_new, a_new, saved_new = F.iterate(kb, vb, s0, p, meta["T"], epsilon=meta["eps"], save=True)
+    monkeypatch.setenv("OCRL_SA_PIPE", "-1")
+    monkeypatch.setenv("OCRL_SA_PC", "-1")
+    s_old, a_old, saved_old = F.iterate(kb, vb, s0, p, meta["T"], epsilon=meta["eps"], save=True)
+    torch.cuda.synchronize()
+    assert rel_err(s_new.cpu(), s_old.cpu()) < BF16_TOL
+    assert saved_new.shape == saved_old.shape
+    assert rel_err(saved_new.cpu(), saved_old.cpu()) < BF16_TOL, rel_err(saved_new.cpu(), saved_old.cpu())
