@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--no-other-mode", action="store_true", help="skip the short run of the other precision mode")
     ap.add_argument("--impl", default="ocrl_b200", choices=["ocrl_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the short SLATE training-step measurement")
     ap.add_argument("--pool", type=int, default=512, help="distinct frames in the synthetic pool")
     return ap.parse_args()
 
@@ -253,6 +254,51 @@ def measure(a, mode, steps, warmup, dev, dist, rank, world, pool_host, pool_dev,
     return res
 
 
+def measure_train(a, dev, pool_dev, steps=8, warmup=3):
+    """SLATE OCR training step (BASELINE.json config 3: num_slots 6, num_iterations 3, bf16 k/v) on one GPU:
+    ``SLATE.update`` = get_loss + backward + inf-norm clip + Adam.  The slot-attention loop and the k/v projection
+    run the hand-written forward and backward kernels; the dVAE, the transformer decoder, the CNN encoder's
+    backward and the optimizer are torch / cuDNN (library code), so this is a context number, not a roofline."""
+    import ocrl_b200
+    from ocrl_b200 import functional as F
+    from ocrl_b200.config import slate_config
+
+    os.environ["OCRL_KV_DTYPE"] = "bf16"
+    torch.backends.cudnn.allow_tf32 = True   # torch's GPU defaults, i.e. what the reference's training runs with
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    model = ocrl_b200.SLATE(*slate_config(num_slots=a.slots, num_iterations=a.iters, slot_size=a.slot_size,
+                                          mlp_hidden_size=a.slot_size, obs_size=a.size))
+    model.to(dev)
+    model.train()
+    nb = a.pool // a.batch
+
+    def step(i):
+        return model.update(pool_dev[(i % nb) * a.batch:(i % nb + 1) * a.batch], None, 1000 + i)
+
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize()
+    F.KERNEL_EVENTS = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        m = step(warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    ev, F.KERNEL_EVENTS = F.KERNEL_EVENTS, None
+    ms = e0.elapsed_time(e1) / steps
+    per = {}
+    for name, s0, s1 in ev:
+        per.setdefault(name, []).append(s0.elapsed_time(s1))
+    return {"value": a.batch / ms * 1e3, "unit": "images/s", "ms_per_step": ms, "steps": steps,
+            "loss": float(m["loss"].detach()), "kernels_ms": {k: sum(v) / len(v) for k, v in per.items()},
+            "config": "SLATE.update (get_loss + backward + clip + Adam), bf16 k/v, batch %d, eager launches; "
+                      "slot-attention fwd/bwd + k/v projection hand-written, dVAE / decoder / CNN backward library code "
+                      "(torch defaults: cuDNN TF32 on, fp32 matmul)"
+                      % a.batch}
+
+
 def roofline_of(a, mode, events):
     it_ms = [s.elapsed_time(e) for name, s, e in events if name == "sa_iter_fwd"]
     tk_ms = [s.elapsed_time(e) for name, s, e in events if name == "kv_proj_fwd"]
@@ -364,6 +410,11 @@ def main():
             line["other_mode"] = {"mode": om, "value": r["value"], "e2e": r["e2e_value"], "unit": UNIT,
                                   "ms_per_step": r["ms_per_step"], "roofline_frac": rf["frac"],
                                   "iter_kernel_ms": rf["avg_launch_ms"], "token_stage_ms": rf["token_stage"]["avg_launch_ms"]}
+        if world == 1 and not a.no_train:
+            try:
+                line["train_step"] = measure_train(a, dev, pool_dev)
+            except Exception as exc:  # the encode metric stands on its own
+                line["train_step"] = {"error": repr(exc)[:300]}
         if world == 1 and not a.no_cpu_baseline:
             csteps = 6
             ips, cms, cores = time_cpu(a, pool_u8, csteps, 1)

@@ -211,16 +211,20 @@ class SlotAttentionFunction(torch.autograd.Function):
         d_slots = _f32c(d_slots)
         d_attn_c = _f32c(d_attn) if d_attn is not None else None
         L = abi.lib()
-        abi.check(L.ocrl_sa_iter_bwd(ctypes.byref(dims), abi.ptr(k), abi.ptr(v), abi.ptr(saved), ctypes.byref(w),
-                                     abi.ptr(d_slots), abi.ptr(d_attn_c), abi.ptr(dk), abi.ptr(dv), abi.ptr(d_slots0),
-                                     ctypes.byref(dw), abi.ptr(ws), abi.stream_ptr()), "ocrl_sa_iter_bwd")
+        with _timed("sa_iter_bwd"):
+            abi.check(L.ocrl_sa_iter_bwd(ctypes.byref(dims), abi.ptr(k), abi.ptr(v), abi.ptr(saved), ctypes.byref(w),
+                                         abi.ptr(d_slots), abi.ptr(d_attn_c), abi.ptr(dk), abi.ptr(dv),
+                                         abi.ptr(d_slots0), ctypes.byref(dw), abi.ptr(ws), abi.stream_ptr()),
+                      "ocrl_sa_iter_bwd")
         # norm_inputs + project_k / project_v
         ws2 = torch.empty(max(L.ocrl_kv_proj_bwd_workspace(ctypes.byref(dims)), 16), device=dev, dtype=torch.uint8)
         dx = torch.empty_like(inputs)
         tw = abi.token_weights(in_ln_w=p["norm_inputs.weight"], in_ln_b=p["norm_inputs.bias"],
                                wk=p["project_k.weight"], wv=p["project_v.weight"])
-        abi.check(L.ocrl_kv_proj_bwd(ctypes.byref(dims), abi.ptr(inputs), ctypes.byref(tw), abi.ptr(dk), abi.ptr(dv),
-                                     abi.ptr(dx), abi.ptr(g["norm_inputs.weight"]), abi.ptr(g["norm_inputs.bias"]),
-                                     abi.ptr(g["project_k.weight"]), abi.ptr(g["project_v.weight"]), abi.ptr(ws2),
-                                     abi.stream_ptr()), "ocrl_kv_proj_bwd")
+        with _timed("kv_proj_bwd"):
+            abi.check(L.ocrl_kv_proj_bwd(ctypes.byref(dims), abi.ptr(inputs), ctypes.byref(tw), abi.ptr(dk),
+                                         abi.ptr(dv), abi.ptr(dx), abi.ptr(g["norm_inputs.weight"]),
+                                         abi.ptr(g["norm_inputs.bias"]), abi.ptr(g["project_k.weight"]),
+                                         abi.ptr(g["project_v.weight"]), abi.ptr(ws2), abi.stream_ptr()),
+                      "ocrl_kv_proj_bwd")
         return (dx, d_slots0, None, None, None, *[g[n] for n in SA_PARAM_ORDER])
