@@ -888,6 +888,10 @@ int sa_iter_fwd_pipe_dispatch(const IterFwdArgs& a, cudaStream_t s) {
     }
     return pipe::launch_pipe<192, 192, 8, 7, 3, 8>(a, s);
   }
+  if (a.D == 64 && a.H == 128) {  // the "Slot-Attention (small)" configuration: D = 64, H_mlp = 128
+    if (a.K <= 6) return pipe::launch_pipe<64, 128, 8, 16, 3, 6>(a, s);
+    return pipe::launch_pipe<64, 128, 8, 16, 3, 8>(a, s);
+  }
   set_error("sa_iter_fwd(pipeline): D=%d H=%d not instantiated", a.D, a.H);
   return OCRL_E_SHAPE;
 }

@@ -122,3 +122,29 @@ def test_saved_state_matches_the_per_image_kernel(monkeypatch):
     assert rel_err(s_new.cpu(), s_old.cpu()) < BF16_TOL
     assert saved_new.shape == saved_old.shape
     assert rel_err(saved_new.cpu(), saved_old.cpu()) < BF16_TOL, rel_err(saved_new.cpu(), saved_old.cpu())
+
+
+@pytest.mark.parametrize("B,N,K,T", [(2, 256, 6, 3), (5, 1000, 7, 7), (64, 4096, 6, 7)])
+def test_small_slot_attention_configuration(B, N, K, T):
+    """D = 64, H_mlp = 128, T = 7: the "Slot-Attention (small)" rows of the paper on the pipeline kernel."""
+    p = so.random_sa_params(K, 64, 64, 128, seed=5)
+    gen = torch.Generator().manual_seed(B + N)
+    x = torch.randn(B, N, 64, generator=gen)
+    s0 = torch.randn(B, K, 64, generator=gen)
+    k_ref, v_ref = so.kv_project(x, p)
+    kb, vb = k_ref.bfloat16(), v_ref.bfloat16()
+    sel = [0, B // 2, B - 1] if B > 3 else list(range(B))
+    s_ref, a_ref = so.iterate(kb[sel].float(), vb[sel].float(), s0[sel], p, T, 1e-8)
+    s, a = _run(kb, vb, s0, p, T)
+    assert rel_err(s[sel], s_ref) < BF16_TOL, rel_err(s[sel], s_ref)
+    assert rel_err(a[sel], a_ref) < BF16_TOL, rel_err(a[sel], a_ref)
+    assert torch.allclose(a.sum(-1), torch.ones(B, N), atol=1e-4)
+
+
+def test_small_configuration_golden_case():
+    meta, g = load_case("sa_small_grad")
+    k_ref, v_ref = so.kv_project(g["in"]["inputs"], g["p"])
+    kb, vb = k_ref.bfloat16(), v_ref.bfloat16()
+    s_ref, a_ref = so.iterate(kb.float(), vb.float(), g["in"]["slots0"], g["p"], meta["T"], meta["eps"])
+    s, a = _run(kb, vb, g["in"]["slots0"], g["p"], meta["T"], meta["eps"])
+    assert rel_err(s, s_ref) < BF16_TOL and rel_err(a, a_ref) < BF16_TOL
