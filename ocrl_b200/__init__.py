@@ -5,7 +5,7 @@ from .slot_attn import SlotAttention, SlotAttentionEncoder  # noqa: F401
 from .feature_stage import PositionalEmbedding, SlotAttnCNNEncoder  # noqa: F401
 from .slate_module import SLATE_Module  # noqa: F401
 from .slate import SLATE, Base  # noqa: F401
-from .graphed import GraphedEncoder  # noqa: F401
+from .graphed import GraphedEncoder, StreamedEncoder  # noqa: F401
 
 __all__ = ["SLATE", "SLATE_Module", "Base", "SlotAttention", "SlotAttentionEncoder", "SlotAttnCNNEncoder",
-           "PositionalEmbedding", "GraphedEncoder"]
+           "PositionalEmbedding", "GraphedEncoder", "StreamedEncoder"]

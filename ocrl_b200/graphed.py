@@ -39,3 +39,66 @@ class GraphedEncoder:
         self.static_obs.copy_(obs, non_blocking=True)
         self.graph.replay()
         return self.static_out
+
+
+class StreamedEncoder:
+    """Host-to-host slot encoding at the GPU's pace: two ``GraphedEncoder`` buffers in ping-pong, the pinned-host ->
+    device copy of batch i+1 and the device -> pinned-host copy of result i-1 run on copy streams while the graph of
+    batch i replays (dataset encoding / PPO rollout feeding, utils/datasets.py + sb3s/ocr_extractor.py:45 use case).
+
+        enc = StreamedEncoder(ocr, example_obs_dev)
+        for i, frames in enumerate(pinned_batches):
+            enc.submit(frames, out_pinned[i])      # asynchronous
+        enc.synchronize()                          # every out_pinned[i] is valid
+
+    Every submit performs its own H2D and D2H copy; nothing is cached between batches."""
+
+    def __init__(self, ocr, example_obs: torch.Tensor, with_masks: bool = False):
+        dev = example_obs.device
+        self._enc = [GraphedEncoder(ocr, example_obs, with_masks), GraphedEncoder(ocr, example_obs, with_masks)]
+        self._in = torch.cuda.Stream(device=dev)
+        self._out = torch.cuda.Stream(device=dev)
+        self._dev = dev
+        self._ev_in = [torch.cuda.Event() for _ in range(2)]
+        self._ev_done = [torch.cuda.Event() for _ in range(2)]
+        self._ev_out = [torch.cuda.Event() for _ in range(2)]
+        self._used = [False, False]
+        self._i = 0
+
+    def submit(self, obs_host: torch.Tensor, out_host):
+        """obs_host: pinned host (or device) frames of the captured shape; out_host: pinned host tensor (or tuple of
+        tensors when with_masks) that receives the result."""
+        s = self._i & 1
+        self._i += 1
+        enc = self._enc[s]
+        main = torch.cuda.current_stream(self._dev)
+        if self._used[s]:
+            self._in.wait_event(self._ev_done[s])   # the graph that read this input buffer has finished
+        with torch.cuda.stream(self._in):
+            enc.static_obs.copy_(obs_host, non_blocking=True)
+            self._ev_in[s].record(self._in)
+        main.wait_event(self._ev_in[s])
+        if self._used[s]:
+            main.wait_event(self._ev_out[s])        # the previous result of this buffer has left the device
+        enc.graph.replay()
+        self._ev_done[s].record(main)
+        self._out.wait_event(self._ev_done[s])
+        with torch.cuda.stream(self._out):
+            if isinstance(enc.static_out, (tuple, list)):
+                for dst, src in zip(out_host, enc.static_out):
+                    dst.copy_(src, non_blocking=True)
+            else:
+                out_host.copy_(enc.static_out, non_blocking=True)
+            self._ev_out[s].record(self._out)
+        self._used[s] = True
+
+    def join(self):
+        """Make the current stream wait for every copy submitted so far (no host synchronisation)."""
+        main = torch.cuda.current_stream(self._dev)
+        main.wait_stream(self._in)
+        main.wait_stream(self._out)
+
+    def synchronize(self):
+        self._in.synchronize()
+        self._out.synchronize()
+        torch.cuda.current_stream(self._dev).synchronize()

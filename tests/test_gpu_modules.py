@@ -124,3 +124,26 @@ def test_bf16_mode_with_tensor_core_convs(monkeypatch, conv):
     es, em = rel_err(slots.cpu(), g["out"]["slots"]), rel_err(masks.cpu(), g["out"]["masks"])
     print(f"bf16 mode, {conv} convs: slots rel err {es:.2e}, masks rel err {em:.2e}")
     assert es < 2e-2 and em < 2e-2
+
+
+def test_streamed_encoder_matches_direct_calls():
+    """StreamedEncoder (double-buffered H2D / graph replay / D2H) returns, batch by batch, what the model returns for
+    the same frames and the same slot-initialisation noise."""
+    meta, g = load_case("slate_encode_64")
+    model = ocrl_b200.SLATE(*slate_config())
+    _load_hot(model._module, g["p"])
+    model.to("cuda")
+    model.eval()
+    _inject_noise(model._module._slotattn, g["in"]["noise"].cuda())  # device tensor: the call is graph-captured
+    obs = (g["in"]["frames_u8"].permute(0, 3, 1, 2).float() / 255.0)
+    batches = [obs, obs.flip(0), obs.roll(1, 0), obs]
+    with torch.no_grad():
+        want = [model(b.cuda()).cpu() for b in batches]
+    enc = ocrl_b200.StreamedEncoder(model, obs.cuda())
+    pinned = [b.contiguous().pin_memory() for b in batches]
+    outs = [torch.empty_like(want[0]).pin_memory() for _ in batches]
+    for b, o in zip(pinned, outs):
+        enc.submit(b, o)
+    enc.synchronize()
+    for w, o in zip(want, outs):
+        assert torch.equal(w, o)
