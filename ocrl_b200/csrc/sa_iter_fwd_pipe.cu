@@ -166,6 +166,8 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
   const int TPC = (ntiles + CL - 1) / CL;
   const int tile0 = rank * TPC;
   const int TP = max(0, min(TPC, ntiles - tile0));
+  // tile j is handled by chain j % 4 and lives in stage j % S: with S % 4 == 0 and TP % 4 == 0 a warp only ever sees its own stages
+  const bool guard = (S % 4 != 0) || (TP % 4 != 0);
 
   // one elected lane: stage (j % S) <- tile j = n * TP + tile of the CTA's tile sequence (pass ops in stream order).
   // L2 policy: tiles of iterations 0..T-2 are read again by the next pass (evict_last), the final pass's are dead
@@ -185,7 +187,7 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
     mbar_expect_tx(&full[s], (uint32_t)C::STAGE_BYTES);
     tma_load_3d_hint(kd, &tm_k, 0, 0, row0, &full[s], pol);
     tma_load_3d_hint(kd + C::TILE_BYTES, &tm_v, 0, 0, row0, &full[s], pol);
-    sts_volatile(&issued[s], j);  // after the expect_tx above in program order: the barrier is in this tile's phase
+    sts_volatile(&issued[s], j);  // after the expect_tx in program order: the barrier is in this tile's phase
     // paced L2 prefetch, only where the data is cold (first pass of an image)
     int pn = n, pt = tile + PFD;
     while (pt >= TP && pn < total_ops) { pt -= TP; ++pn; }
@@ -377,7 +379,9 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
           uint32_t* wt = reinterpret_cast<uint32_t*>(wtiles + s * C::WT_BYTES);
           const bool tt = tracer && tid == 0 && n == TRACE_OP && tile < 32;  // tile stamps of chain 0 in a steady-state op
           if (tt) a.trace[340 + (tile >> 2) * 8 + 0] = clock64();
-          while (lds_volatile(&issued[s]) < j) __nanosleep(20);  // the barrier has entered this tile's phase (parity waits alias)
+          // mbarrier parity waits alias two phases ahead: unless a warp always returns to the same stages, make sure the
+          // barrier has entered this tile's phase first
+          if (guard) while (lds_volatile(&issued[s]) < j) __nanosleep(20);
           mbar_wait(&full[s], ph);
           if (tt) a.trace[340 + (tile >> 2) * 8 + 1] = clock64();
           float ca[4] = {0.f, 0.f, 0.f, 0.f}, cb[4] = {0.f, 0.f, 0.f, 0.f};
@@ -488,7 +492,7 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
           const uint32_t* wt = reinterpret_cast<const uint32_t*>(wtiles + s * C::WT_BYTES);
           const bool tt = tracer && tid == 128 && n == TRACE_OP && tile < 32;
           if (tt) a.trace[340 + (tile >> 2) * 8 + 4] = clock64();
-          while (lds_volatile(&issued[s]) < j) __nanosleep(20);
+          if (guard) while (lds_volatile(&issued[s]) < j) __nanosleep(20);
           mbar_wait(&w_ready[s], ph);  // implies full[s]: the logit warp waited for k and v together
           if (tt) a.trace[340 + (tile >> 2) * 8 + 5] = clock64();
           const uint32_t b0 = wt[lane], b1 = wt[32 + lane];
