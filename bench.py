@@ -233,20 +233,28 @@ def measure(a, mode, steps, warmup, dev, dist, rank, world, pool_host, pool_dev,
         except Exception as exc:  # report, fall back to eager launches
             sys.stderr.write(f"bench.py: CUDA graph capture failed ({exc}); timing eager launches\n")
     if graphed is not None:
-        def step_resident(i):
+        def step_single(i):
             graphed(batch_dev(i))
 
-        # end to end through the public streaming API: every step copies its frames from pinned host memory and its
-        # slots back to pinned host memory; the copies of neighbouring steps overlap the graph replay
-        streamed = ocrl_b200.StreamedEncoder(model, batch_dev(0))
-        outs_host = [torch.empty_like(out_host).pin_memory() for _ in range(2)]
+        # the public streaming API: two batches in flight (two graph buffers replaying on their own streams, so the
+        # latency-bound iteration kernel of one batch shares the GPU with the convolutions of the next).
+        # value: frames already resident in HBM, slots left in HBM.  e2e: every step copies its frames from pinned host
+        # memory and its slots back to pinned host memory, copies overlapping the replays.
+        nbuf = int(os.environ.get("OCRL_BENCH_BUFFERS", 2))
+        streamed = ocrl_b200.StreamedEncoder(model, batch_dev(0), buffers=nbuf)
+        outs_host = [torch.empty_like(out_host).pin_memory() for _ in range(nbuf)]
+        outs_dev = [torch.empty(a.batch, a.slots, a.slot_size, device=dev) for _ in range(nbuf)]
+
+        def step_resident(i):
+            streamed.submit(batch_dev(i), outs_dev[i % nbuf])
 
         def step_e2e(i):
-            streamed.submit(batch_host(i), outs_host[i & 1])
+            streamed.submit(batch_host(i), outs_host[i % nbuf])
         e2e_join = streamed.join
     else:
         obs_stage = torch.empty(a.batch, 3, a.size, a.size, device=dev)
         step_resident = step_eager
+        step_single = None
         e2e_join = None
 
         def step_e2e(i):
@@ -254,11 +262,13 @@ def measure(a, mode, steps, warmup, dev, dist, rank, world, pool_host, pool_dev,
             with torch.no_grad():
                 out_host.copy_(model(obs_stage), non_blocking=True)
 
-    ms_res, _ = timed(step_resident, steps, warmup)
+    ms_res, _ = timed(step_resident, steps, warmup, join=e2e_join)
+    ms_single = timed(step_single, steps, warmup)[0] if step_single is not None else None
     ms_e2e, _ = timed(step_e2e, steps, max(3, warmup), join=e2e_join)
     images = a.batch * steps * world
     res = {"value": images / ms_res * 1e3, "ms_per_step": ms_res / steps, "eager_value": images / ms_eager * 1e3,
            "e2e_value": images / ms_e2e * 1e3, "e2e_ms_per_step": ms_e2e / steps, "graph": graphed is not None,
+           "single_stream_value": (images / ms_single * 1e3) if ms_single else None,
            "events": events or []}
     return res
 
@@ -406,7 +416,8 @@ def main():
                 "config": dict(workload(a), l2="k/v working set per step %.0f MB > 126 MB L2; frame pool of %d rotates"
                                % (a.batch * 2 * N * D * esz / 1e6, a.pool),
                                cnn="cuDNN via torch (library call, fused bias+ReLU in bf16 mode); token stage + iteration loop hand-written CUDA",
-                               launch="CUDA graph replay of SLATE.__call__" if main_res["graph"] else "eager launches",
+                               launch=("CUDA graph replays of SLATE.__call__, two batches in flight on two streams "
+                                       "(single_stream_value: one replay at a time)") if main_res["graph"] else "eager launches",
                                e2e="ocrl_b200.StreamedEncoder: per step H2D from pinned frames, graph replay, D2H to pinned "
                                    "slots; copies of neighbouring steps overlap the replay (two buffers)"),
                 "clocks": clk,
@@ -414,6 +425,7 @@ def main():
                         "h2d_bytes_per_step": a.batch * 3 * a.size * a.size * 4,
                         "d2h_bytes_per_step": a.batch * a.slots * a.slot_size * 4},
                 "gpu_launches": len(mine), "eager_value": main_res["eager_value"],
+                "single_stream_value": main_res["single_stream_value"],
                 "roofline": roofline_of(a, a.mode, main_res["events"])}
         if other is not None:
             om, r = other

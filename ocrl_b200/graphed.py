@@ -53,25 +53,33 @@ class StreamedEncoder:
 
     Every submit performs its own H2D and D2H copy; nothing is cached between batches."""
 
-    def __init__(self, ocr, example_obs: torch.Tensor, with_masks: bool = False):
+    def __init__(self, ocr, example_obs: torch.Tensor, with_masks: bool = False, concurrent_replays: bool = True,
+                 buffers: int = 2):
         dev = example_obs.device
-        self._enc = [GraphedEncoder(ocr, example_obs, with_masks), GraphedEncoder(ocr, example_obs, with_masks)]
+        self._nb = buffers
+        self._enc = [GraphedEncoder(ocr, example_obs, with_masks) for _ in range(buffers)]
+        # with concurrent_replays the two buffers replay on their own streams, so the latency-bound iteration kernel of
+        # one batch (13 clusters of 8 SMs) shares the GPU with the convolutions of the next
+        self._compute = [torch.cuda.Stream(device=dev) for _ in range(buffers)] if concurrent_replays else None
         self._in = torch.cuda.Stream(device=dev)
         self._out = torch.cuda.Stream(device=dev)
         self._dev = dev
-        self._ev_in = [torch.cuda.Event() for _ in range(2)]
-        self._ev_done = [torch.cuda.Event() for _ in range(2)]
-        self._ev_out = [torch.cuda.Event() for _ in range(2)]
-        self._used = [False, False]
+        self._ev_in = [torch.cuda.Event() for _ in range(buffers)]
+        self._ev_done = [torch.cuda.Event() for _ in range(buffers)]
+        self._ev_out = [torch.cuda.Event() for _ in range(buffers)]
+        self._used = [False] * buffers
         self._i = 0
 
     def submit(self, obs_host: torch.Tensor, out_host):
         """obs_host: pinned host (or device) frames of the captured shape; out_host: pinned host tensor (or tuple of
         tensors when with_masks) that receives the result."""
-        s = self._i & 1
+        s = self._i % self._nb
         self._i += 1
         enc = self._enc[s]
-        main = torch.cuda.current_stream(self._dev)
+        caller = torch.cuda.current_stream(self._dev)
+        main = self._compute[s] if self._compute is not None else caller
+        if self._compute is not None and not self._used[s]:
+            main.wait_stream(caller)                # work the caller queued before the first submit
         if self._used[s]:
             self._in.wait_event(self._ev_done[s])   # the graph that read this input buffer has finished
         with torch.cuda.stream(self._in):
@@ -80,8 +88,9 @@ class StreamedEncoder:
         main.wait_event(self._ev_in[s])
         if self._used[s]:
             main.wait_event(self._ev_out[s])        # the previous result of this buffer has left the device
-        enc.graph.replay()
-        self._ev_done[s].record(main)
+        with torch.cuda.stream(main):
+            enc.graph.replay()
+            self._ev_done[s].record(main)
         self._out.wait_event(self._ev_done[s])
         with torch.cuda.stream(self._out):
             if isinstance(enc.static_out, (tuple, list)):
@@ -97,8 +106,14 @@ class StreamedEncoder:
         main = torch.cuda.current_stream(self._dev)
         main.wait_stream(self._in)
         main.wait_stream(self._out)
+        if self._compute is not None:
+            for st in self._compute:
+                main.wait_stream(st)
 
     def synchronize(self):
         self._in.synchronize()
         self._out.synchronize()
+        if self._compute is not None:
+            for st in self._compute:
+                st.synchronize()
         torch.cuda.current_stream(self._dev).synchronize()
