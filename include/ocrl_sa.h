@@ -154,6 +154,12 @@ int ocrl_sa_iter_bwd(const ocrl_sa_dims* dims, const void* k, const void* v, con
  *   ocrl_frames_to_nhwc_bf16: obs [B,C,H,W] fp32 in [0,1] (utils/datasets.py:17) -> out [B,H,W,CP] bf16 with the
  *     channels zero-padded to CP = 8 (input of the first convolution, ocrs/common/models.py:99). */
 int ocrl_conv_bias_relu_bf16(void* y, const float* bias, long long npixels, int channels, void* stream);
+/* First layer of SlotAttnCNNEncoder (ocrs/common/models.py:99 = Conv2dBlock(obs_channels, 64, 5, 1, 2)), fused:
+ *   out[B,H,W,64] (bf16, channels-last) = relu(conv5x5(obs[B,C,H,W] fp32, weight[64,C,5,5]) + bias[64]),
+ * operands rounded to bf16, fp32 accumulate (the arithmetic of the module under bf16 autocast).  C = 3, CO = 64,
+ * W a multiple of 16. */
+int ocrl_conv_first_relu_bf16(const float* obs, const float* weight, const float* bias, void* out, int B, int C,
+                              int H, int W, int CO, void* stream);
 int ocrl_frames_to_nhwc_bf16(const float* obs, void* out, int B, int C, int H, int W, int CP, void* stream);
 
 #ifdef __cplusplus

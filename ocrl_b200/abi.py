@@ -22,6 +22,7 @@ EXPORTS = [
     "ocrl_version", "ocrl_built_arch", "ocrl_last_error", "ocrl_sa_query_workspace",
     "ocrl_kv_proj_fwd_workspace", "ocrl_kv_proj_fwd", "ocrl_kv_proj_bwd_workspace", "ocrl_kv_proj_bwd",
     "ocrl_sa_iter_fwd", "ocrl_sa_iter_bwd", "ocrl_conv_bias_relu_bf16", "ocrl_frames_to_nhwc_bf16",
+    "ocrl_conv_first_relu_bf16",
 ]
 
 
@@ -78,6 +79,9 @@ def lib() -> ctypes.CDLL:
                                        c_void_p]
         L.ocrl_conv_bias_relu_bf16.argtypes = [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p]
         L.ocrl_frames_to_nhwc_bf16.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
+        L.ocrl_conv_first_relu_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                                c_int, c_void_p]
+        L.ocrl_conv_first_relu_bf16.restype = c_int
         for name in ("ocrl_sa_query_workspace", "ocrl_kv_proj_fwd", "ocrl_kv_proj_bwd", "ocrl_sa_iter_fwd",
                      "ocrl_sa_iter_bwd", "ocrl_conv_bias_relu_bf16", "ocrl_frames_to_nhwc_bf16"):
             getattr(L, name).restype = c_int

@@ -55,6 +55,7 @@ class FusedBf16Encoder:
             bs.append(c.bias.detach().float().contiguous())
         self._w, self._b, self._key = ws, bs, key
         self._b16 = [b.to(torch.bfloat16) for b in bs]
+        self._w0_f32 = convs[0].weight.detach().float().contiguous()  # the hand-written first layer rounds it itself
 
     @property
     def last_bias(self):
@@ -72,7 +73,18 @@ class FusedBf16Encoder:
         cin = self._w[0].shape[1]
         use_cudnn_epilogue = os.environ.get("OCRL_CONV_EPILOGUE", "cudnn") == "cudnn"
         L = abi.lib()
-        if cin == 8 and obs.dtype == torch.float32 and obs.is_contiguous():
+        first = 0
+        own_first = (os.environ.get("OCRL_CONV_FIRST", "ocrl") == "ocrl" and C == 3 and W % 16 == 0 and W <= 512
+                     and self._w0_f32.shape[0] == 64 and tuple(self._w0_f32.shape[2:]) == (5, 5)
+                     and obs.dtype == torch.float32 and obs.is_contiguous())
+        if own_first:
+            # hand-written fused first layer: fp32 NCHW frames in, relu(conv + bias) out as bf16 channels-last
+            x = torch.empty(B, 64, H, W, device=obs.device, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            abi.check(L.ocrl_conv_first_relu_bf16(abi.ptr(obs), abi.ptr(self._w0_f32), abi.ptr(self._b[0]),
+                                                  ctypes.c_void_p(x.data_ptr()), B, C, H, W, 64, abi.stream_ptr()),
+                      "ocrl_conv_first_relu_bf16")
+            first = 1
+        elif cin == 8 and obs.dtype == torch.float32 and obs.is_contiguous():
             x = torch.empty(B, cin, H, W, device=obs.device, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
             abi.check(L.ocrl_frames_to_nhwc_bf16(abi.ptr(obs), ctypes.c_void_p(x.data_ptr()), B, C, H, W, cin,
                                                  abi.stream_ptr()), "ocrl_frames_to_nhwc_bf16")
@@ -82,7 +94,7 @@ class FusedBf16Encoder:
         # OCRL_CUDNN_BENCHMARK=1 lets cuDNN time its candidates once per shape (no gain measured on B200)
         autotune = os.environ.get("OCRL_CUDNN_BENCHMARK", "0") != "0"
         with torch.backends.cudnn.flags(enabled=True, benchmark=autotune, deterministic=False, allow_tf32=True):
-            for i in range(3):
+            for i in range(first, 3):
                 if use_cudnn_epilogue or self._w[i].shape[0] not in (64, 128):
                     x = torch.cudnn_convolution_relu(x, self._w[i], self._b16[i], [1, 1], [2, 2], [1, 1], 1)
                 else:
