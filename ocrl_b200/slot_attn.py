@@ -123,7 +123,15 @@ class SlotAttentionEncoder(nn.Module):
     def init_slots(self, batch, like):
         # same draw as the reference (slot_attn.py:155): torch's generator on the tensor's device
         noise = like.new_empty(batch, self.num_slots, self.slot_size).normal_()
-        return self.slot_mu + torch.exp(self.slot_log_sigma) * noise
+        if torch.is_grad_enabled() and (self.slot_mu.requires_grad or self.slot_log_sigma.requires_grad):
+            return self.slot_mu + torch.exp(self.slot_log_sigma) * noise
+        # inference: sigma cached until the parameter changes, one fused multiply-add (same values)
+        key = (self.slot_log_sigma.data_ptr(), self.slot_log_sigma._version)
+        cached = self.__dict__.get("_sigma_cache")
+        if cached is None or cached[0] != key:
+            cached = (key, torch.exp(self.slot_log_sigma.detach()))
+            self.__dict__["_sigma_cache"] = cached
+        return torch.addcmul(self.slot_mu.detach(), cached[1], noise.to(self.slot_mu.dtype))
 
     def forward(self, x, *, _pos_table=None):
         """x [B,N,C] (or the NCHW feature map when ``_pos_table`` is given) -> (slots, attn)."""
