@@ -79,17 +79,17 @@ class FusedBf16Encoder:
                      and obs.dtype == torch.float32 and obs.is_contiguous())
         if own_first:
             # hand-written fused first layer: fp32 NCHW frames in, relu(conv + bias) out as bf16 channels-last
-            x = torch.empty(B, 64, H, W, device=obs.device, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            x = torch.empty((B, 64, H, W), device=obs.device, dtype=torch.bfloat16, memory_format=torch.channels_last)
             abi.check(L.ocrl_conv_first_relu_bf16(abi.ptr(obs), abi.ptr(self._w0_f32), abi.ptr(self._b[0]),
                                                   ctypes.c_void_p(x.data_ptr()), B, C, H, W, 64, abi.stream_ptr()),
                       "ocrl_conv_first_relu_bf16")
             first = 1
         elif cin == 8 and obs.dtype == torch.float32 and obs.is_contiguous():
-            x = torch.empty(B, cin, H, W, device=obs.device, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            x = torch.empty((B, cin, H, W), device=obs.device, dtype=torch.bfloat16, memory_format=torch.channels_last)
             abi.check(L.ocrl_frames_to_nhwc_bf16(abi.ptr(obs), ctypes.c_void_p(x.data_ptr()), B, C, H, W, cin,
                                                  abi.stream_ptr()), "ocrl_frames_to_nhwc_bf16")
         else:
-            x = torch.zeros(B, cin, H, W, device=obs.device, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            x = torch.zeros((B, cin, H, W), device=obs.device, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
             x[:, :C] = obs
         # OCRL_CUDNN_BENCHMARK=1 lets cuDNN time its candidates once per shape (no gain measured on B200)
         autotune = os.environ.get("OCRL_CUDNN_BENCHMARK", "0") != "0"
