@@ -121,7 +121,11 @@ def test_saved_state_matches_the_per_image_kernel(monkeypatch):
     torch.cuda.synchronize()
     assert rel_err(s_new.cpu(), s_old.cpu()) < BF16_TOL
     assert saved_new.shape == saved_old.shape
-    assert rel_err(saved_new.cpu(), saved_old.cpu()) < BF16_TOL, rel_err(saved_new.cpu(), saved_old.cpu())
+    K, D, H, T, B = meta["K"], meta["D"], meta["H"], meta["T"], kb.shape[0]
+    used = 8 * K * D + K * H + K  # the rows are padded to a multiple of 4 floats; the padding is never written
+    new = saved_new.view(B, T, -1)[..., :used].cpu()
+    old = saved_old.view(B, T, -1)[..., :used].cpu()
+    assert rel_err(new, old) < BF16_TOL, rel_err(new, old)
 
 
 @pytest.mark.parametrize("B,N,K,T", [(2, 256, 6, 3), (5, 1000, 7, 7), (64, 4096, 6, 7)])
