@@ -152,3 +152,26 @@ def test_small_configuration_golden_case():
     s_ref, a_ref = so.iterate(kb.float(), vb.float(), g["in"]["slots0"], g["p"], meta["T"], meta["eps"])
     s, a = _run(kb, vb, g["in"]["slots0"], g["p"], meta["T"], meta["eps"])
     assert rel_err(s, s_ref) < BF16_TOL and rel_err(a, a_ref) < BF16_TOL
+
+
+def test_full_size_slot_and_token_permutation_properties():
+    """BASELINE size, properties that need no oracle: permuting the initial slots permutes the output slots and the
+    attention columns (slots are exchangeable; the softmax denominator is summed in slot order, so equality holds up
+    to fp32 summation order and the bf16 rounding of the weights it feeds); permuting the tokens of an image permutes
+    its attention rows and leaves the slots unchanged up to the summation order over tokens."""
+    from ocrl_b200 import functional as F
+
+    torch.manual_seed(1)
+    p = _cuda(so.random_sa_params(6, 64, 192, 192, seed=3))
+    x = torch.randn(8, 4096, 64, device="cuda")
+    s0 = torch.randn(8, 6, 192, device="cuda")
+    k, v, _ = F.kv_project(x, p, kv="bf16")
+    s, a, _ = F.iterate(k, v, s0, p, 3)
+    sp = torch.tensor([3, 0, 5, 1, 4, 2], device="cuda")
+    s_sp, a_sp, _ = F.iterate(k, v, s0[:, sp].contiguous(), p, 3)
+    assert rel_err(s_sp.cpu(), s[:, sp].cpu()) < 2e-3, rel_err(s_sp.cpu(), s[:, sp].cpu())
+    assert rel_err(a_sp.cpu(), a[:, :, sp].cpu()) < 2e-3
+    tp = torch.randperm(4096, device="cuda")
+    s_tp, a_tp, _ = F.iterate(k[:, tp].contiguous(), v[:, tp].contiguous(), s0, p, 3)
+    assert rel_err(s_tp.cpu(), s.cpu()) < 2e-3, rel_err(s_tp.cpu(), s.cpu())
+    assert rel_err(a_tp.cpu(), a[:, tp].cpu()) < 2e-3
