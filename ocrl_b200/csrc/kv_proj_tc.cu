@@ -13,6 +13,7 @@
 // The three GEMMs of a tile (64->64, 64->64, 64->2D) chain through tensor memory (64 + 64 + 2D <= 512
 // columns); activations never return to HBM between the layers.  HBM-bound: 256 B in, 4D B out per token.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -29,6 +30,7 @@ struct ProjTcParams {
   const float* in_ln_w; const float* in_ln_b;
   const float* pos;                               // [64][N] or null (token-major input)
   float* y_out;                                   // [M][64] or null
+  long long* trace;                               // optional clock64 stamps of CTA 0 / thread 0 (development aid)
   int has_mlp, x_format, N, D;
   long long M;
   int ntiles;
@@ -93,6 +95,31 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 64 consecutive fp32 columns: both loads are issued before the single wait
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&lo)[32], float (&hi)[32]) {
+  uint32_t a[32], b[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
+      "%30,%31}, [%32];"
+      : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]), "=r"(a[8]),
+        "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]), "=r"(a[16]),
+        "=r"(a[17]), "=r"(a[18]), "=r"(a[19]), "=r"(a[20]), "=r"(a[21]), "=r"(a[22]), "=r"(a[23]), "=r"(a[24]),
+        "=r"(a[25]), "=r"(a[26]), "=r"(a[27]), "=r"(a[28]), "=r"(a[29]), "=r"(a[30]), "=r"(a[31])
+      : "r"(taddr));
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
+      "%30,%31}, [%32];"
+      : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7]), "=r"(b[8]),
+        "=r"(b[9]), "=r"(b[10]), "=r"(b[11]), "=r"(b[12]), "=r"(b[13]), "=r"(b[14]), "=r"(b[15]), "=r"(b[16]),
+        "=r"(b[17]), "=r"(b[18]), "=r"(b[19]), "=r"(b[20]), "=r"(b[21]), "=r"(b[22]), "=r"(b[23]), "=r"(b[24]),
+        "=r"(b[25]), "=r"(b[26]), "=r"(b[27]), "=r"(b[28]), "=r"(b[29]), "=r"(b[30]), "=r"(b[31])
+      : "r"(taddr + 32));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) { lo[i] = __uint_as_float(a[i]); hi[i] = __uint_as_float(b[i]); }
+}
 
 // K-major, 128-byte-swizzled shared-memory operand descriptor (rows of 64 bf16 = 128 B, 8-row groups 1024 B apart)
 __device__ __forceinline__ uint64_t umma_desc_sw128(const void* smem) {
@@ -109,19 +136,21 @@ __host__ __device__ constexpr uint32_t umma_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
-// LayerNorm of one row held in registers
+// LayerNorm of one row held in registers (four independent partial sums: the 64-long dependent add chains were a
+// tenth of a tile's time)
 __device__ __forceinline__ void row_layer_norm(float (&x)[PT_C], const float* gw, const float* gb, float eps) {
-  float s = 0.f;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-  for (int i = 0; i < PT_C; ++i) s += x[i];
-  const float mean = s * (1.f / PT_C);
-  float q = 0.f;
+  for (int i = 0; i < PT_C; i += 4) { s0 += x[i]; s1 += x[i + 1]; s2 += x[i + 2]; s3 += x[i + 3]; }
+  const float mean = ((s0 + s1) + (s2 + s3)) * (1.f / PT_C);
+  float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll
-  for (int i = 0; i < PT_C; ++i) {
-    x[i] -= mean;
-    q = fmaf(x[i], x[i], q);
+  for (int i = 0; i < PT_C; i += 4) {
+    x[i] -= mean; x[i + 1] -= mean; x[i + 2] -= mean; x[i + 3] -= mean;
+    q0 = fmaf(x[i], x[i], q0); q1 = fmaf(x[i + 1], x[i + 1], q1);
+    q2 = fmaf(x[i + 2], x[i + 2], q2); q3 = fmaf(x[i + 3], x[i + 3], q3);
   }
-  const float rstd = rsqrtf(q * (1.f / PT_C) + eps);
+  const float rstd = rsqrtf(((q0 + q1) + (q2 + q3)) * (1.f / PT_C) + eps);
 #pragma unroll
   for (int i = 0; i < PT_C; ++i) x[i] = x[i] * rstd * gw[i] + gb[i];
 }
@@ -160,13 +189,15 @@ kv_proj_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   unsigned char* O_s = sp; sp += 2 * PT_TM * 128;   // two staging tiles for the TMA stores
   unsigned char* X_s = sp; sp += 2 * PT_TM * PT_C * 4;  // two fp32 token tiles
   float* prm = reinterpret_cast<float*>(sp); sp += 6 * PT_C * sizeof(float);  // enc ln w,b | b1 | b2 | in ln w,b
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sp); sp += 8 * sizeof(uint64_t);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sp); sp += 12 * sizeof(uint64_t);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sp);
   uint64_t* full = bars;        // [2] token tile landed
   uint64_t* empty = bars + 2;   // [2] token tile consumed by the 128 row threads
   uint64_t* a_ready = bars + 4; // A tile written (128 arrivals)
   uint64_t* mma_done = bars + 5;
   uint64_t* w_full = bars + 6;
+  uint64_t* o_ready = bars + 7;  // [2] staging tile written by the 128 row threads
+  uint64_t* o_free = bars + 9;   // [2] the TMA store that used the staging tile has read it (producer lane arrives)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -184,6 +215,8 @@ kv_proj_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     mbar_init(a_ready, PT_ROWT);
     mbar_init(mma_done, 1);
     mbar_init(w_full, 1);
+    mbar_init(&o_ready[0], PT_ROWT); mbar_init(&o_ready[1], PT_ROWT);
+    mbar_init(&o_free[0], 1); mbar_init(&o_free[1], 1);
   }
   mbar_fence_init();
   if (warp == 4) {  // tensor memory: 512 columns for this CTA
@@ -261,7 +294,23 @@ kv_proj_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           mbar_wait(&empty[it & 1], (uint32_t)((it >> 1) & 1));
           load_x(it + 2);
         }
+        // the tile's k | v TMA stores are issued here, off the row threads' critical path: chunk c of this CTA's
+        // store sequence uses staging tile c & 1; a tile is handed back once its store has read it
+        const long long tile = blockIdx.x + (long long)it * gridDim.x;
+        for (int ch = 0; ch < NKV / 64; ++ch) {
+          const int sq = it * (NKV / 64) + ch, buf = sq & 1;
+          mbar_wait(&o_ready[buf], (uint32_t)((sq >> 1) & 1));
+          const int f0 = 64 * ch;
+          if (f0 < D) tma_store_2d(&tm_k, O_s + buf * (PT_TM * 128), f0, (int)(tile * PT_TM));
+          else tma_store_2d(&tm_v, O_s + buf * (PT_TM * 128), f0 - D, (int)(tile * PT_TM));
+          tma_store_commit();
+          if (sq >= 1) {  // the previous store (other staging tile) has been read: that tile is free again
+            tma_store_wait_read<1>();
+            mbar_arrive(&o_free[buf ^ 1]);
+          }
+        }
       }
+      tma_store_wait_all<0>();
     }
   } else {
     // ================================ row threads: one token each ==========================================
@@ -274,7 +323,10 @@ kv_proj_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       const long long m = tile * PT_TM + row;
       const int s = it & 1;
       float x[PT_C];
+      const bool tr = (p.trace != nullptr && blockIdx.x == 0 && tid == 0 && it >= 2 && it < 10);
+      if (tr) p.trace[(it - 2) * 8 + 0] = clock64();
       mbar_wait(&full[s], (uint32_t)((it >> 1) & 1));
+      if (tr) p.trace[(it - 2) * 8 + 1] = clock64();
       const unsigned char* xs = X_s + s * X_BYTES;
       if (p.x_format == OCRL_X_NCHW_F32) {
 #pragma unroll
@@ -307,12 +359,14 @@ kv_proj_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         for (int c = 0; c < PT_C; ++c) x[c] += __ldg(p.pos + (size_t)c * p.N + n);
       }
 
+      if (tr) p.trace[(it - 2) * 8 + 2] = clock64();
       if (p.has_mlp) {
         row_layer_norm(x, prm, prm + 64, p.ln_eps);
         store_row_bf16_sw128(A_s, row, x);
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(a_ready);
+        if (tr) p.trace[(it - 2) * 8 + 3] = clock64();
         // hidden layer: relu(acc + b1)
         mbar_wait(mma_done, md_phase); md_phase ^= 1;
         tc_fence_after();
@@ -329,6 +383,7 @@ kv_proj_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(a_ready);
+        if (tr) p.trace[(it - 2) * 8 + 4] = clock64();
         // output layer: acc + b2  (= the token-MLP output y)
         mbar_wait(mma_done, md_phase); md_phase ^= 1;
         tc_fence_after();
@@ -353,17 +408,19 @@ kv_proj_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       tc_fence_before();
       mbar_arrive(a_ready);
 
+      if (tr) p.trace[(it - 2) * 8 + 5] = clock64();
       // ---- k | v epilogue: TMEM -> bf16 -> swizzled staging tile -> TMA store, 64 features at a time ----
       mbar_wait(mma_done, md_phase); md_phase ^= 1;
+      if (tr) p.trace[(it - 2) * 8 + 6] = clock64();
       tc_fence_after();
 #pragma unroll 1
       for (int ch = 0; ch < NKV / 64; ++ch) {
         float lo[32], hi[32];
-        tmem_ld32(trow + COL_KV + 64 * ch, lo);
-        tmem_ld32(trow + COL_KV + 64 * ch + 32, hi);
-        unsigned char* ot = O_s + (store_seq & 1) * (PT_TM * 128);
-        if (tid == 0) tma_store_wait_read<1>();  // the store that last used this staging tile has read it
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        tmem_ld64(trow + COL_KV + 64 * ch, lo, hi);
+        const int buf = store_seq & 1;
+        unsigned char* ot = O_s + buf * (PT_TM * 128);
+        // staging tile `buf` was last used by store store_seq - 2; its hand-back is phase (store_seq / 2 - 1)
+        if (store_seq >= 2) mbar_wait(&o_free[buf], (uint32_t)(((store_seq >> 1) - 1) & 1));
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const float* src = (c < 4) ? (lo + 8 * c) : (hi + 8 * (c - 4));
@@ -373,18 +430,12 @@ kv_proj_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           *reinterpret_cast<uint4*>(ot + row * 128 + ((c ^ (row & 7)) << 4)) = u;
         }
         fence_proxy_async();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (tid == 0) {
-          const int f0 = 64 * ch;
-          if (f0 < D) tma_store_2d(&tm_k, ot, f0, (int)(tile * PT_TM));
-          else tma_store_2d(&tm_v, ot, f0 - D, (int)(tile * PT_TM));
-          tma_store_commit();
-        }
+        mbar_arrive(&o_ready[buf]);
         ++store_seq;
       }
       tc_fence_before();
+      if (tr) p.trace[(it - 2) * 8 + 7] = clock64();
     }
-    if (tid == 0) tma_store_wait_all<0>();
   }
   __syncthreads();
   if (warp == 4) {
@@ -439,7 +490,7 @@ static bool make_map(CUtensorMap* tm, CUtensorMapDataType dt, int esz, const voi
 }
 
 size_t kv_proj_tc_workspace(const ocrl_sa_dims* d) {
-  return sizeof(__nv_bfloat16) * ((size_t)2 * 64 * 64 + (size_t)2 * d->D * 64) + 256;
+  return sizeof(__nv_bfloat16) * ((size_t)2 * 64 * 64 + (size_t)2 * d->D * 64) + 256 + 1024;  // + trace slots
 }
 
 // returns OCRL_E_SHAPE when this shape has to take the FFMA kernel instead
@@ -484,6 +535,9 @@ int kv_proj_tc_launch(const ocrl_sa_dims* d, const void* x, const float* pos, co
   ProjTcParams p;
   p.enc_ln_w = w->enc_ln_w; p.enc_ln_b = w->enc_ln_b; p.b1 = w->mlp_b1; p.b2 = w->mlp_b2;
   p.in_ln_w = w->in_ln_w; p.in_ln_b = w->in_ln_b; p.pos = pos; p.y_out = y_out;
+  p.trace = nullptr;
+  if (getenv("OCRL_SA_TRACE") != nullptr)
+    p.trace = reinterpret_cast<long long*>(reinterpret_cast<unsigned char*>(workspace) + kv_proj_tc_workspace(d) - 1024);
   p.has_mlp = has_mlp ? 1 : 0; p.x_format = d->x_format; p.N = d->N; p.D = D; p.M = M;
   p.ntiles = (int)((M + PT_TM - 1) / PT_TM);
   p.ln_eps = d->ln_eps;
@@ -492,7 +546,7 @@ int kv_proj_tc_launch(const ocrl_sa_dims* d, const void* x, const float* pos, co
   OCRL_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = p.ntiles < sms ? p.ntiles : sms;
   const size_t smem = 1024 + (size_t)2 * D * 128 + 2 * 64 * 128 + PT_TM * 128 + 2 * PT_TM * 128 + 2 * PT_TM * PT_C * 4 +
-                      6 * PT_C * 4 + 8 * 8 + 16;
+                      6 * PT_C * 4 + 12 * 8 + 16;
 #define OCRL_LAUNCH_PT(DD)                                                                                       \
   do {                                                                                                           \
     OCRL_CHECK_CUDA(cudaFuncSetAttribute(kv_proj_tc_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
