@@ -32,6 +32,7 @@ struct ProjTcParams {
   float* y_out;                                   // [M][64] or null
   long long* trace;                               // optional clock64 stamps of CTA 0 / thread 0 (development aid)
   int has_mlp, x_format, N, D;
+  int pos_tiles;                                  // 1: the position table arrives as bf16 [N][64] tiles through TMA (tm_pos)
   long long M;
   int ntiles;
   float ln_eps;
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(PT_NT, 1)
 kv_proj_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w1,
                   const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_wkv,
                   const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
-                  const ProjTcParams p) {
+                  const __grid_constant__ CUtensorMap tm_pos, const ProjTcParams p) {
   constexpr int NKV = 2 * D;                       // output features of the projection
   constexpr int N_A = NKV > 256 ? 256 : NKV;       // first UMMA N
   constexpr int N_B = NKV - N_A;                   // second UMMA N (0 if none)
@@ -239,13 +240,15 @@ kv_proj_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         const long long tile = blockIdx.x + (long long)it * gridDim.x;
         const int s = it & 1;
         unsigned char* dst = X_s + s * X_BYTES;
-        mbar_expect_tx(&full[s], p.x_format == OCRL_X_TOKENS_BF16 ? X_BYTES / 2 : X_BYTES);
+        mbar_expect_tx(&full[s], (p.x_format == OCRL_X_TOKENS_BF16 && !p.pos_tiles) ? X_BYTES / 2 : X_BYTES);
         if (p.x_format == OCRL_X_NCHW_F32) {
           const long long m0 = tile * PT_TM;
           const int b = (int)(m0 / p.N), n0 = (int)(m0 % p.N);
           tma_load_2d(dst, &tm_x, n0, b * PT_C, &full[s]);           // [64 ch][128 tokens] fp32
         } else if (p.x_format == OCRL_X_TOKENS_BF16) {
           tma_load_2d(dst, &tm_x, 0, (int)(tile * PT_TM), &full[s]);  // [128 tokens][64] bf16, swizzled
+          if (p.pos_tiles)  // the matching rows of the bf16 position table ride in the unused half of the stage
+            tma_load_2d(dst + X_BYTES / 2, &tm_pos, 0, (int)((tile * PT_TM) % p.N), &full[s]);
         } else {
           tma_load_2d(dst, &tm_x, 0, (int)(tile * PT_TM), &full[s]);  // cols 0-31, 128 rows, swizzled
           tma_load_2d(dst + X_BYTES / 2, &tm_x, 32, (int)(tile * PT_TM), &full[s]);
@@ -341,6 +344,15 @@ kv_proj_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             x[8 * c + 2 * i] = __uint_as_float(w4[i] << 16);
             x[8 * c + 2 * i + 1] = __uint_as_float(w4[i] & 0xffff0000u);
           }
+          if (p.pos_tiles) {
+            const uint4 q = *reinterpret_cast<const uint4*>(xs + X_BYTES / 2 + row * 128 + ((c ^ (row & 7)) << 4));
+            const uint32_t q4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              x[8 * c + 2 * i] += __uint_as_float(q4[i] << 16);
+              x[8 * c + 2 * i + 1] += __uint_as_float(q4[i] & 0xffff0000u);
+            }
+          }
         }
       } else {
 #pragma unroll
@@ -353,7 +365,7 @@ kv_proj_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           }
       }
       mbar_arrive(&empty[s]);
-      if (p.pos != nullptr) {  // position table [64][N]: coalesced across the 128 row threads
+      if (p.pos != nullptr && !p.pos_tiles) {  // position table [64][N]: coalesced across the 128 row threads
         const int n = (int)((tile * PT_TM + row) % p.N);
 #pragma unroll
         for (int c = 0; c < PT_C; ++c) x[c] += __ldg(p.pos + (size_t)c * p.N + n);
@@ -446,8 +458,18 @@ kv_proj_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 // fp32 weights -> bf16 copies in the layout the tensor maps describe ([rows][64], k rows pre-scaled by D^-1/2)
 __global__ void proj_tc_prep_kernel(const float* __restrict__ w1, const float* __restrict__ w2,
                                     const float* __restrict__ wk, const float* __restrict__ wv, __nv_bfloat16* w1b,
-                                    __nv_bfloat16* w2b, __nv_bfloat16* wkvb, int D, float kscale) {
+                                    __nv_bfloat16* w2b, __nv_bfloat16* wkvb, int D, float kscale,
+                                    const float* __restrict__ pos, __nv_bfloat16* posb, int N) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (posb != nullptr)  // position table [64][N] fp32 -> token-major bf16 [N][64]: coalesced reads, 16-byte writes
+    for (int j = i; j < 8 * N; j += gridDim.x * blockDim.x) {
+      const int n = j % N, c8 = j / N;
+      uint32_t q[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        q[e] = pack_bf16x2(__ldg(pos + (size_t)(8 * c8 + 2 * e) * N + n), __ldg(pos + (size_t)(8 * c8 + 2 * e + 1) * N + n));
+      *reinterpret_cast<uint4*>(posb + (size_t)n * 64 + 8 * c8) = make_uint4(q[0], q[1], q[2], q[3]);
+    }
   if (i < 64 * 64) {
     if (w1 != nullptr) { w1b[i] = __float2bfloat16_rn(w1[i]); w2b[i] = __float2bfloat16_rn(w2[i]); }
   }
@@ -490,7 +512,7 @@ static bool make_map(CUtensorMap* tm, CUtensorMapDataType dt, int esz, const voi
 }
 
 size_t kv_proj_tc_workspace(const ocrl_sa_dims* d) {
-  return sizeof(__nv_bfloat16) * ((size_t)2 * 64 * 64 + (size_t)2 * d->D * 64) + 256 + 1024;  // + trace slots
+  return sizeof(__nv_bfloat16) * ((size_t)2 * 64 * 64 + (size_t)2 * d->D * 64 + (size_t)d->N * 64) + 256 + 1024;  // + bf16 position table, trace slots
 }
 
 // returns OCRL_E_SHAPE when this shape has to take the FFMA kernel instead
@@ -505,11 +527,16 @@ int kv_proj_tc_launch(const ocrl_sa_dims* d, const void* x, const float* pos, co
   __nv_bfloat16* w2b = w1b + 64 * 64;
   __nv_bfloat16* wkvb = w2b + 64 * 64;
   const bool has_mlp = w->mlp_w1 != nullptr;
-  proj_tc_prep_kernel<<<(D * 64 + 255) / 256, 256, 0, stream>>>(w->mlp_w1, w->mlp_w2, w->wk, w->wv, w1b, w2b, wkvb, D,
-                                                                 1.0f / sqrtf((float)D));
+  // bf16 tokens with a position table whose tiles never straddle two images: the table goes through TMA as well
+  const bool pos_tiles = (d->x_format == OCRL_X_TOKENS_BF16 && pos != nullptr && d->N % PT_TM == 0);
+  __nv_bfloat16* posb = wkvb + (size_t)2 * D * 64;
+  const int prep_threads = (pos_tiles && 8 * d->N > D * 64) ? 8 * d->N : D * 64;
+  proj_tc_prep_kernel<<<(prep_threads + 255) / 256, 256, 0, stream>>>(w->mlp_w1, w->mlp_w2, w->wk, w->wv, w1b, w2b, wkvb, D,
+                                                                 1.0f / sqrtf((float)D), pos, pos_tiles ? posb : nullptr,
+                                                                 d->N);
   OCRL_CHECK_CUDA(cudaGetLastError());
 
-  CUtensorMap tm_x, tm_w1, tm_w2, tm_wkv, tm_k, tm_v;
+  CUtensorMap tm_x, tm_w1, tm_w2, tm_wkv, tm_k, tm_v, tm_pos;
   bool ok = true;
   if (d->x_format == OCRL_X_NCHW_F32)  // NCHW feature map viewed as [B*64][N]; box = 128 tokens x 64 channels
     ok &= make_map(&tm_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, (uint64_t)d->N, (uint64_t)d->B * PT_C,
@@ -528,6 +555,11 @@ int kv_proj_tc_launch(const ocrl_sa_dims* d, const void* x, const float* pos, co
                  CU_TENSOR_MAP_SWIZZLE_128B);
   ok &= make_map(&tm_v, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, v_out, (uint64_t)D, (uint64_t)M, (uint64_t)D * 2, 64, PT_TM,
                  CU_TENSOR_MAP_SWIZZLE_128B);
+  if (pos_tiles)
+    ok &= make_map(&tm_pos, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, posb, PT_C, (uint64_t)d->N, PT_C * 2, PT_C, PT_TM,
+                   CU_TENSOR_MAP_SWIZZLE_128B);
+  else
+    tm_pos = tm_x;  // unused
   if (!ok) {
     set_error("kv_proj(tensor): cuTensorMapEncodeTiled failed");
     return OCRL_E_LAUNCH;
@@ -536,6 +568,7 @@ int kv_proj_tc_launch(const ocrl_sa_dims* d, const void* x, const float* pos, co
   p.enc_ln_w = w->enc_ln_w; p.enc_ln_b = w->enc_ln_b; p.b1 = w->mlp_b1; p.b2 = w->mlp_b2;
   p.in_ln_w = w->in_ln_w; p.in_ln_b = w->in_ln_b; p.pos = pos; p.y_out = y_out;
   p.trace = nullptr;
+  p.pos_tiles = pos_tiles ? 1 : 0;
   if (getenv("OCRL_SA_TRACE") != nullptr)
     p.trace = reinterpret_cast<long long*>(reinterpret_cast<unsigned char*>(workspace) + kv_proj_tc_workspace(d) - 1024);
   p.has_mlp = has_mlp ? 1 : 0; p.x_format = d->x_format; p.N = d->N; p.D = D; p.M = M;
@@ -551,7 +584,7 @@ int kv_proj_tc_launch(const ocrl_sa_dims* d, const void* x, const float* pos, co
   do {                                                                                                           \
     OCRL_CHECK_CUDA(cudaFuncSetAttribute(kv_proj_tc_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                          (int)smem));                                                            \
-    kv_proj_tc_kernel<DD><<<grid, PT_NT, smem, stream>>>(tm_x, tm_w1, tm_w2, tm_wkv, tm_k, tm_v, p);              \
+    kv_proj_tc_kernel<DD><<<grid, PT_NT, smem, stream>>>(tm_x, tm_w1, tm_w2, tm_wkv, tm_k, tm_v, tm_pos, p);              \
   } while (0)
   if (D == 64) OCRL_LAUNCH_PT(64);
   else if (D == 128) OCRL_LAUNCH_PT(128);

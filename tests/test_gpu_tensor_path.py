@@ -55,6 +55,26 @@ def test_tcgen05_feature_map_ingest(S):
     assert rel_err(k.float().cpu(), k_ref) < 1e-2 and rel_err(v.float().cpu(), v_ref) < 1e-2
 
 
+@pytest.mark.parametrize("B,H,W", [(3, 16, 16), (2, 32, 64), (5, 8, 16), (3, 12, 12), (2, 10, 16)])
+def test_tcgen05_bf16_channels_last_ingest(B, H, W):
+    """bf16 channels-last feature map (the conv stack's output) + position table.  When H*W is a multiple
+    of the 128-token tile the table rides through TMA as bf16 tiles, otherwise it is read per row."""
+    from ocrl_b200 import functional as F
+
+    p, enc = so.random_sa_params(6, 64, 192, 192, seed=5), _enc(7)
+    g = torch.Generator().manual_seed(H * 100 + W)
+    fmap = torch.randn(B, 64, H, W, generator=g).bfloat16()
+    pos = torch.randn(64, H * W, generator=g)
+    tok = (fmap.float().flatten(2) + pos.unsqueeze(0)).permute(0, 2, 1).contiguous()
+    k_ref, v_ref = so.kv_project(so.token_mlp(tok, enc), p)
+    fm = fmap.cuda().contiguous(memory_format=torch.channels_last)
+    k, v, _ = F.kv_project(fm, _cuda(p), kv="bf16", enc=_cuda(enc), pos_table=pos.cuda())
+    assert rel_err(k.float().cpu(), k_ref) < 1e-2 and rel_err(v.float().cpu(), v_ref) < 1e-2
+    k2, v2, _ = F.kv_project(fm, _cuda(p), kv="bf16", enc=_cuda(enc))
+    k_ref, v_ref = so.kv_project(so.token_mlp(tok - pos.t().unsqueeze(0), enc), p)
+    assert rel_err(k2.float().cpu(), k_ref) < 1e-2 and rel_err(v2.float().cpu(), v_ref) < 1e-2
+
+
 def test_tensor_core_iteration_kernel_on_exact_bf16_inputs():
     """The mma.sync loop fed with bf16-rounded k, v: compared with the oracle run on the same rounded
     values, so only the kernel's own arithmetic (bf16 q / weights, fp32 accumulate) is measured."""
