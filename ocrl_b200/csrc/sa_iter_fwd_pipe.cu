@@ -255,6 +255,24 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
   };
 
   // ------------------------------------------------------------------ one-time setup
+  // The slots of lane 0's first image are fetched now and written to shared memory at the end of the setup: their global
+  // round trip hides under the weight load instead of standing in front of the first query
+  constexpr int PRE2 = (8 * (D / 2) + 255) / 256, PRE1 = (8 * DS + 255) / 256;
+  float2 pre2[PRE2];
+  float pre1[PRE1];
+  if (tid >= 256 && nops[0] > 0) {
+    const float* src = a.slots0 + (size_t)image_of(0, 0) * K * D;
+#pragma unroll
+    for (int u = 0; u < PRE2; ++u) {
+      const int i = tid - 256 + 256 * u;
+      if (i < K * (D / 2)) pre2[u] = __ldg(reinterpret_cast<const float2*>(src + (i / (D / 2)) * D + 2 * (i % (D / 2))));
+    }
+#pragma unroll
+    for (int u = 0; u < PRE1; ++u) {
+      const int i = tid - 256 + 256 * u;
+      if (i < K * DS) pre1[u] = __ldg(src + (i / DS) * D + rank * DS + i % DS);
+    }
+  }
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(&full[s], 1);
@@ -345,6 +363,20 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
     for (int i = tid; i < (NL * C::LANE_BYTES) / 4; i += C::NT) reinterpret_cast<uint32_t*>(sm + C::OFF_LANE)[i] = 0u;
   }
   __syncthreads();
+  if (tid >= 256 && nops[0] > 0) {  // after the zero fill of the lane buffers; the cluster barrier below publishes it
+    unsigned char* dst = slh_hi(0);
+    float* own = own_of(0);
+#pragma unroll
+    for (int u = 0; u < PRE2; ++u) {
+      const int i = tid - 256 + 256 * u;
+      if (i < K * (D / 2)) *reinterpret_cast<uint32_t*>(dst + (i / (D / 2)) * PITCH + 4 * (i % (D / 2))) = pack_bf16x2(pre2[u].x, pre2[u].y);
+    }
+#pragma unroll
+    for (int u = 0; u < PRE1; ++u) {
+      const int i = tid - 256 + 256 * u;
+      if (i < K * DS) own[i] = pre1[u];
+    }
+  }
   cluster.sync();  // every CTA's barriers are initialised before any peer signals them
   if (tid == 0) PP_TRACE(0);
 
@@ -639,7 +671,7 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
     // initial queries of both lanes
     for (int l = 0; l < NL; ++l)
       if (nops[l] > 0) {
-        load_slots0(l, image_of(l, 0));
+        if (l > 0) load_slots0(l, image_of(l, 0));  // lane 0's were staged during the setup
         q_phase(l, image_of(l, 0), 0);
       }
 
