@@ -287,11 +287,14 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
     mbar_fence_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_k) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_v) : "memory");
-    // first tiles: their HBM latency overlaps the weight load below
-    if (TP > 0)
-      for (int p = 0; p < S; ++p)
+  }
+  // first tiles: their HBM latency overlaps the weight load below.  A tile costs its issuing lane several hundred
+  // cycles, so the pass warps issue one (or two) each, behind a barrier of their own that publishes the mbarrier init
+  if (warp < 8) {
+    asm volatile("bar.sync 3, 256;" ::: "memory");
+    if (lane == 0 && TP > 0)
+      for (int p = warp; p < S; p += 8)
         if (p / TP < total_ops) issue_tile(p / TP, p % TP);
-
   }
   {
     // the CTA's weight slices, fp32 global -> bf16 shared; eight independent 16-byte loads in flight per thread
