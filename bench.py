@@ -236,11 +236,11 @@ def measure(a, mode, steps, warmup, dev, dist, rank, world, pool_host, pool_dev,
         def step_single(i):
             graphed(batch_dev(i))
 
-        # the public streaming API: two batches in flight (two graph buffers replaying on their own streams, so the
+        # the public streaming API: three batches in flight (three graph buffers replaying on their own streams, so the
         # latency-bound iteration kernel of one batch shares the GPU with the convolutions of the next).
         # value: frames already resident in HBM, slots left in HBM.  e2e: every step copies its frames from pinned host
         # memory and its slots back to pinned host memory, copies overlapping the replays.
-        nbuf = int(os.environ.get("OCRL_BENCH_BUFFERS", 2))
+        nbuf = int(os.environ.get("OCRL_BENCH_BUFFERS", 3))
         streamed = ocrl_b200.StreamedEncoder(model, batch_dev(0), buffers=nbuf)
         outs_host = [torch.empty_like(out_host).pin_memory() for _ in range(nbuf)]
         outs_dev = [torch.empty(a.batch, a.slots, a.slot_size, device=dev) for _ in range(nbuf)]
@@ -416,10 +416,10 @@ def main():
                 "config": dict(workload(a), l2="k/v working set per step %.0f MB > 126 MB L2; frame pool of %d rotates"
                                % (a.batch * 2 * N * D * esz / 1e6, a.pool),
                                cnn="cuDNN via torch (library call, fused bias+ReLU in bf16 mode); token stage + iteration loop hand-written CUDA",
-                               launch=("CUDA graph replays of SLATE.__call__, two batches in flight on two streams "
+                               launch=("CUDA graph replays of SLATE.__call__, three batches in flight on three streams "
                                        "(single_stream_value: one replay at a time)") if main_res["graph"] else "eager launches",
                                e2e="ocrl_b200.StreamedEncoder: per step H2D from pinned frames, graph replay, D2H to pinned "
-                                   "slots; copies of neighbouring steps overlap the replay (two buffers)"),
+                                   "slots; copies of neighbouring steps overlap the replays (three buffers)"),
                 "clocks": clk,
                 "e2e": {"value": main_res["e2e_value"], "unit": UNIT, "ms_per_step": main_res["e2e_ms_per_step"],
                         "h2d_bytes_per_step": a.batch * 3 * a.size * a.size * 4,

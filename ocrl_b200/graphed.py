@@ -42,9 +42,9 @@ class GraphedEncoder:
 
 
 class StreamedEncoder:
-    """Host-to-host slot encoding at the GPU's pace: two ``GraphedEncoder`` buffers in ping-pong, the pinned-host ->
-    device copy of batch i+1 and the device -> pinned-host copy of result i-1 run on copy streams while the graph of
-    batch i replays (dataset encoding / PPO rollout feeding, utils/datasets.py + sb3s/ocr_extractor.py:45 use case).
+    """Host-to-host slot encoding at the GPU's pace: ``buffers`` (default three) ``GraphedEncoder`` buffers in
+    rotation, the pinned-host -> device copy of batch i+1 and the device -> pinned-host copy of result i-1 run on copy
+    streams while the graph of batch i replays (dataset encoding / PPO rollout feeding, utils/datasets.py + sb3s/ocr_extractor.py:45 use case).
 
         enc = StreamedEncoder(ocr, example_obs_dev)
         for i, frames in enumerate(pinned_batches):
@@ -54,11 +54,11 @@ class StreamedEncoder:
     Every submit performs its own H2D and D2H copy; nothing is cached between batches."""
 
     def __init__(self, ocr, example_obs: torch.Tensor, with_masks: bool = False, concurrent_replays: bool = True,
-                 buffers: int = 2):
+                 buffers: int = 3):
         dev = example_obs.device
         self._nb = buffers
         self._enc = [GraphedEncoder(ocr, example_obs, with_masks) for _ in range(buffers)]
-        # with concurrent_replays the two buffers replay on their own streams, so the latency-bound iteration kernel of
+        # with concurrent_replays the buffers replay on their own streams, so the latency-bound iteration kernel of
         # one batch (13 clusters of 8 SMs) shares the GPU with the convolutions of the next
         self._compute = [torch.cuda.Stream(device=dev) for _ in range(buffers)] if concurrent_replays else None
         self._in = torch.cuda.Stream(device=dev)
