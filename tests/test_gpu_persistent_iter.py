@@ -145,6 +145,28 @@ def test_small_slot_attention_configuration(B, N, K, T):
     assert torch.allclose(a.sum(-1), torch.ones(B, N), atol=1e-4)
 
 
+def test_small_configuration_cluster_sizes_agree(monkeypatch):
+    """D = 64: batches of 48 and more run on clusters of four (two lanes), smaller ones on clusters of eight.  Same
+    arithmetic, different split: outputs and the saved training state agree to summation order."""
+    from ocrl_b200 import functional as F
+
+    B, N, K, T = 48, 1024, 6, 7
+    p = _cuda(so.random_sa_params(K, 64, 64, 128, seed=5))
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(B, N, 64, generator=gen)
+    s0 = torch.randn(B, K, 64, generator=gen).cuda()
+    k_ref, v_ref = so.kv_project(x, {k_: v_.cpu() for k_, v_ in p.items()})
+    kb, vb = k_ref.bfloat16().cuda(), v_ref.bfloat16().cuda()
+    monkeypatch.setenv("OCRL_SA_PIPE", "0")   # B >= 48: clusters of four
+    s4, a4, saved4 = F.iterate(kb, vb, s0, p, T, save=True)
+    monkeypatch.setenv("OCRL_SA_PIPE", "1")   # clusters of eight
+    s8, a8, saved8 = F.iterate(kb, vb, s0, p, T, save=True)
+    torch.cuda.synchronize()
+    assert rel_err(s4.cpu(), s8.cpu()) < 2e-3 and rel_err(a4.cpu(), a8.cpu()) < 2e-3
+    used = 8 * K * 64 + K * 128 + K
+    assert rel_err(saved4.view(B, T, -1)[..., :used].cpu(), saved8.view(B, T, -1)[..., :used].cpu()) < 2e-3
+
+
 def test_small_configuration_golden_case():
     meta, g = load_case("sa_small_grad")
     k_ref, v_ref = so.kv_project(g["in"]["inputs"], g["p"])
