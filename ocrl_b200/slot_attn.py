@@ -122,7 +122,8 @@ class SlotAttentionEncoder(nn.Module):
 
     def init_slots(self, batch, like):
         # same draw as the reference (slot_attn.py:155): torch's generator on the tensor's device
-        noise = like.new_empty(batch, self.num_slots, self.slot_size).normal_()
+        # (always in the parameters' dtype: a bf16 feature map must not turn the draw into a bf16 one)
+        noise = torch.empty(batch, self.num_slots, self.slot_size, device=like.device, dtype=self.slot_mu.dtype).normal_()
         if torch.is_grad_enabled() and (self.slot_mu.requires_grad or self.slot_log_sigma.requires_grad):
             return self.slot_mu + torch.exp(self.slot_log_sigma) * noise
         # inference: sigma cached until the parameter changes, one fused multiply-add (same values)
@@ -131,7 +132,7 @@ class SlotAttentionEncoder(nn.Module):
         if cached is None or cached[0] != key:
             cached = (key, torch.exp(self.slot_log_sigma.detach()))
             self.__dict__["_sigma_cache"] = cached
-        return torch.addcmul(self.slot_mu.detach(), cached[1], noise.to(self.slot_mu.dtype))
+        return torch.addcmul(self.slot_mu.detach(), cached[1], noise)
 
     def forward(self, x, *, _pos_table=None):
         """x [B,N,C] (or the NCHW feature map when ``_pos_table`` is given) -> (slots, attn)."""
