@@ -241,7 +241,8 @@ def measure(a, mode, steps, warmup, dev, dist, rank, world, pool_host, pool_dev,
         # value: frames already resident in HBM, slots left in HBM.  e2e: every step copies its frames from pinned host
         # memory and its slots back to pinned host memory, copies overlapping the replays.
         nbuf = int(os.environ.get("OCRL_BENCH_BUFFERS", 3))
-        streamed = ocrl_b200.StreamedEncoder(model, batch_dev(0), buffers=nbuf)
+        icl = os.environ.get("OCRL_BENCH_ITER_CLUSTERS")  # experiment knob; the bench line is the default (None)
+        streamed = ocrl_b200.StreamedEncoder(model, batch_dev(0), buffers=nbuf, iter_clusters=int(icl) if icl else None)
         outs_host = [torch.empty_like(out_host).pin_memory() for _ in range(nbuf)]
         outs_dev = [torch.empty(a.batch, a.slots, a.slot_size, device=dev) for _ in range(nbuf)]
 

@@ -8,11 +8,35 @@ replays it: same kernels, same results, one launch.
 """
 from __future__ import annotations
 
+import contextlib
+import os
+
 import torch
 
 
+@contextlib.contextmanager
+def _iteration_cluster_cap(n):
+    """Caps the cluster count of the iteration kernel for the launches made inside the block (the launcher reads
+    ``OCRL_SA_PC_CLUSTERS`` when it sizes the grid; a captured graph keeps the grid it was captured with)."""
+    if n is None:
+        yield
+        return
+    old = os.environ.get("OCRL_SA_PC_CLUSTERS")
+    os.environ["OCRL_SA_PC_CLUSTERS"] = str(int(n))
+    try:
+        yield
+    finally:
+        if old is None:
+            os.environ.pop("OCRL_SA_PC_CLUSTERS", None)
+        else:
+            os.environ["OCRL_SA_PC_CLUSTERS"] = old
+
+
 class GraphedEncoder:
-    def __init__(self, ocr, example_obs: torch.Tensor, with_masks: bool = False, warmup: int = 3):
+    def __init__(self, ocr, example_obs: torch.Tensor, with_masks: bool = False, warmup: int = 3,
+                 iter_clusters: int | None = None):
+        """iter_clusters: upper bound on the clusters of the iteration kernel in the captured graph (None: the
+        launcher's own choice, lowest latency of one replay)."""
         assert example_obs.is_cuda, "GraphedEncoder captures a CUDA graph"
         self._ocr = ocr
         self._with_masks = with_masks
@@ -25,7 +49,7 @@ class GraphedEncoder:
         torch.cuda.current_stream(example_obs.device).wait_stream(side)
         torch.cuda.synchronize(example_obs.device)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph), torch.no_grad():
+        with _iteration_cluster_cap(iter_clusters), torch.cuda.graph(self.graph), torch.no_grad():
             self.static_out = self._call()
 
     def _call(self):
@@ -51,13 +75,20 @@ class StreamedEncoder:
             enc.submit(frames, out_pinned[i])      # asynchronous
         enc.synchronize()                          # every out_pinned[i] is valid
 
-    Every submit performs its own H2D and D2H copy; nothing is cached between batches."""
+    Every submit performs its own H2D and D2H copy; nothing is cached between batches.
+
+    iter_clusters: clusters of the iteration kernel per replay.  The kernel is latency-bound, so with several replays
+    in flight fewer, fuller clusters cost fewer SM-seconds and leave SMs to the neighbours' convolutions: at batch 64
+    eight clusters (8 images each, no tail) give 177.5 k images/s against 169.0 k with the launcher's thirteen, while
+    one replay alone gets 11 % slower and the kernel's own launch goes from 134 to 189 us (profiles/r1/ab_clusters_v9.txt).
+    None (default): the launcher's choice, lowest latency per replay; an integer caps at that count."""
 
     def __init__(self, ocr, example_obs: torch.Tensor, with_masks: bool = False, concurrent_replays: bool = True,
-                 buffers: int = 3):
+                 buffers: int = 3, iter_clusters: int | None = None):
         dev = example_obs.device
         self._nb = buffers
-        self._enc = [GraphedEncoder(ocr, example_obs, with_masks) for _ in range(buffers)]
+        self.iter_clusters = iter_clusters
+        self._enc = [GraphedEncoder(ocr, example_obs, with_masks, iter_clusters=iter_clusters) for _ in range(buffers)]
         # with concurrent_replays the buffers replay on their own streams, so the latency-bound iteration kernel of
         # one batch (13 clusters of 8 SMs) shares the GPU with the convolutions of the next
         self._compute = [torch.cuda.Stream(device=dev) for _ in range(buffers)] if concurrent_replays else None

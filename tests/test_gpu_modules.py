@@ -1,5 +1,7 @@
 """GPU parity of the drop-in modules (SLATE / SLATE_Module / SlotAttentionEncoder / SlotAttention)
 against the frozen reference outputs."""
+import os
+
 import pytest
 import torch
 
@@ -126,7 +128,8 @@ def test_bf16_mode_with_tensor_core_convs(monkeypatch, conv):
     assert es < 2e-2 and em < 2e-2
 
 
-def test_streamed_encoder_matches_direct_calls():
+@pytest.mark.parametrize("iter_clusters", [None, 2])
+def test_streamed_encoder_matches_direct_calls(iter_clusters):
     """StreamedEncoder (double-buffered H2D / graph replay / D2H) returns, batch by batch, what the model returns for
     the same frames and the same slot-initialisation noise."""
     meta, g = load_case("slate_encode_64")
@@ -139,7 +142,9 @@ def test_streamed_encoder_matches_direct_calls():
     batches = [obs, obs.flip(0), obs.roll(1, 0), obs]
     with torch.no_grad():
         want = [model(b.cuda()).cpu() for b in batches]
-    enc = ocrl_b200.StreamedEncoder(model, obs.cuda())
+    before = os.environ.get("OCRL_SA_PC_CLUSTERS")
+    enc = ocrl_b200.StreamedEncoder(model, obs.cuda(), iter_clusters=iter_clusters)  # cap changes the grid, not the result
+    assert os.environ.get("OCRL_SA_PC_CLUSTERS") == before
     pinned = [b.contiguous().pin_memory() for b in batches]
     outs = [torch.empty_like(want[0]).pin_memory() for _ in batches]
     for b, o in zip(pinned, outs):
