@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define OCRL_ABI_VERSION 3
+#define OCRL_ABI_VERSION 4
 
 enum {
   OCRL_OK = 0,
@@ -138,6 +138,32 @@ int ocrl_kv_proj_bwd(const ocrl_sa_dims* dims, const float* x, const ocrl_token_
 int ocrl_sa_iter_fwd(const ocrl_sa_dims* dims, const void* k, const void* v, const float* slots0,
                      const ocrl_sa_weights* w, float* slots_out, float* attn_vis_out,
                      void* saved, void* workspace, void* stream);
+
+/* Launch options of the forward loop (everything that used to be a process-global setting).  A zeroed struct, or a
+ * NULL pointer, is the default: the fastest kernel that covers the shape, its own grid size.
+ *   variant       which implementation to run (OCRL_SA_AUTO picks in the order TCGEN05, PIPE, CLUSTER_TC, FFMA for bf16 k/v
+ *                 with math_mode TENSOR; fp32 k/v always run FFMA)
+ *   max_clusters  > 0: upper bound on the resident clusters of the persistent kernels (TCGEN05, PIPE) -- a latency-bound
+ *                 launch on fewer, fuller clusters leaves SMs to concurrent streams; results do not depend on it
+ *   lanes         images in flight per cluster of the persistent kernels: 0 = default, 2 or 3
+ *   strict        != 0: return OCRL_E_SHAPE when `variant` (or, with OCRL_SA_AUTO, the tcgen05 kernel) does not cover the
+ *                 shape instead of running a slower kernel
+ *   trace         != 0: the kernel writes clock64() phase stamps of CTA 0 to the last 4 KB of `workspace` (development aid)
+ */
+enum { OCRL_SA_AUTO = 0, OCRL_SA_TCGEN05 = 1, OCRL_SA_PIPE = 2, OCRL_SA_CLUSTER_TC = 3, OCRL_SA_FFMA = 4 };
+typedef struct ocrl_sa_launch_opts {
+  int32_t variant;
+  int32_t max_clusters;
+  int32_t lanes;
+  int32_t strict;
+  int32_t trace;
+} ocrl_sa_launch_opts;
+int ocrl_sa_iter_fwd_ex(const ocrl_sa_dims* dims, const void* k, const void* v, const float* slots0,
+                        const ocrl_sa_weights* w, float* slots_out, float* attn_vis_out,
+                        void* saved, void* workspace, const ocrl_sa_launch_opts* opts, void* stream);
+/* Name of the kernel the last ocrl_sa_iter_fwd / _ex call of this thread launched ("" before the first call):
+ * "tcgen05", "pipe", "cluster_tc" or "ffma". */
+const char* ocrl_sa_last_kernel(void);
 
 /* The fused backward of the loop; attention logits are recomputed from k and the saved
  * per-iteration slots rather than stored (autograd of slot_attn.py:64-102).

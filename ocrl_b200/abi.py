@@ -21,9 +21,13 @@ X_TOKENS_F32, X_NCHW_F32, X_TOKENS_BF16 = 0, 1, 2
 EXPORTS = [
     "ocrl_version", "ocrl_built_arch", "ocrl_last_error", "ocrl_sa_query_workspace",
     "ocrl_kv_proj_fwd_workspace", "ocrl_kv_proj_fwd", "ocrl_kv_proj_bwd_workspace", "ocrl_kv_proj_bwd",
-    "ocrl_sa_iter_fwd", "ocrl_sa_iter_bwd", "ocrl_conv_bias_relu_bf16", "ocrl_frames_to_nhwc_bf16",
-    "ocrl_conv_first_relu_bf16",
+    "ocrl_sa_iter_fwd", "ocrl_sa_iter_fwd_ex", "ocrl_sa_last_kernel", "ocrl_sa_iter_bwd",
+    "ocrl_conv_bias_relu_bf16", "ocrl_frames_to_nhwc_bf16", "ocrl_conv_first_relu_bf16",
 ]
+
+# ocrl_sa_launch_opts.variant
+SA_AUTO, SA_TCGEN05, SA_PIPE, SA_CLUSTER_TC, SA_FFMA = 0, 1, 2, 3, 4
+SA_VARIANTS = {"auto": SA_AUTO, "tcgen05": SA_TCGEN05, "pipe": SA_PIPE, "cluster_tc": SA_CLUSTER_TC, "ffma": SA_FFMA}
 
 
 class SaDims(Structure):
@@ -39,6 +43,18 @@ _TOK_W = ["enc_ln_w", "enc_ln_b", "mlp_w1", "mlp_b1", "mlp_w2", "mlp_b2", "in_ln
 
 class SaWeights(Structure):
     _fields_ = [(n, c_void_p) for n in _SA_W]
+
+
+class LaunchOpts(Structure):
+    """ocrl_sa_launch_opts (include/ocrl_sa.h): per-call kernel selection of the iteration loop."""
+    _fields_ = [("variant", c_int32), ("max_clusters", c_int32), ("lanes", c_int32), ("strict", c_int32),
+                ("trace", c_int32)]
+
+
+def launch_opts(variant="auto", max_clusters=0, lanes=0, strict=False, trace=False) -> LaunchOpts:
+    if isinstance(variant, str):
+        variant = SA_VARIANTS[variant]
+    return LaunchOpts(int(variant), int(max_clusters or 0), int(lanes or 0), int(bool(strict)), int(bool(trace)))
 
 
 class SaWeightGrads(Structure):
@@ -74,6 +90,9 @@ def lib() -> ctypes.CDLL:
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
         L.ocrl_sa_iter_fwd.argtypes = [POINTER(SaDims), c_void_p, c_void_p, c_void_p, POINTER(SaWeights), c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p]
+        L.ocrl_sa_iter_fwd_ex.argtypes = [POINTER(SaDims), c_void_p, c_void_p, c_void_p, POINTER(SaWeights), c_void_p,
+                                          c_void_p, c_void_p, c_void_p, POINTER(LaunchOpts), c_void_p]
+        L.ocrl_sa_last_kernel.restype = c_char_p
         L.ocrl_sa_iter_bwd.argtypes = [POINTER(SaDims), c_void_p, c_void_p, c_void_p, POINTER(SaWeights), c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p, POINTER(SaWeightGrads), c_void_p,
                                        c_void_p]
@@ -83,7 +102,7 @@ def lib() -> ctypes.CDLL:
                                                 c_int, c_void_p]
         L.ocrl_conv_first_relu_bf16.restype = c_int
         for name in ("ocrl_sa_query_workspace", "ocrl_kv_proj_fwd", "ocrl_kv_proj_bwd", "ocrl_sa_iter_fwd",
-                     "ocrl_sa_iter_bwd", "ocrl_conv_bias_relu_bf16", "ocrl_frames_to_nhwc_bf16"):
+                     "ocrl_sa_iter_fwd_ex", "ocrl_sa_iter_bwd", "ocrl_conv_bias_relu_bf16", "ocrl_frames_to_nhwc_bf16"):
             getattr(L, name).restype = c_int
         _lib = L
     return _lib

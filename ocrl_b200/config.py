@@ -27,12 +27,13 @@ def load_yaml(path, **overrides):
 
 
 def slate_config(num_slots=6, num_iterations=3, slot_size=192, mlp_hidden_size=192, use_bcdec=False,
-                 use_cnn_feat=False, obs_size=64, obs_channels=3):
+                 use_cnn_feat=False, obs_size=64, obs_channels=3, kv_dtype=None):
     ocr = to_namespace(dict(
         name="SLATE", tau_start=1.0, tau_final=0.1, tau_steps=30000, hard=False, use_cnn_feat=use_cnn_feat,
         use_bcdec=use_bcdec, dvae=dict(vocab_size=4096, d_model=192), cnn=dict(hidden_size=64),
         slotattr=dict(num_iterations=num_iterations, num_slots=num_slots, num_slot_heads=1, slot_size=slot_size,
-                      mlp_hidden_size=mlp_hidden_size, pos_channels=4),
+                      mlp_hidden_size=mlp_hidden_size, pos_channels=4,
+                      **({} if kv_dtype is None else {"kv_dtype": kv_dtype})),
         tfdec=dict(num_dec_blocks=4, num_dec_heads=4),
         learning=dict(lr_half_life=250000, lr_dvae=3e-4, lr_enc=1e-4, lr_dec=3e-4, lr_warmup_steps=30000,
                       dropout=0.1, clip=0.05)))

@@ -20,7 +20,8 @@ int token_stage_launch(const ocrl_sa_dims* d, const void* x, const float* pos, c
                        float* y_out, void* k_out, void* v_out, cudaStream_t stream);
 int sa_iter_fwd_launch(const ocrl_sa_dims* d, const void* k, const void* v, const float* slots0,
                        const ocrl_sa_weights* w, float* slots_out, float* attn_out, float* saved,
-                       void* workspace, cudaStream_t stream);
+                       void* workspace, const ocrl_sa_launch_opts* opts, cudaStream_t stream);
+const char* sa_iter_last_kernel();
 int sa_iter_bwd_launch(const ocrl_sa_dims* d, const void* k, const void* v, const float* saved,
                        const ocrl_sa_weights* w, const float* d_slots, const float* d_attn, float* dk, float* dv,
                        float* d_slots0, const ocrl_sa_weight_grads* dw, void* ws, cudaStream_t stream);
@@ -37,17 +38,10 @@ int kv_proj_tc_launch(const ocrl_sa_dims* d, const void* x, const float* pos, co
 // Cluster size = CTAs per image.  Needs D % CL == 0 and H % CL == 0 (each CTA owns D/CL slot
 // features in the GRU/MLP) and enough tokens per CTA to keep 8 warps busy.
 int sa_iter_pick_cluster(const ocrl_sa_dims* d) {
-  int forced = 0;
-  if (const char* e = getenv("OCRL_SA_CLUSTER")) forced = atoi(e);
-  const int cands[5] = {16, 8, 4, 2, 1};
-  for (int i = 0; i < 5; ++i) {
+  const int cands[4] = {8, 4, 2, 1};
+  for (int i = 0; i < 4; ++i) {
     const int cl = cands[i];
     if (d->D % cl || d->H_mlp % cl) continue;
-    if (forced) {
-      if (cl == forced) return cl;
-      continue;
-    }
-    if (cl == 16) continue;  // non-portable size only on request
     // measured on B200 (profiles/r1/sweep_cl.log): ~2048-4096 tokens per CTA is the sweet spot -- larger
     // clusters spend more time in the DSMEM exchanges of the slot update than they save in the token pass
     const int want = d->N >= 8192 ? 4 : (d->N >= 512 ? 2 : 1);
@@ -60,10 +54,6 @@ int sa_iter_pick_cluster(const ocrl_sa_dims* d) {
 // Warps per CTA of the iteration kernel: 4-warp CTAs let two clusters share every SM (the slot
 // update of one image overlaps the token pass of another); needs <= ~112 KB of shared memory per CTA.
 int sa_iter_pick_warps(int D, int KP, int CL) {
-  if (const char* e = getenv("OCRL_SA_WARPS")) {
-    const int w = atoi(e);
-    if (w == 4 || w == 8) return w;
-  }
   (void)D; (void)KP; (void)CL;
   return 8;
 }
@@ -174,9 +164,17 @@ int ocrl_kv_proj_bwd(const ocrl_sa_dims* d, const float* x, const ocrl_token_wei
   return kv_proj_bwd_launch(d, x, w, dk, dv, dx, d_ln_w, d_ln_b, dwk, dwv, ws, (cudaStream_t)stream);
 }
 
+const char* ocrl_sa_last_kernel(void) { return sa_iter_last_kernel(); }
+
 int ocrl_sa_iter_fwd(const ocrl_sa_dims* d, const void* k, const void* v, const float* slots0,
                      const ocrl_sa_weights* w, float* slots_out, float* attn_vis_out, void* saved, void* workspace,
                      void* stream) {
+  return ocrl_sa_iter_fwd_ex(d, k, v, slots0, w, slots_out, attn_vis_out, saved, workspace, nullptr, stream);
+}
+
+int ocrl_sa_iter_fwd_ex(const ocrl_sa_dims* d, const void* k, const void* v, const float* slots0,
+                        const ocrl_sa_weights* w, float* slots_out, float* attn_vis_out, void* saved, void* workspace,
+                        const ocrl_sa_launch_opts* opts, void* stream) {
   int rc = check_dims(d);
   if (rc) return rc;
   if ((rc = check_arch())) return rc;
@@ -190,8 +188,14 @@ int ocrl_sa_iter_fwd(const ocrl_sa_dims* d, const void* k, const void* v, const 
     return OCRL_E_ALIGN;
   }
   if (d->B == 0) return OCRL_OK;
+  if (opts && (opts->variant < OCRL_SA_AUTO || opts->variant > OCRL_SA_FFMA || opts->max_clusters < 0 ||
+               (opts->lanes != 0 && opts->lanes != 2 && opts->lanes != 3))) {
+    set_error("sa_iter_fwd: bad launch options (variant %d, max_clusters %d, lanes %d)", opts->variant, opts->max_clusters,
+              opts->lanes);
+    return OCRL_E_SHAPE;
+  }
   return sa_iter_fwd_launch(d, k, v, slots0, w, slots_out, attn_vis_out, reinterpret_cast<float*>(saved), workspace,
-                            (cudaStream_t)stream);
+                            opts, (cudaStream_t)stream);
 }
 
 int ocrl_sa_iter_bwd(const ocrl_sa_dims* d, const void* k, const void* v, const void* saved, const ocrl_sa_weights* w,

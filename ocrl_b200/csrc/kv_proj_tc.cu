@@ -569,8 +569,6 @@ int kv_proj_tc_launch(const ocrl_sa_dims* d, const void* x, const float* pos, co
   p.in_ln_w = w->in_ln_w; p.in_ln_b = w->in_ln_b; p.pos = pos; p.y_out = y_out;
   p.trace = nullptr;
   p.pos_tiles = pos_tiles ? 1 : 0;
-  if (getenv("OCRL_SA_TRACE") != nullptr)
-    p.trace = reinterpret_cast<long long*>(reinterpret_cast<unsigned char*>(workspace) + kv_proj_tc_workspace(d) - 1024);
   p.has_mlp = has_mlp ? 1 : 0; p.x_format = d->x_format; p.N = d->N; p.D = D; p.M = M;
   p.ntiles = (int)((M + PT_TM - 1) / PT_TM);
   p.ln_eps = d->ln_eps;

@@ -605,10 +605,9 @@ template <int D>
 static int tc_dispatch_k(const IterFwdArgs& a, cudaStream_t s) {
   // token-pass warps x tokens per group: ring = NPW * stages * 2 * GT * (2D+16) bytes.  Eight warps on
   // 8-token groups hide the in-order latencies of the softmax / MMA chain better than four on 16.
-  const char* e = getenv("OCRL_SA_GT");
-  const int gt = e ? atoi(e) : 8;  // measured on B200: 0.27 ms (8-token groups, 8 warps) vs 0.51 ms (16-token groups) at B=64, N=4096
+  // measured on B200: 0.27 ms (8-token groups, 8 warps) vs 0.51 ms (16-token groups) at B=64, N=4096
   if (D >= 192) {
-    if (a.K <= 8) return gt == 16 ? launch_tc<D, 8, 4, 16>(a, s) : launch_tc<D, 8, 8, 8>(a, s);
+    if (a.K <= 8) return launch_tc<D, 8, 8, 8>(a, s);
     return launch_tc<D, 16, 4, 16>(a, s);
   } else {
     if (a.K <= 8) return launch_tc<D, 8, 8, 16>(a, s);

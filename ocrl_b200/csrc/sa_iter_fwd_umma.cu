@@ -1,46 +1,52 @@
-// Two-engine persistent-cluster form of the fused T-iteration loop (slot_attn.py:64-102) for bf16 k/v.
+// tcgen05 form of the fused T-iteration loop (slot_attn.py:64-102) for bf16 k/v: the token pass runs on the
+// 5th-generation tensor cores with its accumulators in tensor memory.
 //
-// A cluster of CL CTAs works on TWO images at a time ("lanes").  Every CTA runs
-//   * a PASS engine  (warps 0-7: 4 logit warps + 4 U warps) that streams k/v tiles of its token share through a
-//     TMA ring and produces the partial sum_n w v and sum_n w of one (image, iteration), and
-//   * an UPDATE engine (warps 8-15) that runs the slot update of the other lane: reduce-scatter over the
-//     cluster, GRU, residual MLP, next q -- six DSMEM exchange rounds with tensor-core matrix-vector products
-//     against the CTA's weight slice, which stays in shared memory for the whole kernel.
-// The engines alternate lanes (pass A0 | pass B0 + update A0 | pass A1 + update B0 | ...), so the
-// latency-bound update of one image hides behind the bandwidth-bound pass of the other and the ring never
-// drains: tiles of the next pass are already in flight when a pass ends.  Hand-offs are shared-memory
-// mbarriers (u_ready / u_free / q_ready); the cluster exchange is st.async + complete_tx, double-buffered
-// by round parity (see pc_common.cuh / sa_iter_fwd_pc.cu for the single-engine form and the protocol).
-// Only 2 * (#clusters) images are in flight, so passes 2..T read k/v from L2.
+// Structure as in sa_iter_fwd_pipe.cu: a cluster of CL CTAs works on NL images at a time ("lanes"); every CTA
+// streams its share of the tokens (PASS engine, warps 0-7) while warps 8-15 run the slot update of another lane
+// (UPDATE engine: reduce-scatter over the cluster, GRU, residual MLP, next q; weights stationary in shared memory).
+// The pass engine here is
+//   * warp 4 / warp 6, one lane each: TMA producers of the k ring and the v ring (64-token half tiles,
+//     [D/64][64 rows][128 B] with the 128-byte swizzle = the canonical UMMA layouts: K-major for k, MN-major for v);
+//   * warp 5, one lane: issues  logits[64 x 8] = k_half . q^T  (M = 64; the two halves of a 128-token pair land in
+//     the lower / upper 16 lanes of every 32-lane quarter of one tensor-memory buffer) and
+//     U^T[D x 16] += v_half^T . w  (M = 128 for features 0-127, M = 64 for 128-191), tcgen05.commit frees the ring
+//     slots and signals the softmax warps;
+//   * warps 0-3, one token per thread: tcgen05.ld of the token's logits, K-way softmax in registers (no shuffles),
+//     attn_vis store in the last iteration, w = a + eps rounded to bf16 into the B-operand tile of the U product.
+// q arrives from the update engine already in the UMMA K-major layout ([D/8][8 slots][8] bf16).
 #include "pc_common.cuh"
+#include "umma_common.cuh"
 
 namespace ocrl {
-namespace pipe {
+namespace umma {
 
 using namespace pc;
 
-#ifndef TRACE_OP
-#define TRACE_OP 2
-#endif
-
-template <int D_, int H_, int CL_, int S_, int NL_, int KB_>
+template <int D_, int H_, int CL_, int NL_, int KB_, int NKS_, int NVS_, int NWB_>
 struct Cfg {
-  // NL image lanes per cluster; KB rows in the slot-indexed buffers (6 when K <= 6: room for one more ring stage)
-  static constexpr int D = D_, H = H_, CL = CL_, S = S_, NL = NL_, KB = KB_;
-  static constexpr int KP = 8, NT = 512, TOK = 16;
+  // NL image lanes per cluster; KB rows in the slot-indexed buffers; NKS / NVS ring slots for k / v half tiles;
+  // NWB buffers for the softmax weights of a 128-token pair
+  static constexpr int D = D_, H = H_, CL = CL_, NL = NL_, KB = KB_, NKS = NKS_, NVS = NVS_, NWB = NWB_;
+  static constexpr int KP = 8, NT = 512, HT = 64, NCH = D / 64;
   static constexpr int PITCH = D * 2 + 16, PITCHH = H * 2 + 16;
   static constexpr int LX = D > H ? D : H;
   static constexpr int PITCHX = LX * 2 + 16;
-  static constexpr int TILE_BYTES = TOK * D * 2, STAGE_BYTES = 2 * TILE_BYTES, WT_BYTES = 256;
+  static constexpr int CH_BYTES = HT * 128, HT_BYTES = NCH * CH_BYTES;  // one 64-wide feature chunk / one half tile
+  static constexpr int WH_BYTES = 2048, WP_BYTES = 2 * WH_BYTES;        // w tile of a half ([8][16 slots][8] bf16) / a pair
+  static constexpr int QOP_BYTES = D * 16;                              // q operand [D/8][8 slots][8] bf16
   static constexpr int DS = D / CL, HS = H / CL;
-  static constexpr int NMU = D / 16, NMG = (3 * DS + 15) / 16, NM1 = (HS + 15) / 16, NM2 = (DS + 15) / 16, NKC = 4;
+  static constexpr int NMG = (3 * DS + 15) / 16, NM1 = (HS + 15) / 16, NM2 = (DS + 15) / 16, NKC = 4;
   static constexpr int UP = D + 4;
-  static_assert(D % 64 == 0 && H % 64 == 0 && DS % 4 == 0 && HS % 4 == 0, "shape");
-  static_assert(TILE_BYTES % 1024 == 0, "swizzle atoms are 1024 bytes");
+  static constexpr int MA = NCH >= 2 ? 128 : 64;   // U product, features [0, 128) (or all 64)
+  static constexpr bool HAS_B = NCH == 3;          // second U product, features [128, 192)
+  static_assert(D % 64 == 0 && H % 64 == 0 && DS % 4 == 0 && HS % 4 == 0 && NCH <= 3, "shape");
+  // tensor memory columns: two logit buffers, two U accumulators (features 0-127 | 128-191)
+  static constexpr uint32_t COL_LG = 0, COL_U = 32, TMEM_COLS = 128;
 
-  static constexpr int OFF_RING = 0;
-  static constexpr int OFF_WT = OFF_RING + S * STAGE_BYTES;
-  static constexpr int OFF_WIH = OFF_WT + S * WT_BYTES;
+  static constexpr int OFF_KRING = 0;
+  static constexpr int OFF_VRING = OFF_KRING + NKS * HT_BYTES;
+  static constexpr int OFF_WT = OFF_VRING + NVS * HT_BYTES;
+  static constexpr int OFF_WIH = OFF_WT + NWB * WP_BYTES;
   static constexpr int OFF_WHH = OFF_WIH + 3 * DS * PITCH;
   static constexpr int OFF_W1 = OFF_WHH + 3 * DS * PITCH;
   static constexpr int OFF_W2 = OFF_W1 + HS * PITCH;
@@ -53,26 +59,29 @@ struct Cfg {
   static constexpr int OFF_XBUF = (OFF_BIAS + NCONST * 4 + 15) & ~15;
   static constexpr int OFF_ACT = OFF_XBUF + XBUF_BYTES;            // bf16 all-gather targets, by round parity
   static constexpr int P_ROWS = (3 * NMG > NKC * (NM1 > NM2 ? NM1 : NM2)) ? 3 * NMG * 16 : NKC * (NM1 > NM2 ? NM1 : NM2) * 16;
-  static constexpr int OFF_UST = OFF_ACT + 2 * KB * PITCHX;        // U staging a, b (pass -> update hand-off)
-  static constexpr int OFF_LANE = OFF_UST + 2 * KB * UP * 4;       // per lane: slots (bf16), q (bf16), own slice (fp32)
-  static constexpr int LANE_BYTES = KB * PITCH + KB * PITCH + KB * DS * 4;
+  static constexpr int OFF_UST = OFF_ACT + 2 * KB * PITCHX;        // U staging (pass -> update hand-off)
+  static constexpr int OFF_LANE = (OFF_UST + KB * UP * 4 + 127) & ~127;  // per lane: q operand, slots (bf16), own slice (fp32)
+  static constexpr int LANE_BYTES = (QOP_BYTES + KB * PITCH + KB * DS * 4 + 127) & ~127;
   // rows KB..7 of the slot-indexed buffers are read as (ignored) padding columns of the MMAs, so plain data follows
   // them: the MMA partial outputs and the token sums close the list
   static constexpr int OFF_P = (OFF_LANE + NL * LANE_BYTES + 15) & ~15;
-  static constexpr int OFF_SRED = OFF_P + P_ROWS * 32;             // [4][8] token sums of the logit warps
-  static constexpr int OFF_BAR = OFF_SRED + 128;  // full[S] w_ready[S] xbar[2] u_ready u_free q_ready[NL]
-  static constexpr int OFF_ISSUED = OFF_BAR + (2 * S + 4 + NL) * 8;
-  static constexpr int SMEM_BYTES = OFF_ISSUED + S * 4;
+  static constexpr int OFF_SRED = OFF_P + P_ROWS * 32;             // [4][8] token sums of the softmax warps
+  // k_full k_empty [NKS] v_full v_empty [NVS] lg_full lg_empty w_full w_empty u_full u_accfree [2 each] xbar[2]
+  // u_ready u_free q_ready[NL]
+  static constexpr int OFF_BAR = OFF_SRED + 128;
+  static constexpr int NBAR = 2 * NKS + 2 * NVS + 12 + 2 + 2 + NL;
+  static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
+  static constexpr int SMEM_BYTES = OFF_TMEM + 16;
 };
 
 __device__ __forceinline__ void upd_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-template <int D, int H, int CL, int S, int NL, int KB>
+template <int D, int H, int CL, int NL, int KB, int NKS, int NVS, int NWB>
 __global__ void __launch_bounds__(512, 1)
-sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v) {
-  using C = Cfg<D, H, CL, S, NL, KB>;
+sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v) {
+  using C = Cfg<D, H, CL, NL, KB, NKS, NVS, NWB>;
   constexpr int PITCH = C::PITCH, PITCHH = C::PITCHH, PITCHX = C::PITCHX, DS = C::DS, HS = C::HS;
-  constexpr int NMU = C::NMU, NMG = C::NMG, NM1 = C::NM1, NM2 = C::NM2, NKC = C::NKC, UP = C::UP, TOK = C::TOK;
+  constexpr int NMG = C::NMG, NM1 = C::NM1, NM2 = C::NM2, NKC = C::NKC, UP = C::UP, HT = C::HT, NCH = C::NCH;
   constexpr float LOG2E = 1.4426950408889634f;
 
   extern __shared__ __align__(1024) unsigned char sm[];  // swizzled TMA tiles need 1024-byte alignment
@@ -81,12 +90,12 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
   const int rank = (int)cluster.block_rank();
   const int cid = blockIdx.x / CL, ncl = gridDim.x / CL;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int g8 = lane >> 2, t4 = lane & 3;
   const int K = a.K, N = a.N, T = a.T, B = a.B;
   const bool tracer = (a.trace != nullptr && blockIdx.x == 0);
 #define PP_TRACE(i) do { if (tracer) a.trace[(i)] = clock64(); } while (0)
 
-  unsigned char* ring = sm + C::OFF_RING;
+  unsigned char* kring = sm + C::OFF_KRING;
+  unsigned char* vring = sm + C::OFF_VRING;
   unsigned char* wtiles = sm + C::OFF_WT;
   unsigned char* s_wih = sm + C::OFF_WIH;
   unsigned char* s_whh = sm + C::OFF_WHH;
@@ -107,34 +116,39 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
   unsigned char* xbuf = sm + C::OFF_XBUF;
   auto act = [&](uint32_t r) { return sm + C::OFF_ACT + (r & 1) * (KB * PITCHX); };  // bf16 [KB][PITCHX]
   float* P = reinterpret_cast<float*>(sm + C::OFF_P);
-  float* ustage_a = reinterpret_cast<float*>(sm + C::OFF_UST);
-  float* ustage_b = ustage_a + KB * UP;
+  float* ustage = reinterpret_cast<float*>(sm + C::OFF_UST);
   float* sred = reinterpret_cast<float*>(sm + C::OFF_SRED);
-  auto slh_hi = [&](int l) { return sm + C::OFF_LANE + l * C::LANE_BYTES; };
-  auto qbuf = [&](int l) { return sm + C::OFF_LANE + l * C::LANE_BYTES + KB * PITCH; };
-  auto own_of = [&](int l) { return reinterpret_cast<float*>(sm + C::OFF_LANE + l * C::LANE_BYTES + 2 * KB * PITCH); };
+  auto qop = [&](int l) { return sm + C::OFF_LANE + l * C::LANE_BYTES; };
+  auto slh_hi = [&](int l) { return sm + C::OFF_LANE + l * C::LANE_BYTES + C::QOP_BYTES; };
+  auto own_of = [&](int l) { return reinterpret_cast<float*>(sm + C::OFF_LANE + l * C::LANE_BYTES + C::QOP_BYTES + KB * PITCH); };
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
-  uint64_t* full = bars;
-  uint64_t* w_ready = bars + S;
-  uint64_t* xbar = bars + 2 * S;
-  uint64_t* u_ready = bars + 2 * S + 2;
-  uint64_t* u_free = bars + 2 * S + 3;
-  uint64_t* q_ready = bars + 2 * S + 4;
-  int* issued = reinterpret_cast<int*>(sm + C::OFF_ISSUED);
+  uint64_t* k_full = bars;
+  uint64_t* k_empty = k_full + NKS;
+  uint64_t* v_full = k_empty + NKS;
+  uint64_t* v_empty = v_full + NVS;
+  uint64_t* lg_full = v_empty + NVS;   // [2] logits of a pair are in tensor memory
+  uint64_t* lg_empty = lg_full + 2;    // [2] the softmax warps have read them
+  uint64_t* w_full = lg_empty + 2;     // [2] softmax weights of a pair are in shared memory
+  uint64_t* w_empty = w_full + 2;      // [2] the U products that read them are complete
+  uint64_t* u_full = w_empty + 2;      // [2] U accumulator of an op is complete
+  uint64_t* u_accfree = u_full + 2;    // [2] ... and has been drained
+  uint64_t* xbar = u_accfree + 2;
+  uint64_t* u_ready = xbar + 2;
+  uint64_t* u_free = u_ready + 1;
+  uint64_t* q_ready = u_free + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + C::OFF_TMEM);
 
-  // ------------------------------------------------------------------ work assignment (two lanes per cluster)
+  // ------------------------------------------------------------------ work assignment (NL lanes per cluster)
   // Images are dealt to clusters round-robin (newest first: the projection kernel left them in L2) and a cluster
-  // alternates its images between its two lanes, so every cluster gets floor or ceil of B / #clusters images.
+  // deals its images to its lanes, so every cluster gets floor or ceil of B / #clusters images.
   const int ncimg = (B > cid) ? (B - cid + ncl - 1) / ncl : 0;
   // Lane l takes the cluster's images l, l + NL, ...; ops (one pass + one update of one lane) are streamed row by row:
   // row c holds op c of every lane that still has one, lanes in order (lane counts are non-increasing in l and
-  // differ by at most one image).  With NL = 3 an update has two pass slots to finish in, so the stream advances at
-  // the pace of the pass engine alone.
+  // differ by at most one image).
   int nops[NL], row_start[NL + 1], row_width[NL + 1], seg_base[NL + 1];
   auto nimg_of = [&](int l) { return (ncimg > l) ? (ncimg - l + NL - 1) / NL : 0; };
 #pragma unroll
   for (int l = 0; l < NL; ++l) nops[l] = nimg_of(l) * T;
-  // segments of rows with constant width: width NL while c < nops[NL-1], NL-1 while c < nops[NL-2], ...
   int total_ops = 0;
   {
     int prev = 0;
@@ -162,96 +176,44 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
     }
   };
   auto image_of = [&](int l, int m) { return B - 1 - (cid + (NL * m + l) * ncl); };
-  const int ntiles = (N + TOK - 1) / TOK;
+  const int ntiles = (N + HT - 1) / HT;          // 64-token half tiles of an image
   const int TPC = (ntiles + CL - 1) / CL;
   const int tile0 = rank * TPC;
-  const int TP = max(0, min(TPC, ntiles - tile0));
-  // tile j is handled by chain j % 4 and lives in stage j % S: with S % 4 == 0 and TP % 4 == 0 a warp only ever sees its own stages
-  const bool guard = (S % 4 != 0) || (TP % 4 != 0);
+  const int TP = max(0, min(TPC, ntiles - tile0));  // half tiles of this CTA per pass
+  const int NP = (TP + 1) / 2;                       // 128-token pairs
+  const int total_ht = total_ops * TP;
 
-  // one elected lane: stage (j % S) <- tile j = n * TP + tile of the CTA's tile sequence (pass ops in stream order).
+  // One elected lane per ring: slot (j % NS) <- half tile j of the CTA's stream (ops in stream order).
   // L2 policy: tiles of iterations 0..T-2 are read again by the next pass (evict_last), the final pass's are dead
-  // afterwards (evict_first).  For the first pass of an image the tile `PFD` tiles further on is prefetched into L2
-  // at the same rate as tiles are consumed (a burst would queue in front of the demand loads).
+  // afterwards (evict_first).  For the first pass of an image the half tile `PFD` further on is prefetched into L2
+  // at the rate tiles are consumed.
   const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
-  constexpr int PFD = 24;
-  auto issue_tile = [&](int n, int tile) {
-    const int j = n * TP + tile;
-    const int s = j % S;
+  constexpr int PFD = 6;
+  auto issue_half = [&](int j, bool is_v) {
+    const int n = j / TP, tile = j - n * TP;
     int l, c;
     op_of(n, l, c);
     const int t = c % T;
-    const int row0 = image_of(l, c / T) * N + (tile0 + tile) * TOK;
-    unsigned char* kd = ring + (size_t)s * C::STAGE_BYTES;
+    const int row0 = image_of(l, c / T) * N + (tile0 + tile) * HT;
     const uint64_t pol = (t == T - 1) ? pol_drop : pol_keep;
-    mbar_expect_tx(&full[s], (uint32_t)C::STAGE_BYTES);
-    tma_load_3d_hint(kd, &tm_k, 0, 0, row0, &full[s], pol);
-    tma_load_3d_hint(kd + C::TILE_BYTES, &tm_v, 0, 0, row0, &full[s], pol);
-    sts_volatile(&issued[s], j);  // after the expect_tx in program order: the barrier is in this tile's phase
-    // paced L2 prefetch, only where the data is cold (first pass of an image)
-    int pn = n, pt = tile + PFD;
-    while (pt >= TP && pn < total_ops) { pt -= TP; ++pn; }
-    if (pn < total_ops) {
+    const int s = j % (is_v ? NVS : NKS);
+    unsigned char* dst = (is_v ? vring : kring) + (size_t)s * C::HT_BYTES;
+    uint64_t* bar = is_v ? &v_full[s] : &k_full[s];
+    const CUtensorMap* tm = is_v ? &tm_v : &tm_k;
+    mbar_expect_tx(bar, (uint32_t)C::HT_BYTES);
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) tc::tma_load_2d_hint(dst + ch * C::CH_BYTES, tm, ch * 64, row0, bar, pol);
+    const int jp = j + PFD;
+    if (jp < total_ht) {
+      const int pn = jp / TP, pt = jp - pn * TP;
       int pl, pc;
       op_of(pn, pl, pc);
       if (pc % T == 0) {
-        const size_t off = ((size_t)image_of(pl, pc / T) * N + (size_t)(tile0 + pt) * TOK) * D * 2;
-        if (off + C::TILE_BYTES <= (size_t)B * N * D * 2) {
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(a.k) + off), "r"(C::TILE_BYTES) : "memory");
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(a.v) + off), "r"(C::TILE_BYTES) : "memory");
-        }
+        const size_t off = ((size_t)image_of(pl, pc / T) * N + (size_t)(tile0 + pt) * HT) * D * 2;
+        if (off + C::HT_BYTES <= (size_t)B * N * D * 2)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(is_v ? a.v : a.k) + off), "r"(C::HT_BYTES) : "memory");
       }
     }
-  };
-  // Per-op constants of the refill path (row base of the CTA's share, L2 policy, cold = first pass of an image),
-  // computed once per op so that the per-tile refill is a handful of instructions.
-  struct OpInfo { int row_base; int cold; int valid; uint64_t pol; };
-  auto op_info = [&](int n) {
-    OpInfo o;
-    o.valid = (n < total_ops);
-    o.row_base = 0; o.cold = 0; o.pol = pol_keep;
-    if (o.valid) {
-      int l, c;
-      op_of(n, l, c);
-      const int t = c % T;
-      o.row_base = image_of(l, c / T) * N + tile0 * TOK;
-      o.cold = (t == 0);
-      o.pol = (t == T - 1) ? pol_drop : pol_keep;
-    }
-    return o;
-  };
-  // refill of stage j % S with tile (op, tile) and paced prefetch; `cur` / `nxt` describe ops n and n + 1
-  auto refill_fast = [&](int n, int tile, const OpInfo& cur, const OpInfo& nxt) {
-    int tn = tile + S;
-    const OpInfo& o = (tn < TP) ? cur : nxt;
-    const int nn = (tn < TP) ? n : n + 1;
-    if (tn >= TP) tn -= TP;
-    if (o.valid) {
-      const int j = nn * TP + tn;
-      const int s = j % S;
-      const int row0 = o.row_base + tn * TOK;
-      unsigned char* kd = ring + (size_t)s * C::STAGE_BYTES;
-      mbar_expect_tx(&full[s], (uint32_t)C::STAGE_BYTES);
-      tma_load_3d_hint(kd, &tm_k, 0, 0, row0, &full[s], o.pol);
-      tma_load_3d_hint(kd + C::TILE_BYTES, &tm_v, 0, 0, row0, &full[s], o.pol);
-      sts_volatile(&issued[s], j);
-    }
-    int pt = tile + PFD;
-    const OpInfo& po = (pt < TP) ? cur : nxt;
-    if (pt >= TP) pt -= TP;
-    if (po.valid && po.cold) {
-      const size_t off = (size_t)(po.row_base + pt * TOK) * (D * 2);
-      if (off + C::TILE_BYTES <= (size_t)B * N * D * 2) {
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(a.k) + off), "r"(C::TILE_BYTES) : "memory");
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(a.v) + off), "r"(C::TILE_BYTES) : "memory");
-      }
-    }
-  };
-  // tile (n, tile) + S in stream order, or n = -1 past the end
-  auto advance = [&](int& n, int& tile) {
-    tile += S;
-    while (tile >= TP) { tile -= TP; ++n; }
-    if (n >= total_ops) n = -1;
   };
 
   // ------------------------------------------------------------------ one-time setup
@@ -274,27 +236,34 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
     }
   }
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&w_ready[s], 1);
-      sts_volatile(&issued[s], -1);
+    for (int s = 0; s < NKS; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
+    for (int s = 0; s < NVS; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&lg_full[s], 1);
+      mbar_init(&lg_empty[s], 4);
+      mbar_init(&w_full[s], 4);
+      mbar_init(&w_empty[s], 1);
+      mbar_init(&u_full[s], 1);
+      mbar_init(&u_accfree[s], 4);
     }
     mbar_init(&xbar[0], 1);
     mbar_init(&xbar[1], 1);
-    mbar_init(u_ready, 8);
+    mbar_init(u_ready, 4);
     mbar_init(u_free, 8);
     for (int l = 0; l < NL; ++l) mbar_init(&q_ready[l], 1);
     mbar_fence_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_k) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_v) : "memory");
   }
-  // first tiles: their HBM latency overlaps the weight load below.  A tile costs its issuing lane several hundred
-  // cycles, so the pass warps issue one (or two) each, behind a barrier of their own that publishes the mbarrier init
+  if (warp == 7) tc::tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  // first half tiles: their HBM latency overlaps the weight load below (behind a barrier of the pass warps that
+  // publishes the mbarrier init)
   if (warp < 8) {
     asm volatile("bar.sync 3, 256;" ::: "memory");
-    if (lane == 0 && TP > 0)
-      for (int p = warp; p < S; p += 8)
-        if (p / TP < total_ops) issue_tile(p / TP, p % TP);
+    if (lane == 0 && TP > 0) {
+      if (warp == 4) for (int j = 0; j < NKS && j < total_ht; ++j) issue_half(j, false);
+      if (warp == 6) for (int j = 0; j < NVS && j < total_ht; ++j) issue_half(j, true);
+    }
   }
   {
     // the CTA's weight slices, fp32 global -> bf16 shared; eight independent 16-byte loads in flight per thread
@@ -326,7 +295,6 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
     // LayerNorm folded into the product that follows it:  W LN(x) = rstd (W' x - mean c) + W beta,  W' = W diag(gamma),
     // c = row sums of the (bf16-rounded) W'.  One warp per row.
     {
-      constexpr int NCH = D / 64;
       for (int r = warp; r < HS + DS; r += C::NT / 32) {
         const bool is1 = r < HS;
         const int rr = is1 ? r : r - HS;
@@ -361,11 +329,17 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
       s_bias[3 * DS + i] = a.w.b_hh[gate * D + rank * DS + dl];
     }
     for (int i = tid; i < DS; i += C::NT) s_bias[6 * DS + HS + i] = a.w.b2[rank * DS + i];
-    // staging rows of the padded slots are never written by the conversions; keep them finite
+    // staging rows of the padded slots are never written by the conversions; keep them finite.  The w tiles' slot rows
+    // 8..15 and the q operands' rows K..7 stay zero for the whole kernel.
     for (int i = tid; i < (2 * KB * PITCHX) / 4; i += C::NT) reinterpret_cast<uint32_t*>(sm + C::OFF_ACT)[i] = 0u;
     for (int i = tid; i < (NL * C::LANE_BYTES) / 4; i += C::NT) reinterpret_cast<uint32_t*>(sm + C::OFF_LANE)[i] = 0u;
+    for (int i = tid; i < (NWB * C::WP_BYTES) / 4; i += C::NT) reinterpret_cast<uint32_t*>(wtiles)[i] = 0u;
+    fence_proxy_async();  // the zero rows are read by tcgen05.mma (async proxy)
   }
+  tc::fence_before();
   __syncthreads();
+  tc::fence_after();
+  const uint32_t tmem = *tmem_slot;
   if (tid >= 256 && nops[0] > 0) {  // after the zero fill of the lane buffers; the cluster barrier below publishes it
     unsigned char* dst = slh_hi(0);
     float* own = own_of(0);
@@ -385,198 +359,206 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
 
   if (warp < 8) {
     // ==================================================================================== PASS ENGINE
-    for (int n = 0; n < total_ops; ++n) {
-      int l, c;
-      op_of(n, l, c);
-      const int t = c % T, img = image_of(l, c / T);
-      const bool last = (t == T - 1);
-      const int jbase = n * TP;
-      if (warp < 4) {
-        // ---- logit warp
-        mbar_wait(&q_ready[l], (uint32_t)(c & 1));
-        if (tid == 0 && n < 40) PP_TRACE(8 + n * 8);
-        const unsigned char* qsrc = qbuf(l);
-        uint32_t qb[D / 16][2];
+    if (warp < 4) {
+      // ---- softmax warps: one token per thread.  Thread (warp w, lane) reads tensor-memory lane 32 w + lane:
+      // lanes 0-15 hold rows 16 w .. 16 w + 15 of the pair's first half, lanes 16-31 the same rows of the second half.
+      const int half = lane >> 4, r16 = lane & 15;
+      const int tt = warp * 16 + r16;  // token inside its half
+      const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+      uint32_t gp = 0;  // pairs handled so far (selects the logit / w buffers and their phases)
+      for (int n = 0; n < total_ops; ++n) {
+        int l, c;
+        op_of(n, l, c);
+        const int t = c % T, img = image_of(l, c / T);
+        const bool last = (t == T - 1);
+        float Sl[8];
 #pragma unroll
-        for (int ks = 0; ks < D / 16; ++ks) {
-          qb[ks][0] = *reinterpret_cast<const uint32_t*>(qsrc + g8 * PITCH + ks * 32 + 4 * t4);
-          qb[ks][1] = *reinterpret_cast<const uint32_t*>(qsrc + g8 * PITCH + ks * 32 + 16 + 4 * t4);
-        }
-        const int c0 = 2 * t4, c1 = 2 * t4 + 1;
-        const bool ok0 = c0 < K, ok1 = c1 < K;
-        float Sl0 = 0.f, Sl1 = 0.f;
-        const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lhalf = (lane >> 4) * 16;
-        for (int tile = warp; tile < TP; tile += 4) {
-          const int j = jbase + tile;
-          const int s = j % S;
-          const uint32_t ph = (uint32_t)((j / S) & 1);
-          const unsigned char* kt = ring + (size_t)s * C::STAGE_BYTES;
-          uint32_t* wt = reinterpret_cast<uint32_t*>(wtiles + s * C::WT_BYTES);
-          const bool tt = tracer && tid == 0 && n == TRACE_OP && tile < 32;  // tile stamps of chain 0 in a steady-state op
-          if (tt) a.trace[340 + (tile >> 2) * 8 + 0] = clock64();
-          // mbarrier parity waits alias two phases ahead: unless a warp always returns to the same stages, make sure the
-          // barrier has entered this tile's phase first
-          if (guard) while (lds_volatile(&issued[s]) < j) __nanosleep(20);
-          mbar_wait(&full[s], ph);
-          if (tt) a.trace[340 + (tile >> 2) * 8 + 1] = clock64();
-          float ca[4] = {0.f, 0.f, 0.f, 0.f}, cb[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int i = 0; i < 8; ++i) Sl[i] = 0.f;
+        for (int p = 0; p < NP; ++p, ++gp) {
+          const uint32_t lb = gp & 1, wb = gp % NWB;
+          mbar_wait(&lg_full[lb], (gp >> 1) & 1);
+          if (tid == 0 && p == 0 && n < 40) PP_TRACE(8 + n * 8);
+          tc::fence_after();
+          float x[8];
+          tc::tmem_ld8(tlane + C::COL_LG + 16 * lb, x);
+          tc::fence_before();
+          __syncwarp();
+          if (lane == 0) tc::arrive(&lg_empty[lb]);
+          const int ht = 2 * p + half;
+          const int tok = (tile0 + ht) * HT + tt;
+          const bool tok_ok = (ht < TP) && (tok < N);
+          float mx = -INFINITY;
 #pragma unroll
-          for (int ks = 0; ks < D / 16; ++ks) {
-            uint32_t kf[4];
-            ldmatrix_x4(kf, kt + swz_off<D>(lrow, ks * 32 + lhalf));
-            if (ks & 1) mma_bf16_16816(cb, kf, qb[ks][0], qb[ks][1]);
-            else mma_bf16_16816(ca, kf, qb[ks][0], qb[ks][1]);
+          for (int i = 0; i < 8; ++i) {
+            x[i] = (i < K) ? x[i] : -INFINITY;
+            mx = fmaxf(mx, x[i]);
           }
-          if (tt) a.trace[340 + (tile >> 2) * 8 + 2] = clock64();
-          // softmax over the slot axis: a token's 8 logits live in the 4 lanes of a quad (2 each).  Both token rows
-          // of the fragment go through the reductions together (straight-line code, the two chains interleave);
-          // the divergent attn_vis stores come afterwards.
-          const int tok = (tile0 + tile) * TOK + g8;
-          float x0[2], x1[2], mx[2], e0[2], e1[2], sum[2];
+          float sum = 0.f;
 #pragma unroll
-          for (int hrow = 0; hrow < 2; ++hrow) {
-            x0[hrow] = ok0 ? ca[2 * hrow] + cb[2 * hrow] : -INFINITY;
-            x1[hrow] = ok1 ? ca[2 * hrow + 1] + cb[2 * hrow + 1] : -INFINITY;
-            mx[hrow] = fmaxf(x0[hrow], x1[hrow]);
+          for (int i = 0; i < 8; ++i) {
+            x[i] = ex2f(x[i] - mx);  // q carries log2(e)
+            sum += x[i];
           }
+          const float inv = __fdividef(1.f, sum);
 #pragma unroll
-          for (int o = 1; o <= 2; o <<= 1) {
-            const float m0 = __shfl_xor_sync(FULL, mx[0], o), m1 = __shfl_xor_sync(FULL, mx[1], o);
-            mx[0] = fmaxf(mx[0], m0);
-            mx[1] = fmaxf(mx[1], m1);
-          }
+          for (int i = 0; i < 8; ++i) x[i] *= inv;
+          if (last && a.attn_out != nullptr && tok_ok) {
+            float* ao = a.attn_out + ((size_t)img * N + tok) * K;
+            if ((K & 1) == 0) {
 #pragma unroll
-          for (int hrow = 0; hrow < 2; ++hrow) {
-            e0[hrow] = ex2f(x0[hrow] - mx[hrow]);
-            e1[hrow] = ex2f(x1[hrow] - mx[hrow]);
-            sum[hrow] = e0[hrow] + e1[hrow];
-          }
+              for (int i = 0; i < 8; i += 2)
+                if (i < K) __stcs(reinterpret_cast<float2*>(ao + i), make_float2(x[i], x[i + 1]));
+            } else {
 #pragma unroll
-          for (int o = 1; o <= 2; o <<= 1) {
-            const float s0 = __shfl_xor_sync(FULL, sum[0], o), s1 = __shfl_xor_sync(FULL, sum[1], o);
-            sum[0] += s0;
-            sum[1] += s1;
-          }
-          float w[4];
-          float av[4];
-#pragma unroll
-          for (int hrow = 0; hrow < 2; ++hrow) {
-            const float inv = __fdividef(1.f, sum[hrow]);
-            av[2 * hrow] = e0[hrow] * inv;
-            av[2 * hrow + 1] = e1[hrow] * inv;
-            const bool tok_ok = (tok + 8 * hrow) < N;
-            w[2 * hrow] = (tok_ok && ok0) ? av[2 * hrow] + a.eps : 0.f;
-            w[2 * hrow + 1] = (tok_ok && ok1) ? av[2 * hrow + 1] + a.eps : 0.f;
-          }
-          if (last && a.attn_out != nullptr) {
-#pragma unroll
-            for (int hrow = 0; hrow < 2; ++hrow) {
-              const int tk = tok + 8 * hrow;
-              if (tk < N) {
-                float* ao = a.attn_out + ((size_t)img * N + tk) * K;
-                if ((K & 1) == 0) {
-                  if (ok0) __stcs(reinterpret_cast<float2*>(ao + c0), make_float2(av[2 * hrow], av[2 * hrow + 1]));
-                } else {
-                  if (ok0) ao[c0] = av[2 * hrow];
-                  if (ok1) ao[c1] = av[2 * hrow + 1];
-                }
-              }
+              for (int i = 0; i < 8; ++i)
+                if (i < K) __stcs(ao + i, x[i]);
             }
           }
-          if (tt) a.trace[420 + (tile >> 2) * 4 + 0] = clock64();
           // weights rounded to bf16 once; the same rounded values feed the numerator and the token sum
-          const __nv_bfloat162 p0 = __floats2bfloat162_rn(w[0], w[1]);
-          const __nv_bfloat162 p1 = __floats2bfloat162_rn(w[2], w[3]);
-          Sl0 += __low2float(p0) + __low2float(p1);
-          Sl1 += __high2float(p0) + __high2float(p1);
-          wt[lane] = movmatrix_trans(*reinterpret_cast<const uint32_t*>(&p0));
-          wt[32 + lane] = movmatrix_trans(*reinterpret_cast<const uint32_t*>(&p1));
-          if (tt) a.trace[420 + (tile >> 2) * 4 + 1] = clock64();
+          if (gp >= (uint32_t)NWB) mbar_wait(&w_empty[wb], ((gp / NWB) - 1) & 1);
+          unsigned char* wrow = wtiles + wb * C::WP_BYTES + half * C::WH_BYTES + (tt >> 3) * 256 + (tt & 7) * 2;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float wv = (tok_ok && i < K) ? x[i] + a.eps : 0.f;
+            const __nv_bfloat16 wq = __float2bfloat16_rn(wv);
+            *reinterpret_cast<__nv_bfloat16*>(wrow + i * 16) = wq;
+            Sl[i] += __bfloat162float(wq);
+          }
+          fence_proxy_async();
           __syncwarp();
-          if (tt) a.trace[420 + (tile >> 2) * 4 + 2] = clock64();
-          if (lane == 0) mbar_arrive(&w_ready[s]);
-          if (tt) a.trace[340 + (tile >> 2) * 8 + 3] = clock64();
+          if (lane == 0) tc::arrive(&w_full[wb]);
         }
 #pragma unroll
-        for (int o = 4; o < 32; o <<= 1) {
-          Sl0 += __shfl_xor_sync(FULL, Sl0, o);
-          Sl1 += __shfl_xor_sync(FULL, Sl1, o);
+        for (int i = 0; i < 8; ++i) Sl[i] = warp_sum(Sl[i]);
+        // ---- drain the op's U accumulator into the staging buffer of the update engine
+        float ua[8], ub[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { ua[i] = 0.f; ub[i] = 0.f; }
+        if (NP > 0) {
+          mbar_wait(&u_full[n & 1], (n >> 1) & 1);
+          tc::fence_after();
+          tc::tmem_ld8(tlane + C::COL_U + 32 * (n & 1), ua);
+          if (C::HAS_B) tc::tmem_ld8(tlane + C::COL_U + 32 * (n & 1) + 16, ub);
+          tc::fence_before();
+          __syncwarp();
+          if (lane == 0) tc::arrive(&u_accfree[n & 1]);
         }
         if (n > 0) mbar_wait(u_free, (uint32_t)((n - 1) & 1));  // the previous update has read sred / the U staging
-        if (g8 == 0) {
-          sred[warp * 8 + c0] = Sl0;
-          sred[warp * 8 + c1] = Sl1;
+        {
+          // features: M = 128 block -> lane index 32 w + lane; M = 64 blocks -> lanes 0-15 of every quarter
+          const int da = (C::MA == 128) ? warp * 32 + lane : warp * 16 + r16;
+          const bool oka = (C::MA == 128) || lane < 16;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (i < KB && oka) ustage[i * UP + da] = ua[i];
+          if (C::HAS_B && lane < 16) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (i < KB) ustage[i * UP + 128 + warp * 16 + r16] = ub[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (lane == i) sred[warp * 8 + i] = Sl[i];
         }
         if (tid == 0 && n < 40) PP_TRACE(8 + n * 8 + 1);
-      } else {
-        // ---- U warp: all D features of its tiles
-        const int uw = warp - 4;
-        float acc[NMU][4];
-#pragma unroll
-        for (int i = 0; i < NMU; ++i)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) acc[i][e] = 0.f;
-        const int urow = (lane & 7) + (lane >> 4) * 8, uhalf = ((lane >> 3) & 1) * 16;
-        const bool fast = (S <= TP) && (PFD <= TP);
-        const OpInfo oi_cur = op_info(n), oi_nxt = op_info(n + 1);
-        for (int tile = uw; tile < TP; tile += 4) {
-          const int j = jbase + tile;
-          const int s = j % S;
-          const uint32_t ph = (uint32_t)((j / S) & 1);
-          const unsigned char* vt = ring + (size_t)s * C::STAGE_BYTES + C::TILE_BYTES;
-          const uint32_t* wt = reinterpret_cast<const uint32_t*>(wtiles + s * C::WT_BYTES);
-          const bool tt = tracer && tid == 128 && n == TRACE_OP && tile < 32;
-          if (tt) a.trace[340 + (tile >> 2) * 8 + 4] = clock64();
-          if (guard) while (lds_volatile(&issued[s]) < j) __nanosleep(20);
-          mbar_wait(&w_ready[s], ph);  // implies full[s]: the logit warp waited for k and v together
-          if (tt) a.trace[340 + (tile >> 2) * 8 + 5] = clock64();
-          const uint32_t b0 = wt[lane], b1 = wt[32 + lane];
-#pragma unroll
-          for (int i = 0; i < NMU; ++i) {
-            uint32_t vf[4];
-            ldmatrix_x4_trans(vf, vt + swz_off<D>(urow, uhalf + i * 32));
-            mma_bf16_16816(acc[i], vf, b0, b1);
-          }
-          __syncwarp();  // every lane is done with the stage (this warp is its only remaining reader)
-          if (tt) a.trace[340 + (tile >> 2) * 8 + 6] = clock64();
-          if (lane == 0) {
-            if (fast) {
-              refill_fast(n, tile, oi_cur, oi_nxt);
-            } else {
-              int nn = n, tn = tile;
-              advance(nn, tn);
-              if (nn >= 0) issue_tile(nn, tn);
-            }
-          }
-          if (tt) a.trace[340 + (tile >> 2) * 8 + 7] = clock64();
-        }
-        if (n > 0) mbar_wait(u_free, (uint32_t)((n - 1) & 1));
-        // combine the four partial sums: warps 4, 5 write the two staging buffers, warps 6, 7 add into them
-        float* ust = (uw & 1) ? ustage_b : ustage_a;
-        if (uw >= 2) asm volatile("bar.sync 2, 128;" ::: "memory");
-#pragma unroll
-        for (int i = 0; i < NMU; ++i) {
-          const int d0 = 16 * i + g8;
-          float* u0 = ust + (2 * t4) * UP + d0;
-          float* u1 = ust + (2 * t4 + 1) * UP + d0;
-          if (2 * t4 < KB) {  // rows KB..7 are padding slots
-            if (uw >= 2) {
-              u0[0] += acc[i][0]; u1[0] += acc[i][1]; u0[8] += acc[i][2]; u1[8] += acc[i][3];
-            } else {
-              u0[0] = acc[i][0]; u1[0] = acc[i][1]; u0[8] = acc[i][2]; u1[8] = acc[i][3];
-            }
-          }
-        }
-        if (uw < 2) asm volatile("bar.sync 2, 128;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(u_ready);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(u_ready);
+    } else if (warp == 4 || warp == 6) {
+      // ---- TMA producers: warp 4 the k ring, warp 6 the v ring
+      if (lane == 0) {
+        const bool is_v = (warp == 6);
+        const int NS = is_v ? NVS : NKS;
+        uint64_t* empty = is_v ? v_empty : k_empty;
+        for (int j = NS; j < total_ht; ++j) {
+          mbar_wait(&empty[j % NS], (uint32_t)(((j / NS) - 1) & 1));
+          issue_half(j, is_v);
+        }
+      }
+    } else if (warp == 5) {
+      // ---- MMA issuer
+      if (lane == 0) {
+        constexpr uint32_t ID_LG = tc::idesc_bf16(64, 8);
+        constexpr uint32_t ID_UA = tc::idesc_bf16(C::MA, 16, 1, 0);
+        constexpr uint32_t ID_UB = tc::idesc_bf16(64, 16, 1, 0);
+        uint32_t gp = 0, gu = 0;  // pairs whose logit / U products have been issued
+        int jk = 0, jv = 0;       // half tiles consumed from the k / v rings
+        for (int n = 0; n < total_ops; ++n) {
+          int l, c;
+          op_of(n, l, c);
+          if (NP == 0) continue;
+          mbar_wait(&q_ready[l], (uint32_t)(c & 1));
+          fence_proxy_async();
+          tc::fence_after();
+          const uint32_t qa = smem_u32(qop(l));
+          const uint32_t ucol = tmem + C::COL_U + 32 * (n & 1);
+          auto logits = [&](int p) {
+            const uint32_t lb = gp & 1;
+            if (gp >= 2) {
+              mbar_wait(&lg_empty[lb], ((gp >> 1) - 1) & 1);
+              tc::fence_after();
+            }
+            for (int h = 0; h < 2 && 2 * p + h < TP; ++h) {
+              const int s = jk % NKS;
+              mbar_wait(&k_full[s], (uint32_t)((jk / NKS) & 1));
+              tc::fence_after();
+              const uint32_t ka = smem_u32(kring + (size_t)s * C::HT_BYTES);
+              const uint32_t dcol = tmem + C::COL_LG + 16 * lb + ((uint32_t)(16 * h) << 16);
+#pragma unroll
+              for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  tc::mma_bf16(dcol, tc::smem_desc(ka + ch * C::CH_BYTES + ks * 32, 16, 1024, tc::SW_128),
+                               tc::smem_desc(qa + (ch * 4 + ks) * 256, 128, 128, tc::SW_NONE), ID_LG, (ch | ks) != 0);
+              tc::commit(&k_empty[s]);
+              ++jk;
+            }
+            tc::commit(&lg_full[lb]);
+            ++gp;
+          };
+          auto uprod = [&](int p) {
+            const uint32_t wb = gu % NWB;
+            mbar_wait(&w_full[wb], (gu / NWB) & 1);
+            tc::fence_after();
+            if (p == 0 && n >= 2) {  // the accumulator was last used by op n - 2
+              mbar_wait(&u_accfree[n & 1], (uint32_t)(((n >> 1) - 1) & 1));
+              tc::fence_after();
+            }
+            for (int h = 0; h < 2 && 2 * p + h < TP; ++h) {
+              const int s = jv % NVS;
+              mbar_wait(&v_full[s], (uint32_t)((jv / NVS) & 1));
+              tc::fence_after();
+              const uint32_t va = smem_u32(vring + (size_t)s * C::HT_BYTES);
+              const uint32_t wa = smem_u32(wtiles + wb * C::WP_BYTES + h * C::WH_BYTES);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {  // 16 tokens per step: two 8-token groups 1024 B apart, next step +2048 B
+                const uint32_t acc = (p | h | ks) != 0;
+                const uint64_t db = tc::smem_desc(wa + ks * 512, 256, 128, tc::SW_NONE);
+                tc::mma_bf16(ucol, tc::smem_desc(va + ks * 2048, C::CH_BYTES, 1024, tc::SW_128), db, ID_UA, acc);
+                if (C::HAS_B)
+                  tc::mma_bf16(ucol + 16, tc::smem_desc(va + 2 * C::CH_BYTES + ks * 2048, C::CH_BYTES, 1024, tc::SW_128), db, ID_UB, acc);
+              }
+              tc::commit(&v_empty[s]);
+              ++jv;
+            }
+            tc::commit(&w_empty[wb]);
+            ++gu;
+          };
+          for (int p = 0; p < NP; ++p) {
+            logits(p);
+            if (p > 0) uprod(p - 1);
+          }
+          uprod(NP - 1);
+          tc::commit(&u_full[n & 1]);
+        }
+      }
     }
+    __syncwarp();
   } else {
     // ==================================================================================== UPDATE ENGINE
     // Every exchange round is  push -> wait -> tensor-core product -> one barrier -> epilogue (= next push):
     // all-gather payloads travel as bf16 straight into the receivers' MMA staging buffers (act[parity], slh[lane],
-    // qbuf[lane]); the LayerNorms are folded into the products that follow them (statistics from the received rows).
+    // the lane's q operand); the LayerNorms are folded into the products that follow them (statistics from the received rows).
     const int utid = tid - 256, uwarp = warp - 8;
     uint32_t round = 0;
     // training: per-(image, iteration) state for the fused backward (SavedLayout, slot_math.cuh); every CTA writes
@@ -597,6 +579,23 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
       if (i < K * SL) {
         const int slot = i / SL, f4 = (i % SL) & ~3;
         const uint32_t lbuf = smem_u32(dst) + (uint32_t)(slot * pitch + (rank * SL + f4) * 2);
+        const uint32_t lbar = smem_u32(&xbar[r & 1]);
+        const uint32_t lo = pack_bf16x2(v0, v1), hi = pack_bf16x2(v2, v3);
+#pragma unroll
+        for (int q = 0; q < CL / 4; ++q) {
+          const int dest = (lane & 3) + 4 * q;
+          st_async_v2(mapa_u32(lbuf, dest), lo, hi, mapa_u32(lbar, dest));
+        }
+      }
+    };
+    // same for the queries, into the K-major UMMA operand [D/8][8 slots][8 features] of every CTA
+    auto quad_push_q = [&](uint32_t r, float val, int i, unsigned char* dst) {
+      const int qb = lane & ~3;
+      const float v0 = __shfl_sync(FULL, val, qb), v1 = __shfl_sync(FULL, val, qb + 1);
+      const float v2 = __shfl_sync(FULL, val, qb + 2), v3 = __shfl_sync(FULL, val, qb + 3);
+      if (i < K * DS) {
+        const int slot = i / DS, f = rank * DS + ((i % DS) & ~3);
+        const uint32_t lbuf = smem_u32(dst) + (uint32_t)((f >> 3) * 128 + slot * 16 + (f & 7) * 2);
         const uint32_t lbar = smem_u32(&xbar[r & 1]);
         const uint32_t lo = pack_bf16x2(v0, v1), hi = pack_bf16x2(v2, v3);
 #pragma unroll
@@ -642,7 +641,7 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
       for (int i = utid; i < K * DS; i += 256) own[i] = __ldg(src + (i / DS) * D + rank * DS + i % DS);
       upd_sync();
     };
-    // q = W_q LN(slots) of lane l for the CTA's slice (slots = slh[l], bf16), all-gathered (times log2 e) into qbuf[l]
+    // q = W_q LN(slots) of lane l for the CTA's slice (slots = slh[l], bf16), all-gathered (times log2 e) into the lane's q operand
     auto q_phase = [&](int l, int q_img, int q_t) {
       for (int job = uwarp; job < NM2 * NKC; job += 8) {
         const int mt = job / NKC, kc = job % NKC;
@@ -664,11 +663,14 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
           if (a.saved != nullptr) saved_at(q_img, q_t)[SL.off_q() + slot * D + rank * DS + dl] = qv;
           val = qv * LOG2E;
         }
-        quad_push(round, val, i, DS, qbuf(l), PITCH);
+        quad_push_q(round, val, i, qop(l));
       }
       xwait(round);
       ++round;
-      if (utid == 0) mbar_arrive(&q_ready[l]);  // the logit warps of lane l may load their q fragments
+      if (utid == 0) {  // the MMA issuer may read lane l's q operand (tcgen05.mma reads it through the async proxy)
+        fence_proxy_async();
+        mbar_arrive(&q_ready[l]);
+      }
     };
 
     // initial queries of both lanes
@@ -696,9 +698,7 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
         for (int i = utid; i < K * QPR; i += 256) {
           const int slot = i / QPR, d = 4 * (i % QPR);
           const int dest = d / DS, dl = d % DS;
-          const float4 xa = *reinterpret_cast<const float4*>(ustage_a + slot * UP + d);
-          const float4 xb4 = *reinterpret_cast<const float4*>(ustage_b + slot * UP + d);
-          const float4 val = make_float4(xa.x + xb4.x, xa.y + xb4.y, xa.z + xb4.z, xa.w + xb4.w);
+          const float4 val = *reinterpret_cast<const float4*>(ustage + slot * UP + d);
           const uint32_t off = (uint32_t)(((rank * KB + slot) * DS + dl) * 4);
           st_async_v4(mapa_u32(lbuf + off, dest), val, mapa_u32(lbar, dest));
         }
@@ -852,25 +852,24 @@ sa_iter_fwd_pipe_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
       PP_T(7);
     }
   }
+  tc::fence_before();
   __syncthreads();
+  if (warp == 7) tc::tmem_dealloc<C::TMEM_COLS>(tmem);
   cluster.sync();  // no CTA leaves while a peer may still address its shared memory
 }
 
-template <int D, int H, int CL, int S, int NL, int KB>
-static int launch_pipe(const IterFwdArgs& a, cudaStream_t stream) {
-  using C = Cfg<D, H, CL, S, NL, KB>;
-  auto kern = sa_iter_fwd_pipe_kernel<D, H, CL, S, NL, KB>;
+
+template <int D, int H, int CL, int NL, int KB, int NKS, int NVS, int NWB>
+static int launch_umma(const IterFwdArgs& a, cudaStream_t stream) {
+  using C = Cfg<D, H, CL, NL, KB, NKS, NVS, NWB>;
+  auto kern = sa_iter_fwd_umma_kernel<D, H, CL, NL, KB, NKS, NVS, NWB>;
   static_assert(C::SMEM_BYTES <= 227 * 1024, "shared memory budget");
   CUtensorMap tm_k, tm_v;
-  if (!make_kv_map(&tm_k, a.k, (long long)a.B * a.N, D, C::TOK) || !make_kv_map(&tm_v, a.v, (long long)a.B * a.N, D, C::TOK)) {
-    set_error("sa_iter_fwd(pipeline): cuTensorMapEncodeTiled failed");
+  const uint64_t rows = (uint64_t)a.B * a.N;
+  if (!tc::make_map_bf16_sw128(&tm_k, a.k, D, rows, (uint64_t)D * 2, C::HT) ||
+      !tc::make_map_bf16_sw128(&tm_v, a.v, D, rows, (uint64_t)D * 2, C::HT)) {
+    set_error("sa_iter_fwd(tcgen05): cuTensorMapEncodeTiled failed");
     return OCRL_E_LAUNCH;
-  }
-  static bool configured = false;
-  if (!configured) {
-    OCRL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    if (CL > 8) OCRL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    configured = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(C::NT);
@@ -883,14 +882,15 @@ static int launch_pipe(const IterFwdArgs& a, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  static int max_clusters = -1;
+  static int max_clusters = -1;  // per instantiation; one device per process
   if (max_clusters < 0) {
+    OCRL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     cfg.gridDim = dim3(CL * 148);
     int n = 0;
     cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
     if (e != cudaSuccess || n <= 0) {
       (void)cudaGetLastError();
-      set_error("sa_iter_fwd(pipeline): cluster size %d with %d B of shared memory cannot be scheduled", CL, C::SMEM_BYTES);
+      set_error("sa_iter_fwd(tcgen05): cluster size %d with %d B of shared memory cannot be scheduled", CL, C::SMEM_BYTES);
       return OCRL_E_SHAPE;
     }
     max_clusters = n;
@@ -908,31 +908,26 @@ static int launch_pipe(const IterFwdArgs& a, cudaStream_t stream) {
   return OCRL_OK;
 }
 
-}  // namespace pipe
+}  // namespace umma
 
-// Returns OCRL_E_SHAPE (without launching) for shapes this kernel does not cover; the caller falls back.
-int sa_iter_fwd_pipe_dispatch(const IterFwdArgs& a, cudaStream_t s) {
+// Returns OCRL_E_SHAPE (without launching) for shapes this kernel does not cover.
+int sa_iter_fwd_umma_dispatch(const IterFwdArgs& a, cudaStream_t s) {
   if (a.K > 8) {
-    set_error("sa_iter_fwd(pipeline): K <= 8");
+    set_error("sa_iter_fwd(tcgen05): K <= 8");
     return OCRL_E_SHAPE;
   }
   if (a.D == 192 && a.H == 192) {
-    if (a.K <= 6) {  // six slot rows in the exchange / staging buffers leave room for an eighth ring stage
-      if (a.lanes == 2) return pipe::launch_pipe<192, 192, 8, 8, 2, 6>(a, s);
-      return pipe::launch_pipe<192, 192, 8, 8, 3, 6>(a, s);
+    if (a.K <= 6) {
+      if (a.lanes == 3) return umma::launch_umma<192, 192, 8, 3, 6, 2, 2, 1>(a, s);
+      return umma::launch_umma<192, 192, 8, 2, 6, 2, 2, 2>(a, s);
     }
-    return pipe::launch_pipe<192, 192, 8, 7, 3, 8>(a, s);
+    return umma::launch_umma<192, 192, 8, 2, 8, 2, 2, 1>(a, s);
   }
-  if (a.D == 64 && a.H == 128) {  // the "Slot-Attention (small)" configuration: D = 64, H_mlp = 128
-    // The whole weight set is 88 KB here, so clusters of four are enough: 33 of them fit (132 SMs against 120 with
-    // clusters of eight) and the seven updates per image stop being the serial bottleneck of a 15-cluster grid.
-    // One image is slower on four CTAs than on eight, so small batches stay on clusters of eight
-    // (B = 64, T = 7: 146 against 191 us; B = 256: 545 against 653 us; B = 16: 145 against 119 us).
-    if (a.lanes == 2 || (a.lanes == 0 && a.B >= 48)) return pipe::launch_pipe<64, 128, 4, 16, 2, 8>(a, s);
-    if (a.K <= 6) return pipe::launch_pipe<64, 128, 8, 16, 3, 6>(a, s);
-    return pipe::launch_pipe<64, 128, 8, 16, 3, 8>(a, s);
+  if (a.D == 64 && a.H == 128) {  // the "Slot-Attention (small)" configuration
+    if (a.B >= 48 && a.lanes != 3) return umma::launch_umma<64, 128, 4, 2, 8, 4, 4, 2>(a, s);
+    return umma::launch_umma<64, 128, 8, 3, 8, 4, 4, 2>(a, s);
   }
-  set_error("sa_iter_fwd(pipeline): D=%d H=%d not instantiated", a.D, a.H);
+  set_error("sa_iter_fwd(tcgen05): D=%d H=%d not instantiated", a.D, a.H);
   return OCRL_E_SHAPE;
 }
 

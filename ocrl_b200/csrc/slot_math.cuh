@@ -34,6 +34,8 @@ struct IterFwdArgs {
   float eps, ln_eps;
   long long* trace;  // optional: clock64() at phase boundaries of CTA 0 (development aid), else null
   const __nv_bfloat16* wb16;  // optional bf16 copies [wq | w_ih | w_hh | w1 | w2] for the tensor-core slot update
+  int max_clusters = 0;  // ocrl_sa_launch_opts: cap on the resident clusters of the persistent kernels (0 = launcher's choice)
+  int lanes = 0;         // ocrl_sa_launch_opts: images in flight per cluster (0 = default)
 };
 
 // out[j*ldo + out_off + row] = dot(W[row0+row, 0:L], vec[j, 0:L]) for row < nrows, j < KP.

@@ -7,6 +7,8 @@ token LayerNorm+MLP of ``SlotAttentionEncoder.forward`` (slot_attn.py:151).
 """
 from __future__ import annotations
 
+import contextlib
+import contextvars
 import ctypes
 import os
 from typing import Dict, Optional, Tuple
@@ -46,6 +48,26 @@ class _timed:
             e1.record()
             KERNEL_EVENTS.append((self.name, self.e0, e1))
         return False
+
+
+# Launch options of the iteration loop for the calls made inside a ``launch_options(...)`` block (context-local, so
+# threads and asyncio tasks do not see each other's setting).  An explicit ``opts=`` argument wins.
+_LAUNCH_OPTS: contextvars.ContextVar = contextvars.ContextVar("ocrl_sa_launch_opts", default=None)
+
+
+@contextlib.contextmanager
+def launch_options(**kw):
+    """``with launch_options(variant="pipe", max_clusters=8): ...`` -- see ``abi.launch_opts`` / ocrl_sa_launch_opts."""
+    tok = _LAUNCH_OPTS.set(abi.launch_opts(**kw))
+    try:
+        yield
+    finally:
+        _LAUNCH_OPTS.reset(tok)
+
+
+def last_kernel() -> str:
+    """Which kernel the last ``iterate`` of this thread launched: tcgen05 | pipe | cluster_tc | ffma."""
+    return abi.lib().ocrl_sa_last_kernel().decode()
 
 
 def _math_mode(dt_code: int) -> int:
@@ -130,8 +152,10 @@ def kv_project(x: Tensor, p: Dict[str, Tensor], *, kv: str = "fp32", enc: Option
 
 def iterate(k: Tensor, v: Tensor, slots0: Tensor, p: Dict[str, Tensor], num_iterations: int, *,
             epsilon: float = 1e-8, ln_eps: float = 1e-5, want_attn: bool = True, save: bool = False,
-            _workspace: Optional[Tensor] = None):
+            _workspace: Optional[Tensor] = None, opts: Optional[abi.LaunchOpts] = None):
     """The fused T-iteration loop.  k, v: [B,N,D] fp32 or bf16; slots0 [B,K,D].
+    ``opts``: ``abi.launch_opts(...)`` (kernel variant, cluster cap, lanes, strict); default: the enclosing
+    ``launch_options`` block, else the library's own choice.
     Returns (slots, attn_vis or None, saved or None)."""
     _require_cuda(k, "iterate")
     B, N, D = k.shape
@@ -152,19 +176,23 @@ def iterate(k: Tensor, v: Tensor, slots0: Tensor, p: Dict[str, Tensor], num_iter
     if _workspace is None and dims.math_mode == abi.MATH_TENSOR:  # bf16 weight copies for the tensor-core slot update
         fwd_ws, _, _ = abi.query_workspace(dims)
         _workspace = torch.empty(fwd_ws, device=k.device, dtype=torch.uint8)
+    if opts is None:
+        opts = _LAUNCH_OPTS.get()
     with _timed("sa_iter_fwd"):
-        abi.check(abi.lib().ocrl_sa_iter_fwd(ctypes.byref(dims), abi.ptr(k), abi.ptr(v), abi.ptr(slots0),
-                                             ctypes.byref(w), abi.ptr(slots), abi.ptr(attn), abi.ptr(saved),
-                                             abi.ptr(_workspace), abi.stream_ptr()), "ocrl_sa_iter_fwd")
+        abi.check(abi.lib().ocrl_sa_iter_fwd_ex(ctypes.byref(dims), abi.ptr(k), abi.ptr(v), abi.ptr(slots0),
+                                                ctypes.byref(w), abi.ptr(slots), abi.ptr(attn), abi.ptr(saved),
+                                                abi.ptr(_workspace), ctypes.byref(opts) if opts is not None else None,
+                                                abi.stream_ptr()), "ocrl_sa_iter_fwd")
     return slots, attn, saved
 
 
 def slot_attention(inputs: Tensor, slots0: Tensor, p: Dict[str, Tensor], num_iterations: int, *,
                    epsilon: float = 1e-8, kv: str = "fp32", enc: Optional[Dict[str, Tensor]] = None,
-                   pos_table: Optional[Tensor] = None, want_attn: bool = True) -> Tuple[Tensor, Optional[Tensor]]:
+                   pos_table: Optional[Tensor] = None, want_attn: bool = True,
+                   opts: Optional[abi.LaunchOpts] = None) -> Tuple[Tensor, Optional[Tensor]]:
     """Inference-only SlotAttention.forward (no autograd graph)."""
     k, v, _ = kv_project(inputs, p, kv=kv, enc=enc, pos_table=pos_table)
-    slots, attn, _ = iterate(k, v, slots0, p, num_iterations, epsilon=epsilon, want_attn=want_attn)
+    slots, attn, _ = iterate(k, v, slots0, p, num_iterations, epsilon=epsilon, want_attn=want_attn, opts=opts)
     return slots, attn
 
 
@@ -186,6 +214,7 @@ class SlotAttentionFunction(torch.autograd.Function):
         return slots, attn
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, d_slots, d_attn):
         inputs, k, v, saved, *params = ctx.saved_tensors
         T, epsilon, kv, K = ctx.meta
@@ -198,6 +227,9 @@ class SlotAttentionFunction(torch.autograd.Function):
         dev = k.device
         _, bwd_ws, _ = abi.query_workspace(dims)
         ws = torch.empty(max(bwd_ws, 16), device=dev, dtype=torch.uint8)
+        if B == 0:  # an empty shard (uneven dp.shard): the kernels do not run, every gradient is exactly zero
+            return (torch.zeros_like(inputs), torch.zeros(0, K, D, device=dev), None, None, None,
+                    *[torch.zeros_like(p[n]) for n in SA_PARAM_ORDER])
         dk = torch.empty(B, N, D, device=dev, dtype=torch.float32)
         dv = torch.empty(B, N, D, device=dev, dtype=torch.float32)
         d_slots0 = torch.empty(B, K, D, device=dev, dtype=torch.float32)

@@ -8,35 +8,17 @@ replays it: same kernels, same results, one launch.
 """
 from __future__ import annotations
 
-import contextlib
-import os
-
 import torch
 
-
-@contextlib.contextmanager
-def _iteration_cluster_cap(n):
-    """Caps the cluster count of the iteration kernel for the launches made inside the block (the launcher reads
-    ``OCRL_SA_PC_CLUSTERS`` when it sizes the grid; a captured graph keeps the grid it was captured with)."""
-    if n is None:
-        yield
-        return
-    old = os.environ.get("OCRL_SA_PC_CLUSTERS")
-    os.environ["OCRL_SA_PC_CLUSTERS"] = str(int(n))
-    try:
-        yield
-    finally:
-        if old is None:
-            os.environ.pop("OCRL_SA_PC_CLUSTERS", None)
-        else:
-            os.environ["OCRL_SA_PC_CLUSTERS"] = old
+from . import functional as F
 
 
 class GraphedEncoder:
     def __init__(self, ocr, example_obs: torch.Tensor, with_masks: bool = False, warmup: int = 3,
                  iter_clusters: int | None = None):
         """iter_clusters: upper bound on the clusters of the iteration kernel in the captured graph (None: the
-        launcher's own choice, lowest latency of one replay)."""
+        launcher's own choice, lowest latency of one replay); passed as ocrl_sa_launch_opts.max_clusters for the
+        launches made during the capture (a graph keeps the grid it was captured with)."""
         assert example_obs.is_cuda, "GraphedEncoder captures a CUDA graph"
         self._ocr = ocr
         self._with_masks = with_masks
@@ -49,7 +31,7 @@ class GraphedEncoder:
         torch.cuda.current_stream(example_obs.device).wait_stream(side)
         torch.cuda.synchronize(example_obs.device)
         self.graph = torch.cuda.CUDAGraph()
-        with _iteration_cluster_cap(iter_clusters), torch.cuda.graph(self.graph), torch.no_grad():
+        with F.launch_options(max_clusters=iter_clusters or 0), torch.cuda.graph(self.graph), torch.no_grad():
             self.static_out = self._call()
 
     def _call(self):

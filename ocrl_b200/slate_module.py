@@ -71,7 +71,8 @@ class SLATE_Module(nn.Module):
         self._enc = SlotAttnCNNEncoder(obs_size, obs_channels, cnn_hsize)
         self._enc_pos = PositionalEmbedding(obs_size, cnn_hsize)
         self._slotattn = SlotAttentionEncoder(sa.num_iterations, num_slots, cnn_hsize, slot_size,
-                                              sa.mlp_hidden_size, sa.pos_channels, sa.num_slot_heads)
+                                              sa.mlp_hidden_size, sa.pos_channels, sa.num_slot_heads,
+                                              kv_dtype=getattr(sa, "kv_dtype", None))  # optional key of this implementation
         if self._use_bcdec:
             self._dec = BroadCastDecoder(obs_size, obs_channels, cnn_hsize, slot_size)
         self._slotproj = linear(slot_size, d_model, bias=False)

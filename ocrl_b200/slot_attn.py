@@ -26,7 +26,11 @@ def default_kv_dtype() -> str:
 
 
 class SlotAttention(nn.Module):
-    def __init__(self, num_iterations, num_slots, input_size, slot_size, mlp_hidden_size, heads, epsilon=1e-8):
+    def __init__(self, num_iterations, num_slots, input_size, slot_size, mlp_hidden_size, heads, epsilon=1e-8,
+                 kv_dtype=None, launch_opts=None):
+        """Reference signature (slot_attn.py:10-19) plus two keyword-only extras of this implementation:
+        ``kv_dtype`` 'fp32' (exact-parity mode) | 'bf16' (bf16 k/v, tensor cores); None reads OCRL_KV_DTYPE once, here;
+        ``launch_opts`` an ``abi.launch_opts(...)`` applied to every forward of this module (None: library default)."""
         super().__init__()
         self.num_iterations = num_iterations
         self.num_slots = num_slots
@@ -35,7 +39,10 @@ class SlotAttention(nn.Module):
         self.mlp_hidden_size = mlp_hidden_size
         self.epsilon = epsilon
         self.num_heads = heads
-        self.kv_dtype = default_kv_dtype()
+        self.kv_dtype = default_kv_dtype() if kv_dtype is None else kv_dtype
+        if self.kv_dtype not in ("fp32", "bf16"):
+            raise ValueError(f"kv_dtype must be fp32 or bf16, got {self.kv_dtype}")
+        self.launch_opts = launch_opts
 
         self.norm_inputs = nn.LayerNorm(input_size)
         self.norm_slots = nn.LayerNorm(slot_size)
@@ -85,7 +92,7 @@ class SlotAttention(nn.Module):
         if not needs_grad:
             with torch.no_grad():
                 return F.slot_attention(inputs, slots, p, self.num_iterations, epsilon=self.epsilon,
-                                        kv=self.kv_dtype, enc=_enc, pos_table=_pos_table)
+                                        kv=self.kv_dtype, enc=_enc, pos_table=_pos_table, opts=self.launch_opts)
         assert _enc is None and _pos_table is None, "fused token stage is an inference-only path"
         return F.SlotAttentionFunction.apply(inputs, slots, self.num_iterations, self.epsilon, self.kv_dtype,
                                              *[p[n] for n in F.SA_PARAM_ORDER])
@@ -93,7 +100,7 @@ class SlotAttention(nn.Module):
 
 class SlotAttentionEncoder(nn.Module):
     def __init__(self, num_iterations, num_slots, input_channels, slot_size, mlp_hidden_size, pos_channels,
-                 num_heads):
+                 num_heads, kv_dtype=None):
         super().__init__()
         self.num_iterations = num_iterations
         self.num_slots = num_slots
@@ -113,7 +120,7 @@ class SlotAttentionEncoder(nn.Module):
         nn.init.xavier_uniform_(self.slot_mu)
         nn.init.xavier_uniform_(self.slot_log_sigma)
         self.slot_attention = SlotAttention(num_iterations, num_slots, input_channels, slot_size, mlp_hidden_size,
-                                            num_heads)
+                                            num_heads, kv_dtype=kv_dtype)
 
     def _enc_params(self):
         return {"layer_norm.weight": self.layer_norm.weight, "layer_norm.bias": self.layer_norm.bias,

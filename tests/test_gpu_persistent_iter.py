@@ -1,12 +1,11 @@
-"""GPU parity of the persistent-cluster iteration kernels (sa_iter_fwd_pipe.cu: two-engine pipeline, the default
-for K <= 8 / D = H = 192 in bf16 mode; sa_iter_fwd_pc.cu: single-engine form) against the CPU oracle.
+"""GPU parity of the persistent-cluster iteration kernels (sa_iter_fwd_umma.cu: tcgen05 token pass, the default for
+K <= 8 / D = H = 192 or D = 64, H = 128 in bf16 mode; sa_iter_fwd_pipe.cu: its mma.sync predecessor) against the CPU
+oracle.  Variants are selected per call through ocrl_sa_launch_opts (no environment variables).
 
 The kernels are fed exactly bf16-representable k, v, so the comparison measures only the kernels' own arithmetic
 (bf16 q / weights / slot-update activations on tensor cores, fp32 accumulate): 2e-2 relative, the north-star bf16
 tolerance.  Shapes cover ragged token counts, batches that do not fill the clusters' image lanes evenly, K = 1..8
 and T = 1..7."""
-import os
-
 import pytest
 import torch
 
@@ -15,9 +14,9 @@ from tests.golden_io import load_case, rel_err
 
 pytestmark = pytest.mark.gpu
 BF16_TOL = 2e-2
-VARIANTS = {"pipe": {"OCRL_SA_PIPE": "0"}, "pipe_2lanes_s4": {"OCRL_SA_PIPE": "1"},
-            "single_engine": {"OCRL_SA_PIPE": "-1", "OCRL_SA_PC": "0"},
-            "single_engine_cl16": {"OCRL_SA_PIPE": "-1", "OCRL_SA_PC": "1"}}
+VARIANTS = {"tcgen05": dict(variant="tcgen05", strict=True), "tcgen05_3lanes": dict(variant="tcgen05", lanes=3, strict=True),
+            "tcgen05_2clusters": dict(variant="tcgen05", max_clusters=2, strict=True),
+            "pipe": dict(variant="pipe", strict=True), "pipe_2lanes": dict(variant="pipe", lanes=2, strict=True)}
 
 
 def _cuda(d):
@@ -25,10 +24,12 @@ def _cuda(d):
 
 
 @pytest.fixture(params=sorted(VARIANTS))
-def variant(request, monkeypatch):
-    for k, v in VARIANTS[request.param].items():
-        monkeypatch.setenv(k, v)
-    return request.param
+def variant(request):
+    from ocrl_b200 import functional as F
+
+    with F.launch_options(**VARIANTS[request.param]):
+        yield request.param
+    assert F.last_kernel() == request.param.split("_")[0]  # strict: the requested kernel ran, nothing fell back
 
 
 def _run(kb, vb, s0, p, T, eps=1e-8):
@@ -104,7 +105,8 @@ def test_argmax_masks_against_oracle_report_flip_rate():
     assert not (flips & clear).any()
 
 
-def test_saved_state_matches_the_per_image_kernel(monkeypatch):
+@pytest.mark.parametrize("variant_name", ["tcgen05", "pipe"])
+def test_saved_state_matches_the_per_image_kernel(variant_name):
     """Training: the per-(image, iteration) state the pipeline kernel keeps for the fused backward agrees with the
     per-image cluster kernel's (same layout, SavedLayout in slot_math.cuh), and the gradients computed from it agree."""
     from ocrl_b200 import functional as F
@@ -113,11 +115,13 @@ def test_saved_state_matches_the_per_image_kernel(monkeypatch):
     p = _cuda(g["p"])
     k_ref, v_ref = so.kv_project(g["in"]["inputs"], g["p"])
     kb, vb, s0 = k_ref.bfloat16().cuda(), v_ref.bfloat16().cuda(), g["in"]["slots0"].cuda()
-    monkeypatch.setenv("OCRL_SA_PIPE", "0")
-    s_new, a_new, saved_new = F.iterate(kb, vb, s0, p, meta["T"], epsilon=meta["eps"], save=True)
-    monkeypatch.setenv("OCRL_SA_PIPE", "-1")
-    monkeypatch.setenv("OCRL_SA_PC", "-1")
-    s_old, a_old, saved_old = F.iterate(kb, vb, s0, p, meta["T"], epsilon=meta["eps"], save=True)
+    from ocrl_b200 import abi
+
+    s_new, a_new, saved_new = F.iterate(kb, vb, s0, p, meta["T"], epsilon=meta["eps"], save=True,
+                                        opts=abi.launch_opts(variant=variant_name, strict=True))
+    s_old, a_old, saved_old = F.iterate(kb, vb, s0, p, meta["T"], epsilon=meta["eps"], save=True,
+                                        opts=abi.launch_opts(variant="cluster_tc", strict=True))
+    assert F.last_kernel() == "cluster_tc"
     torch.cuda.synchronize()
     assert rel_err(s_new.cpu(), s_old.cpu()) < BF16_TOL
     assert saved_new.shape == saved_old.shape
@@ -145,7 +149,7 @@ def test_small_slot_attention_configuration(B, N, K, T):
     assert torch.allclose(a.sum(-1), torch.ones(B, N), atol=1e-4)
 
 
-def test_small_configuration_cluster_sizes_agree(monkeypatch):
+def test_small_configuration_cluster_sizes_agree():
     """D = 64: batches of 48 and more run on clusters of four (two lanes), smaller ones on clusters of eight.  Same
     arithmetic, different split: outputs and the saved training state agree to summation order."""
     from ocrl_b200 import functional as F
@@ -157,10 +161,11 @@ def test_small_configuration_cluster_sizes_agree(monkeypatch):
     s0 = torch.randn(B, K, 64, generator=gen).cuda()
     k_ref, v_ref = so.kv_project(x, {k_: v_.cpu() for k_, v_ in p.items()})
     kb, vb = k_ref.bfloat16().cuda(), v_ref.bfloat16().cuda()
-    monkeypatch.setenv("OCRL_SA_PIPE", "0")   # B >= 48: clusters of four
-    s4, a4, saved4 = F.iterate(kb, vb, s0, p, T, save=True)
-    monkeypatch.setenv("OCRL_SA_PIPE", "1")   # clusters of eight
-    s8, a8, saved8 = F.iterate(kb, vb, s0, p, T, save=True)
+    from ocrl_b200 import abi
+
+    s4, a4, saved4 = F.iterate(kb, vb, s0, p, T, save=True, opts=abi.launch_opts(strict=True))  # B >= 48: clusters of four
+    s8, a8, saved8 = F.iterate(kb, vb, s0, p, T, save=True, opts=abi.launch_opts(lanes=3, strict=True))  # clusters of eight
+    assert F.last_kernel() == "tcgen05"
     torch.cuda.synchronize()
     assert rel_err(s4.cpu(), s8.cpu()) < 2e-3 and rel_err(a4.cpu(), a8.cpu()) < 2e-3
     used = 8 * K * 64 + K * 128 + K
