@@ -4,7 +4,8 @@
 // Structure as in sa_iter_fwd_pipe.cu: a cluster of CL CTAs works on NL images at a time ("lanes"); every CTA
 // streams its share of the tokens (PASS engine, warps 0-7) while warps 8-15 run the slot update of another lane
 // (UPDATE engine: reduce-scatter over the cluster, GRU, residual MLP, next q; weights stationary in shared memory).
-// The pass engine here is
+// The slot-update weights live in TENSOR MEMORY (A operand of tcgen05.mma, 2 x 96 columns of bf16 pairs), which
+// leaves the shared memory to the k/v ring: seven 24 KB slots instead of four.  The pass engine is
 //   * warp 4 / warp 6, one lane each: TMA producers of the k ring and the v ring (64-token half tiles,
 //     [D/64][64 rows][128 B] with the 128-byte swizzle = the canonical UMMA layouts: K-major for k, MN-major for v);
 //   * warp 5, one lane: issues  logits[64 x 8] = k_half . q^T  (M = 64; the two halves of a 128-token pair land in
@@ -13,7 +14,8 @@
 //     slots and signals the softmax warps;
 //   * warps 0-3, one token per thread: tcgen05.ld of the token's logits, K-way softmax in registers (no shuffles),
 //     attn_vis store in the last iteration, w = a + eps rounded to bf16 into the B-operand tile of the U product.
-// q arrives from the update engine already in the UMMA K-major layout ([D/8][8 slots][8] bf16).
+// The update engine's matrix-vector products are tcgen05.mma as well: D[weight rows x slots] = W (tensor memory) x
+// activations (shared memory, K-major [features/8][8 slots][8] bf16 -- the layout the all-gathers write directly).
 #include "pc_common.cuh"
 #include "umma_common.cuh"
 
@@ -22,54 +24,52 @@ namespace umma {
 
 using namespace pc;
 
+#ifndef TRACE_OP
+#define TRACE_OP 2
+#endif
+
 template <int D_, int H_, int CL_, int NL_, int KB_, int NKS_, int NVS_, int NWB_>
 struct Cfg {
   // NL image lanes per cluster; KB rows in the slot-indexed buffers; NKS / NVS ring slots for k / v half tiles;
   // NWB buffers for the softmax weights of a 128-token pair
   static constexpr int D = D_, H = H_, CL = CL_, NL = NL_, KB = KB_, NKS = NKS_, NVS = NVS_, NWB = NWB_;
-  static constexpr int KP = 8, NT = 512, HT = 64, NCH = D / 64;
-  static constexpr int PITCH = D * 2 + 16, PITCHH = H * 2 + 16;
+  static constexpr int NT = 512, HT = 64, NCH = D / 64;
   static constexpr int LX = D > H ? D : H;
-  static constexpr int PITCHX = LX * 2 + 16;
   static constexpr int CH_BYTES = HT * 128, HT_BYTES = NCH * CH_BYTES;  // one 64-wide feature chunk / one half tile
   static constexpr int WH_BYTES = 2048, WP_BYTES = 2 * WH_BYTES;        // w tile of a half ([8][16 slots][8] bf16) / a pair
-  static constexpr int QOP_BYTES = D * 16;                              // q operand [D/8][8 slots][8] bf16
+  static constexpr int OPD_BYTES = D * 16, OPX_BYTES = LX * 16;         // activation operands [features/8][8 slots][8] bf16
   static constexpr int DS = D / CL, HS = H / CL;
-  static constexpr int NMG = (3 * DS + 15) / 16, NM1 = (HS + 15) / 16, NM2 = (DS + 15) / 16, NKC = 4;
+  // weight blocks in tensor memory (row = lane): X = W_ih (3 DS rows) | W1' (HS) | W2 (DS);  Y = W_hh (3 DS) | Wq' (DS)
+  static constexpr int RX = 3 * DS + HS + DS, RY = 3 * DS + DS;
   static constexpr int UP = D + 4;
   static constexpr int MA = NCH >= 2 ? 128 : 64;   // U product, features [0, 128) (or all 64)
   static constexpr bool HAS_B = NCH == 3;          // second U product, features [128, 192)
-  static_assert(D % 64 == 0 && H % 64 == 0 && DS % 4 == 0 && HS % 4 == 0 && NCH <= 3, "shape");
-  // tensor memory columns: two logit buffers, two U accumulators (features 0-127 | 128-191)
-  static constexpr uint32_t COL_LG = 0, COL_U = 32, TMEM_COLS = 128;
+  static_assert(D % 64 == 0 && H % 64 == 0 && DS % 4 == 0 && HS % 4 == 0 && NCH <= 3 && RX <= 128 && RY <= 128, "shape");
+  // Tensor memory columns: two logit buffers, two U accumulators (features 0-127 | 128-191), the update engine's two
+  // accumulators, the weight blocks (a column holds two bf16: K features take K / 2 columns).  (No need to spread a
+  // product over several accumulators: back-to-back MMAs into the same columns issue at full rate, scripts/umma_time.cu.)
+  static constexpr uint32_t COL_LG = 0, LG_STRIDE = 16, COL_U = 32, U_STRIDE = 32, U_B = 16, COL_GI = 96, COL_GH = 112;
+  static constexpr uint32_t COL_WX = 128, COL_WY = COL_WX + LX / 2, TMEM_COLS = 512;
+  static_assert(COL_WY + D / 2 <= 512, "tensor memory");
 
   static constexpr int OFF_KRING = 0;
   static constexpr int OFF_VRING = OFF_KRING + NKS * HT_BYTES;
   static constexpr int OFF_WT = OFF_VRING + NVS * HT_BYTES;
-  static constexpr int OFF_WIH = OFF_WT + NWB * WP_BYTES;
-  static constexpr int OFF_WHH = OFF_WIH + 3 * DS * PITCH;
-  static constexpr int OFF_W1 = OFF_WHH + 3 * DS * PITCH;
-  static constexpr int OFF_W2 = OFF_W1 + HS * PITCH;
-  static constexpr int OFF_WQ = OFF_W2 + DS * PITCHH;
-  static constexpr int OFF_ZROW = OFF_WQ + DS * PITCH;
-  static constexpr int OFF_BIAS = (OFF_ZROW + PITCHX + 15) & ~15;  // (the LayerNorm affine parameters are folded into W1', Wq')
+  static constexpr int OFF_BIAS = OFF_WT + NWB * WP_BYTES;  // (the LayerNorm affine parameters are folded into W1', Wq')
   // fp32 constants: b_ih[3DS] b_hh[3DS] b1'[HS] b2[DS] c1[HS] cq[DS] bq'[DS] + LayerNorm stats mean[8] rstd[8]
   static constexpr int NCONST = 9 * DS + 2 * HS + 16;
   static constexpr int XBUF_BYTES = KB * D * 4 + 32 * CL;          // R1 receive buffer (fp32 partial sums), single
   static constexpr int OFF_XBUF = (OFF_BIAS + NCONST * 4 + 15) & ~15;
-  static constexpr int OFF_ACT = OFF_XBUF + XBUF_BYTES;            // bf16 all-gather targets, by round parity
-  static constexpr int P_ROWS = (3 * NMG > NKC * (NM1 > NM2 ? NM1 : NM2)) ? 3 * NMG * 16 : NKC * (NM1 > NM2 ? NM1 : NM2) * 16;
-  static constexpr int OFF_UST = OFF_ACT + 2 * KB * PITCHX;        // U staging (pass -> update hand-off)
-  static constexpr int OFF_LANE = (OFF_UST + KB * UP * 4 + 127) & ~127;  // per lane: q operand, slots (bf16), own slice (fp32)
-  static constexpr int LANE_BYTES = (QOP_BYTES + KB * PITCH + KB * DS * 4 + 127) & ~127;
-  // rows KB..7 of the slot-indexed buffers are read as (ignored) padding columns of the MMAs, so plain data follows
-  // them: the MMA partial outputs and the token sums close the list
-  static constexpr int OFF_P = (OFF_LANE + NL * LANE_BYTES + 15) & ~15;
-  static constexpr int OFF_SRED = OFF_P + P_ROWS * 32;             // [4][8] token sums of the softmax warps
+  static constexpr int OFF_ACT = (OFF_XBUF + XBUF_BYTES + 127) & ~127;  // bf16 all-gather targets (operands), by round parity
+  static constexpr int OFF_UST = OFF_ACT + 2 * OPX_BYTES;          // U staging (pass -> update hand-off)
+  static constexpr int OFF_LANE = (OFF_UST + KB * UP * 4 + 127) & ~127;  // per lane: q operand, slots operand, own slice (fp32)
+  static constexpr int LANE_BYTES = (2 * OPD_BYTES + KB * DS * 4 + 127) & ~127;
+  static constexpr int OFF_P = (OFF_LANE + NL * LANE_BYTES + 15) & ~15;   // product outputs, fp32 [2][128 rows][8 slots]
+  static constexpr int OFF_SRED = OFF_P + 2 * 128 * 32;            // [4][8] token sums of the softmax warps
   // k_full k_empty [NKS] v_full v_empty [NVS] lg_full lg_empty w_full w_empty u_full u_accfree [2 each] xbar[2]
-  // u_ready u_free q_ready[NL]
+  // u_ready u_free ubar[2] q_ready[NL]
   static constexpr int OFF_BAR = OFF_SRED + 128;
-  static constexpr int NBAR = 2 * NKS + 2 * NVS + 12 + 2 + 2 + NL;
+  static constexpr int NBAR = 2 * NKS + 2 * NVS + 12 + 2 + 4 + NL;
   static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
   static constexpr int SMEM_BYTES = OFF_TMEM + 16;
 };
@@ -80,8 +80,7 @@ template <int D, int H, int CL, int NL, int KB, int NKS, int NVS, int NWB>
 __global__ void __launch_bounds__(512, 1)
 sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v) {
   using C = Cfg<D, H, CL, NL, KB, NKS, NVS, NWB>;
-  constexpr int PITCH = C::PITCH, PITCHH = C::PITCHH, PITCHX = C::PITCHX, DS = C::DS, HS = C::HS;
-  constexpr int NMG = C::NMG, NM1 = C::NM1, NM2 = C::NM2, NKC = C::NKC, UP = C::UP, HT = C::HT, NCH = C::NCH;
+  constexpr int DS = C::DS, HS = C::HS, UP = C::UP, HT = C::HT, NCH = C::NCH;
   constexpr float LOG2E = 1.4426950408889634f;
 
   extern __shared__ __align__(1024) unsigned char sm[];  // swizzled TMA tiles need 1024-byte alignment
@@ -97,12 +96,6 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
   unsigned char* kring = sm + C::OFF_KRING;
   unsigned char* vring = sm + C::OFF_VRING;
   unsigned char* wtiles = sm + C::OFF_WT;
-  unsigned char* s_wih = sm + C::OFF_WIH;
-  unsigned char* s_whh = sm + C::OFF_WHH;
-  unsigned char* s_w1 = sm + C::OFF_W1;
-  unsigned char* s_w2 = sm + C::OFF_W2;
-  unsigned char* s_wq = sm + C::OFF_WQ;
-  unsigned char* s_zrow = sm + C::OFF_ZROW;
   float* s_bias = reinterpret_cast<float*>(sm + C::OFF_BIAS);
   const float* s_bih = s_bias;
   const float* s_bhh = s_bias + 3 * DS;
@@ -114,13 +107,16 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
   float* s_mean = s_bias + 9 * DS + 2 * HS;  // LayerNorm statistics of the round in flight
   float* s_rstd = s_mean + 8;
   unsigned char* xbuf = sm + C::OFF_XBUF;
-  auto act = [&](uint32_t r) { return sm + C::OFF_ACT + (r & 1) * (KB * PITCHX); };  // bf16 [KB][PITCHX]
-  float* P = reinterpret_cast<float*>(sm + C::OFF_P);
+  auto act = [&](uint32_t r) { return sm + C::OFF_ACT + (r & 1) * C::OPX_BYTES; };  // operand [LX/8][8 slots][8] bf16
+  float* P_GI = reinterpret_cast<float*>(sm + C::OFF_P);  // [128 rows of block X][8 slots]
+  float* P_GH = P_GI + 128 * 8;                           // [128 rows of block Y][8 slots]
   float* ustage = reinterpret_cast<float*>(sm + C::OFF_UST);
   float* sred = reinterpret_cast<float*>(sm + C::OFF_SRED);
   auto qop = [&](int l) { return sm + C::OFF_LANE + l * C::LANE_BYTES; };
-  auto slh_hi = [&](int l) { return sm + C::OFF_LANE + l * C::LANE_BYTES + C::QOP_BYTES; };
-  auto own_of = [&](int l) { return reinterpret_cast<float*>(sm + C::OFF_LANE + l * C::LANE_BYTES + C::QOP_BYTES + KB * PITCH); };
+  auto slh_hi = [&](int l) { return sm + C::OFF_LANE + l * C::LANE_BYTES + C::OPD_BYTES; };  // the lane's slots, operand layout
+  auto own_of = [&](int l) { return reinterpret_cast<float*>(sm + C::OFF_LANE + l * C::LANE_BYTES + 2 * C::OPD_BYTES); };
+  // byte offset of (slot, feature f) inside an operand buffer
+  auto opnd_off = [](int slot, int f) { return (f >> 3) * 128 + slot * 16 + (f & 7) * 2; };
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
   uint64_t* k_full = bars;
   uint64_t* k_empty = k_full + NKS;
@@ -135,7 +131,8 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
   uint64_t* xbar = u_accfree + 2;
   uint64_t* u_ready = xbar + 2;
   uint64_t* u_free = u_ready + 1;
-  uint64_t* q_ready = u_free + 1;
+  uint64_t* ubar = u_free + 1;         // [2] a product of the update engine is complete ([1]: W_hh h, which overlaps others)
+  uint64_t* q_ready = ubar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + C::OFF_TMEM);
 
   // ------------------------------------------------------------------ work assignment (NL lanes per cluster)
@@ -183,37 +180,63 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
   const int NP = (TP + 1) / 2;                       // 128-token pairs
   const int total_ht = total_ops * TP;
 
-  // One elected lane per ring: slot (j % NS) <- half tile j of the CTA's stream (ops in stream order).
+  // TMA producers (warp 4: k ring, warp 6: v ring).  The whole warp walks the half-tile stream of the CTA (ops in
+  // stream order) so that addresses and coordinates stay warp-uniform; one elected lane issues.  All per-tile state is
+  // kept incrementally -- an integer division costs the issuing warp more than the three TMA instructions.
   // L2 policy: tiles of iterations 0..T-2 are read again by the next pass (evict_last), the final pass's are dead
   // afterwards (evict_first).  For the first pass of an image the half tile `PFD` further on is prefetched into L2
   // at the rate tiles are consumed.
   const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
   constexpr int PFD = 6;
-  auto issue_half = [&](int j, bool is_v) {
-    const int n = j / TP, tile = j - n * TP;
-    int l, c;
-    op_of(n, l, c);
-    const int t = c % T;
-    const int row0 = image_of(l, c / T) * N + (tile0 + tile) * HT;
-    const uint64_t pol = (t == T - 1) ? pol_drop : pol_keep;
-    const int s = j % (is_v ? NVS : NKS);
-    unsigned char* dst = (is_v ? vring : kring) + (size_t)s * C::HT_BYTES;
-    uint64_t* bar = is_v ? &v_full[s] : &k_full[s];
-    const CUtensorMap* tm = is_v ? &tm_v : &tm_k;
-    mbar_expect_tx(bar, (uint32_t)C::HT_BYTES);
+  struct OpInfo { int row_base; int cold; uint64_t pol; };
+  auto op_info = [&](int n) {
+    OpInfo o;
+    o.row_base = 0; o.cold = 0; o.pol = pol_keep;
+    if (n < total_ops) {
+      int l, c;
+      op_of(n, l, c);
+      const int t = c % T;
+      o.row_base = image_of(l, c / T) * N + tile0 * HT;
+      o.cold = (t == 0);
+      o.pol = (t == T - 1) ? pol_drop : pol_keep;
+    }
+    return o;
+  };
+  const bool prod_v = (warp == 6);
+  const int PNS = prod_v ? NVS : NKS;
+  int pj = 0, p_n = 0, p_tile = 0, p_slot = 0, p_round = 0;  // next half tile to issue, its ring slot and round
+  int f_n = 0, f_tile = 0;                                   // the half tile PFD further on (L2 prefetch)
+  OpInfo p_cur = op_info(0), f_cur = p_cur;
+  if ((warp == 4 || warp == 6) && TP > 0) {
+    f_n = PFD / TP;
+    f_tile = PFD - f_n * TP;
+    f_cur = op_info(f_n);
+  }
+  auto produce = [&]() {
+    unsigned char* dst = (prod_v ? vring : kring) + (size_t)p_slot * C::HT_BYTES;
+    uint64_t* full = (prod_v ? v_full : k_full) + p_slot;
+    const bool tt = tracer && lane == 0 && p_n == TRACE_OP && p_tile < 16;
+    if (tt) a.trace[400 + p_tile * 4 + (prod_v ? 2 : 0)] = clock64();
+    if (p_round > 0) mbar_wait((prod_v ? v_empty : k_empty) + p_slot, (uint32_t)((p_round - 1) & 1));
+    if (tt) a.trace[400 + p_tile * 4 + (prod_v ? 3 : 1)] = clock64();
+    const CUtensorMap* tm = prod_v ? &tm_v : &tm_k;
+    const int row0 = p_cur.row_base + p_tile * HT;
+    const bool leader = tc::elect_one();
+    if (leader) {
+      mbar_expect_tx(full, (uint32_t)C::HT_BYTES);
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) tc::tma_load_2d_hint(dst + ch * C::CH_BYTES, tm, ch * 64, row0, bar, pol);
-    const int jp = j + PFD;
-    if (jp < total_ht) {
-      const int pn = jp / TP, pt = jp - pn * TP;
-      int pl, pc;
-      op_of(pn, pl, pc);
-      if (pc % T == 0) {
-        const size_t off = ((size_t)image_of(pl, pc / T) * N + (size_t)(tile0 + pt) * HT) * D * 2;
+      for (int ch = 0; ch < NCH; ++ch) tc::tma_load_2d_hint(dst + ch * C::CH_BYTES, tm, ch * 64, row0, full, p_cur.pol);
+      if (f_n < total_ops && f_cur.cold) {
+        const size_t off = (size_t)(f_cur.row_base + f_tile * HT) * (D * 2);
         if (off + C::HT_BYTES <= (size_t)B * N * D * 2)
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(is_v ? a.v : a.k) + off), "r"(C::HT_BYTES) : "memory");
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(prod_v ? a.v : a.k) + off), "r"(C::HT_BYTES) : "memory");
       }
     }
+    __syncwarp();
+    ++pj;
+    if (++p_slot == PNS) { p_slot = 0; ++p_round; }
+    if (++p_tile == TP) { p_tile = 0; ++p_n; p_cur = op_info(p_n); }
+    if (++f_tile == TP) { f_tile = 0; ++f_n; f_cur = op_info(f_n); }
   };
 
   // ------------------------------------------------------------------ one-time setup
@@ -250,6 +273,8 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
     mbar_init(&xbar[1], 1);
     mbar_init(u_ready, 4);
     mbar_init(u_free, 8);
+    mbar_init(&ubar[0], 1);
+    mbar_init(&ubar[1], 1);
     for (int l = 0; l < NL; ++l) mbar_init(&q_ready[l], 1);
     mbar_fence_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_k) : "memory");
@@ -260,78 +285,78 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
   // publishes the mbarrier init)
   if (warp < 8) {
     asm volatile("bar.sync 3, 256;" ::: "memory");
-    if (lane == 0 && TP > 0) {
-      if (warp == 4) for (int j = 0; j < NKS && j < total_ht; ++j) issue_half(j, false);
-      if (warp == 6) for (int j = 0; j < NVS && j < total_ht; ++j) issue_half(j, true);
-    }
+    if (warp == 4 || warp == 6)
+      while (pj < PNS && pj < total_ht) produce();
   }
+  tc::fence_before();
+  __syncthreads();  // tensor memory is allocated
+  tc::fence_after();
+  const uint32_t tmem = *tmem_slot;
   {
-    // the CTA's weight slices, fp32 global -> bf16 shared; eight independent 16-byte loads in flight per thread
-    auto load_rows = [&](unsigned char* dst, int pitch, const float* src, int L, int nrows) {
-      const int total = nrows * (L / 4);
-      for (int i0 = tid; i0 < total; i0 += 8 * C::NT) {
-        float4 x[8];
+    // The CTA's weight slices, fp32 global -> bf16 pairs in tensor memory, one weight row per thread (= lane):
+    // warps 0-3 fill block X, warps 8-11 block Y.  LayerNorm folded into the product that follows it:
+    // W LN(x) = rstd (W' x - mean c) + W beta,  W' = W diag(gamma),  c = row sums of the (bf16-rounded) W'.
+    const bool fill_x = warp < 4, fill_y = (warp >= 8 && warp < 12);
+    if (fill_x || fill_y) {
+      const int r = (warp & 3) * 32 + lane;
+      const float* src = a.w.w_ih;
+      const float* gam = a.w.ln_mlp_w;
+      const float* bet = a.w.ln_mlp_b;
+      int len = 0, fold = 0;  // fold: 1 = W1' row, 2 = Wq' row
+      if (fill_x) {
+        if (r < 3 * DS) { src = a.w.w_ih + ((size_t)(r / DS) * D + rank * DS + r % DS) * D; len = D; }
+        else if (r < 3 * DS + HS) { src = a.w.w1 + ((size_t)rank * HS + (r - 3 * DS)) * D; len = D; fold = 1; }
+        else if (r < C::RX) { src = a.w.w2 + ((size_t)rank * DS + (r - 3 * DS - HS)) * H; len = H; }
+      } else {
+        if (r < 3 * DS) { src = a.w.w_hh + ((size_t)(r / DS) * D + rank * DS + r % DS) * D; len = D; }
+        else if (r < C::RY) { src = a.w.wq + ((size_t)rank * DS + (r - 3 * DS)) * D; len = D; fold = 2; gam = a.w.ln_slots_w; bet = a.w.ln_slots_b; }
+      }
+      const int lmax = fill_x ? C::LX : D;
+      const uint32_t tcol = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (fill_x ? C::COL_WX : C::COL_WY);
+      float csum = 0.f, bsum = 0.f;
+      for (int k0 = 0; k0 < lmax; k0 += 64) {  // 64 features per batch: sixteen 16-byte loads in flight
+        float4 x[16];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int i = i0 + u * C::NT;
-          if (i < total) x[u] = __ldg(reinterpret_cast<const float4*>(src) + i);
-        }
+        for (int u = 0; u < 16; ++u)
+          x[u] = (k0 + 4 * u < len) ? __ldg(reinterpret_cast<const float4*>(src + k0) + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (fold && k0 < len) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int i = i0 + u * C::NT;
-          if (i < total) {
-            const int r = i / (L / 4), c4 = i % (L / 4);
-            *reinterpret_cast<uint2*>(dst + r * pitch + 8 * c4) =
-                make_uint2(pack_bf16x2(x[u].x, x[u].y), pack_bf16x2(x[u].z, x[u].w));
+          for (int u = 0; u < 16; ++u) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gam + k0) + u);
+            const float4 b = __ldg(reinterpret_cast<const float4*>(bet + k0) + u);
+            bsum = fmaf(x[u].x, b.x, fmaf(x[u].y, b.y, fmaf(x[u].z, b.z, fmaf(x[u].w, b.w, bsum))));
+            x[u] = make_float4(x[u].x * g.x, x[u].y * g.y, x[u].z * g.z, x[u].w * g.w);
           }
         }
-      }
-    };
-    for (int gate = 0; gate < 3; ++gate) {
-      load_rows(s_wih + gate * DS * PITCH, PITCH, a.w.w_ih + ((size_t)gate * D + rank * DS) * D, D, DS);
-      load_rows(s_whh + gate * DS * PITCH, PITCH, a.w.w_hh + ((size_t)gate * D + rank * DS) * D, D, DS);
-    }
-    load_rows(s_w2, PITCHH, a.w.w2 + (size_t)rank * DS * H, H, DS);
-    // LayerNorm folded into the product that follows it:  W LN(x) = rstd (W' x - mean c) + W beta,  W' = W diag(gamma),
-    // c = row sums of the (bf16-rounded) W'.  One warp per row.
-    {
-      for (int r = warp; r < HS + DS; r += C::NT / 32) {
-        const bool is1 = r < HS;
-        const int rr = is1 ? r : r - HS;
-        const float* wrow = is1 ? a.w.w1 + ((size_t)rank * HS + rr) * D : a.w.wq + ((size_t)rank * DS + rr) * D;
-        const float* gam = is1 ? a.w.ln_mlp_w : a.w.ln_slots_w;
-        const float* bet = is1 ? a.w.ln_mlp_b : a.w.ln_slots_b;
-        unsigned char* drow = (is1 ? s_w1 : s_wq) + rr * PITCH;
-        float csum = 0.f, bsum = 0.f;
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          const int d = 64 * c + 2 * lane;
-          const float2 wv = __ldg(reinterpret_cast<const float2*>(wrow + d));
-          const float2 g = __ldg(reinterpret_cast<const float2*>(gam + d));
-          const float2 b = __ldg(reinterpret_cast<const float2*>(bet + d));
-          const __nv_bfloat162 wf = __floats2bfloat162_rn(wv.x * g.x, wv.y * g.y);
-          *reinterpret_cast<__nv_bfloat162*>(drow + d * 2) = wf;
-          csum += __low2float(wf) + __high2float(wf);
-          bsum = fmaf(wv.x, b.x, fmaf(wv.y, b.y, bsum));
-        }
-        csum = warp_sum(csum);
-        bsum = warp_sum(bsum);
-        if (lane == 0) {
-          if (is1) { s_c1[rr] = csum; s_b1f[rr] = bsum + a.w.b1[rank * HS + rr]; }
-          else { s_cq[rr] = csum; s_bqf[rr] = bsum; }
+        for (int q = 0; q < 4; ++q) {  // one k step (16 features = 8 columns) per store
+          uint32_t wv[8];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float4 v4 = x[4 * q + e];
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(v4.x, v4.y), hi = __floats2bfloat162_rn(v4.z, v4.w);
+            csum += (__low2float(lo) + __high2float(lo)) + (__low2float(hi) + __high2float(hi));
+            wv[2 * e] = *reinterpret_cast<const uint32_t*>(&lo);
+            wv[2 * e + 1] = *reinterpret_cast<const uint32_t*>(&hi);
+          }
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(tcol + (uint32_t)(k0 / 2 + 8 * q)),
+                       "r"(wv[0]), "r"(wv[1]), "r"(wv[2]), "r"(wv[3]), "r"(wv[4]), "r"(wv[5]), "r"(wv[6]), "r"(wv[7])
+                       : "memory");
         }
       }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      if (fold == 1) { s_c1[r - 3 * DS] = csum; s_b1f[r - 3 * DS] = bsum + a.w.b1[rank * HS + (r - 3 * DS)]; }
+      if (fold == 2) { s_cq[r - 3 * DS] = csum; s_bqf[r - 3 * DS] = bsum; }
     }
-    for (int i = tid; i < PITCHX / 4; i += C::NT) reinterpret_cast<uint32_t*>(s_zrow)[i] = 0u;
     for (int i = tid; i < 3 * DS; i += C::NT) {
       const int gate = i / DS, dl = i % DS;
       s_bias[i] = a.w.b_ih[gate * D + rank * DS + dl];
       s_bias[3 * DS + i] = a.w.b_hh[gate * D + rank * DS + dl];
     }
     for (int i = tid; i < DS; i += C::NT) s_bias[6 * DS + HS + i] = a.w.b2[rank * DS + i];
-    // staging rows of the padded slots are never written by the conversions; keep them finite.  The w tiles' slot rows
-    // 8..15 and the q operands' rows K..7 stay zero for the whole kernel.
-    for (int i = tid; i < (2 * KB * PITCHX) / 4; i += C::NT) reinterpret_cast<uint32_t*>(sm + C::OFF_ACT)[i] = 0u;
+    // operand rows of the padded slots are never written; keep them zero.  The w tiles' slot rows 8..15 and the
+    // operands' rows K..7 stay zero for the whole kernel.
+    for (int i = tid; i < (2 * C::OPX_BYTES) / 4; i += C::NT) reinterpret_cast<uint32_t*>(sm + C::OFF_ACT)[i] = 0u;
     for (int i = tid; i < (NL * C::LANE_BYTES) / 4; i += C::NT) reinterpret_cast<uint32_t*>(sm + C::OFF_LANE)[i] = 0u;
     for (int i = tid; i < (NWB * C::WP_BYTES) / 4; i += C::NT) reinterpret_cast<uint32_t*>(wtiles)[i] = 0u;
     fence_proxy_async();  // the zero rows are read by tcgen05.mma (async proxy)
@@ -339,20 +364,20 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
   tc::fence_before();
   __syncthreads();
   tc::fence_after();
-  const uint32_t tmem = *tmem_slot;
   if (tid >= 256 && nops[0] > 0) {  // after the zero fill of the lane buffers; the cluster barrier below publishes it
     unsigned char* dst = slh_hi(0);
     float* own = own_of(0);
 #pragma unroll
     for (int u = 0; u < PRE2; ++u) {
       const int i = tid - 256 + 256 * u;
-      if (i < K * (D / 2)) *reinterpret_cast<uint32_t*>(dst + (i / (D / 2)) * PITCH + 4 * (i % (D / 2))) = pack_bf16x2(pre2[u].x, pre2[u].y);
+      if (i < K * (D / 2)) *reinterpret_cast<uint32_t*>(dst + opnd_off(i / (D / 2), 2 * (i % (D / 2)))) = pack_bf16x2(pre2[u].x, pre2[u].y);
     }
 #pragma unroll
     for (int u = 0; u < PRE1; ++u) {
       const int i = tid - 256 + 256 * u;
       if (i < K * DS) own[i] = pre1[u];
     }
+    fence_proxy_async();  // the slots are an MMA operand
   }
   cluster.sync();  // every CTA's barriers are initialised before any peer signals them
   if (tid == 0) PP_TRACE(0);
@@ -363,7 +388,7 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
       // ---- softmax warps: one token per thread.  Thread (warp w, lane) reads tensor-memory lane 32 w + lane:
       // lanes 0-15 hold rows 16 w .. 16 w + 15 of the pair's first half, lanes 16-31 the same rows of the second half.
       const int half = lane >> 4, r16 = lane & 15;
-      const int tt = warp * 16 + r16;  // token inside its half
+      const int tih = warp * 16 + r16;  // token inside its half
       const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
       uint32_t gp = 0;  // pairs handled so far (selects the logit / w buffers and their phases)
       for (int n = 0; n < total_ops; ++n) {
@@ -376,16 +401,20 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
         for (int i = 0; i < 8; ++i) Sl[i] = 0.f;
         for (int p = 0; p < NP; ++p, ++gp) {
           const uint32_t lb = gp & 1, wb = gp % NWB;
+          const bool tt = tracer && tid == 0 && n == TRACE_OP && p < 4;
+          if (tt) a.trace[340 + p * 12 + 0] = clock64();
           mbar_wait(&lg_full[lb], (gp >> 1) & 1);
+          if (tt) a.trace[340 + p * 12 + 1] = clock64();
           if (tid == 0 && p == 0 && n < 40) PP_TRACE(8 + n * 8);
           tc::fence_after();
           float x[8];
-          tc::tmem_ld8(tlane + C::COL_LG + 16 * lb, x);
+          tc::tmem_ld8(tlane + C::COL_LG + C::LG_STRIDE * lb, x);
           tc::fence_before();
           __syncwarp();
           if (lane == 0) tc::arrive(&lg_empty[lb]);
+          if (tt) a.trace[340 + p * 12 + 2] = clock64();
           const int ht = 2 * p + half;
-          const int tok = (tile0 + ht) * HT + tt;
+          const int tok = (tile0 + ht) * HT + tih;
           const bool tok_ok = (ht < TP) && (tok < N);
           float mx = -INFINITY;
 #pragma unroll
@@ -415,8 +444,10 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
             }
           }
           // weights rounded to bf16 once; the same rounded values feed the numerator and the token sum
+          if (tt) a.trace[340 + p * 12 + 3] = clock64();
           if (gp >= (uint32_t)NWB) mbar_wait(&w_empty[wb], ((gp / NWB) - 1) & 1);
-          unsigned char* wrow = wtiles + wb * C::WP_BYTES + half * C::WH_BYTES + (tt >> 3) * 256 + (tt & 7) * 2;
+          if (tt) a.trace[340 + p * 12 + 4] = clock64();
+          unsigned char* wrow = wtiles + wb * C::WP_BYTES + half * C::WH_BYTES + (tih >> 3) * 256 + (tih & 7) * 2;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float wv = (tok_ok && i < K) ? x[i] + a.eps : 0.f;
@@ -427,6 +458,7 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) tc::arrive(&w_full[wb]);
+          if (tt) a.trace[340 + p * 12 + 5] = clock64();
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) Sl[i] = warp_sum(Sl[i]);
@@ -437,8 +469,9 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
         if (NP > 0) {
           mbar_wait(&u_full[n & 1], (n >> 1) & 1);
           tc::fence_after();
-          tc::tmem_ld8(tlane + C::COL_U + 32 * (n & 1), ua);
-          if (C::HAS_B) tc::tmem_ld8(tlane + C::COL_U + 32 * (n & 1) + 16, ub);
+          const uint32_t ucol = tlane + C::COL_U + C::U_STRIDE * (n & 1);
+          tc::tmem_ld8(ucol, ua);
+          if (C::HAS_B) tc::tmem_ld8(ucol + C::U_B, ub);
           tc::fence_before();
           __syncwarp();
           if (lane == 0) tc::arrive(&u_accfree[n & 1]);
@@ -465,19 +498,12 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
         if (lane == 0) mbar_arrive(u_ready);
       }
     } else if (warp == 4 || warp == 6) {
-      // ---- TMA producers: warp 4 the k ring, warp 6 the v ring
-      if (lane == 0) {
-        const bool is_v = (warp == 6);
-        const int NS = is_v ? NVS : NKS;
-        uint64_t* empty = is_v ? v_empty : k_empty;
-        for (int j = NS; j < total_ht; ++j) {
-          mbar_wait(&empty[j % NS], (uint32_t)(((j / NS) - 1) & 1));
-          issue_half(j, is_v);
-        }
-      }
+      // ---- TMA producers: the rest of the stream (the first ring-full was issued during the setup)
+      while (pj < total_ht) produce();
     } else if (warp == 5) {
-      // ---- MMA issuer
-      if (lane == 0) {
+      // ---- MMA issuer: the whole warp runs the control flow (uniform operands), one elected lane issues
+      {
+        const bool leader = tc::elect_one();
         constexpr uint32_t ID_LG = tc::idesc_bf16(64, 8);
         constexpr uint32_t ID_UA = tc::idesc_bf16(C::MA, 16, 1, 0);
         constexpr uint32_t ID_UB = tc::idesc_bf16(64, 16, 1, 0);
@@ -491,9 +517,11 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
           fence_proxy_async();
           tc::fence_after();
           const uint32_t qa = smem_u32(qop(l));
-          const uint32_t ucol = tmem + C::COL_U + 32 * (n & 1);
+          const uint32_t ucol = tmem + C::COL_U + C::U_STRIDE * (n & 1);
+          const bool tn = tracer && lane == 0 && n == TRACE_OP;
           auto logits = [&](int p) {
             const uint32_t lb = gp & 1;
+            if (tn && p < 4) a.trace[340 + p * 12 + 6] = clock64();
             if (gp >= 2) {
               mbar_wait(&lg_empty[lb], ((gp >> 1) - 1) & 1);
               tc::fence_after();
@@ -503,22 +531,28 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
               mbar_wait(&k_full[s], (uint32_t)((jk / NKS) & 1));
               tc::fence_after();
               const uint32_t ka = smem_u32(kring + (size_t)s * C::HT_BYTES);
-              const uint32_t dcol = tmem + C::COL_LG + 16 * lb + ((uint32_t)(16 * h) << 16);
+              const uint32_t dcol = tmem + C::COL_LG + C::LG_STRIDE * lb + ((uint32_t)(16 * h) << 16);
 #pragma unroll
               for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
-                  tc::mma_bf16(dcol, tc::smem_desc(ka + ch * C::CH_BYTES + ks * 32, 16, 1024, tc::SW_128),
-                               tc::smem_desc(qa + (ch * 4 + ks) * 256, 128, 128, tc::SW_NONE), ID_LG, (ch | ks) != 0);
-              tc::commit(&k_empty[s]);
+                  if (leader)
+                    tc::mma_bf16(dcol, tc::smem_desc(ka + ch * C::CH_BYTES + ks * 32, 16, 1024, tc::SW_128),
+                                 tc::smem_desc(qa + (ch * 4 + ks) * 256, 128, 128, tc::SW_NONE), ID_LG, (ch | ks) != 0);
+              if (leader) tc::commit(&k_empty[s]);
+              __syncwarp();
               ++jk;
             }
-            tc::commit(&lg_full[lb]);
+            if (leader) tc::commit(&lg_full[lb]);
+            __syncwarp();
             ++gp;
+            if (tn && p < 4) a.trace[340 + p * 12 + 7] = clock64();
           };
           auto uprod = [&](int p) {
             const uint32_t wb = gu % NWB;
+            if (tn && p < 4) a.trace[340 + p * 12 + 8] = clock64();
             mbar_wait(&w_full[wb], (gu / NWB) & 1);
+            if (tn && p < 4) a.trace[340 + p * 12 + 9] = clock64();
             tc::fence_after();
             if (p == 0 && n >= 2) {  // the accumulator was last used by op n - 2
               mbar_wait(&u_accfree[n & 1], (uint32_t)(((n >> 1) - 1) & 1));
@@ -534,31 +568,38 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
               for (int ks = 0; ks < 4; ++ks) {  // 16 tokens per step: two 8-token groups 1024 B apart, next step +2048 B
                 const uint32_t acc = (p | h | ks) != 0;
                 const uint64_t db = tc::smem_desc(wa + ks * 512, 256, 128, tc::SW_NONE);
-                tc::mma_bf16(ucol, tc::smem_desc(va + ks * 2048, C::CH_BYTES, 1024, tc::SW_128), db, ID_UA, acc);
-                if (C::HAS_B)
-                  tc::mma_bf16(ucol + 16, tc::smem_desc(va + 2 * C::CH_BYTES + ks * 2048, C::CH_BYTES, 1024, tc::SW_128), db, ID_UB, acc);
+                if (leader) {
+                  tc::mma_bf16(ucol, tc::smem_desc(va + ks * 2048, C::CH_BYTES, 1024, tc::SW_128), db, ID_UA, acc);
+                  if (C::HAS_B)
+                    tc::mma_bf16(ucol + C::U_B, tc::smem_desc(va + 2 * C::CH_BYTES + ks * 2048, C::CH_BYTES, 1024, tc::SW_128), db, ID_UB, acc);
+                }
               }
-              tc::commit(&v_empty[s]);
+              if (leader) tc::commit(&v_empty[s]);
+              __syncwarp();
               ++jv;
             }
-            tc::commit(&w_empty[wb]);
+            if (leader) tc::commit(&w_empty[wb]);
+            __syncwarp();
             ++gu;
+            if (tn && p < 4) a.trace[340 + p * 12 + 10] = clock64();
           };
           for (int p = 0; p < NP; ++p) {
             logits(p);
             if (p > 0) uprod(p - 1);
           }
           uprod(NP - 1);
-          tc::commit(&u_full[n & 1]);
+          if (leader) tc::commit(&u_full[n & 1]);
+          __syncwarp();
         }
       }
     }
     __syncwarp();
   } else {
     // ==================================================================================== UPDATE ENGINE
-    // Every exchange round is  push -> wait -> tensor-core product -> one barrier -> epilogue (= next push):
-    // all-gather payloads travel as bf16 straight into the receivers' MMA staging buffers (act[parity], slh[lane],
-    // the lane's q operand); the LayerNorms are folded into the products that follow them (statistics from the received rows).
+    // Every exchange round is  push -> wait -> tensor-core product -> accumulator rows to shared memory -> one barrier
+    // -> epilogue (= next push): all-gather payloads travel as bf16 straight into the receivers' MMA operand buffers
+    // (act[parity], the lane's slots and q operands); the LayerNorms are folded into the products that follow them
+    // (statistics from the received rows).
     const int utid = tid - 256, uwarp = warp - 8;
     uint32_t round = 0;
     // training: per-(image, iteration) state for the fused backward (SavedLayout, slot_math.cuh); every CTA writes
@@ -571,14 +612,14 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
     };
     auto xwait = [&](uint32_t r) { mbar_wait_cluster(&xbar[r & 1], (r >> 1) & 1); };
     // All-gather push: thread i < K*SL holds element (slot = i / SL, f = i % SL) of the CTA's slice.  The four lanes
-    // of a quad assemble 4 features (8 bytes of bf16) and each sends them to CL/4 CTAs, into `dst` ([8][pitch] bf16).
-    auto quad_push = [&](uint32_t r, float val, int i, int SL, unsigned char* dst, int pitch) {
+    // of a quad assemble 4 features (8 bytes of bf16) and each sends them to CL/4 CTAs, into the operand buffer `dst`.
+    auto quad_push = [&](uint32_t r, float val, int i, int SL, unsigned char* dst) {
       const int qb = lane & ~3;
       const float v0 = __shfl_sync(FULL, val, qb), v1 = __shfl_sync(FULL, val, qb + 1);
       const float v2 = __shfl_sync(FULL, val, qb + 2), v3 = __shfl_sync(FULL, val, qb + 3);
       if (i < K * SL) {
-        const int slot = i / SL, f4 = (i % SL) & ~3;
-        const uint32_t lbuf = smem_u32(dst) + (uint32_t)(slot * pitch + (rank * SL + f4) * 2);
+        const int slot = i / SL, f = rank * SL + ((i % SL) & ~3);
+        const uint32_t lbuf = smem_u32(dst) + (uint32_t)opnd_off(slot, f);
         const uint32_t lbar = smem_u32(&xbar[r & 1]);
         const uint32_t lo = pack_bf16x2(v0, v1), hi = pack_bf16x2(v2, v3);
 #pragma unroll
@@ -588,32 +629,14 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
         }
       }
     };
-    // same for the queries, into the K-major UMMA operand [D/8][8 slots][8 features] of every CTA
-    auto quad_push_q = [&](uint32_t r, float val, int i, unsigned char* dst) {
-      const int qb = lane & ~3;
-      const float v0 = __shfl_sync(FULL, val, qb), v1 = __shfl_sync(FULL, val, qb + 1);
-      const float v2 = __shfl_sync(FULL, val, qb + 2), v3 = __shfl_sync(FULL, val, qb + 3);
-      if (i < K * DS) {
-        const int slot = i / DS, f = rank * DS + ((i % DS) & ~3);
-        const uint32_t lbuf = smem_u32(dst) + (uint32_t)((f >> 3) * 128 + slot * 16 + (f & 7) * 2);
-        const uint32_t lbar = smem_u32(&xbar[r & 1]);
-        const uint32_t lo = pack_bf16x2(v0, v1), hi = pack_bf16x2(v2, v3);
-#pragma unroll
-        for (int q = 0; q < CL / 4; ++q) {
-          const int dest = (lane & 3) + 4 * q;
-          st_async_v2(mapa_u32(lbuf, dest), lo, hi, mapa_u32(lbar, dest));
-        }
-      }
-    };
-    // mean / rstd of the K rows (bf16, length D) that just arrived: one warp per row
-    auto row_stats = [&](const unsigned char* rows, int pitch) {
-      constexpr int NCH = D / 64;
+    // mean / rstd of the K rows (bf16, length D, operand layout) that just arrived: one warp per row
+    auto row_stats = [&](const unsigned char* opnd) {
       if (uwarp < K) {
         float2 x[NCH];
         float s = 0.f;
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
-          const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(rows + uwarp * pitch + (64 * c + 2 * lane) * 2);
+          const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(opnd + opnd_off(uwarp, 64 * c + 2 * lane));
           x[c] = make_float2(__low2float(v), __high2float(v));
           s += x[c].x + x[c].y;
         }
@@ -628,42 +651,76 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
         if (lane == 0) { s_mean[uwarp] = mean; s_rstd[uwarp] = rstd; }
       }
     };
-    // slots of image `img` (fp32, global) -> this CTA's bf16 copy slh[l] and the fp32 own slice
+    // Products: D[128 weight rows x 16] = W block (tensor memory, `wcol`) x operand (K-major [k/8][8 slots][8] bf16,
+    // the second 8-row group aliased onto the first: SBO = 0), `ksteps` of 16 features.  Warp 0 of the engine issues
+    // (uniform control flow, one elected lane) and commits to ubar[which]; every thread of the engine waits for the
+    // commits of a barrier in order (`uph` counts them; a barrier is never more than one phase ahead of its waiters:
+    // W_hh h, which stays in flight across other products, has a barrier of its own); warps 0-3 / 4-7 then move
+    // accumulator rows to P_GI / P_GH.
+    constexpr uint32_t ID_UPD = tc::idesc_bf16(128, 16);
+    uint32_t uph[2] = {0u, 0u};
+    auto product = [&](uint32_t wcol, const unsigned char* opnd, int ksteps, uint32_t dcol, int which) {
+      if (uwarp == 0) {
+        fence_proxy_async();  // the operand was written through the generic proxy (st.async / st.shared)
+        tc::fence_after();
+        const uint32_t oa = smem_u32(opnd);
+        if (tc::elect_one()) {
+          for (int ks = 0; ks < ksteps; ++ks)
+            tc::mma_bf16_ts(tmem + dcol, tmem + wcol + 8 * ks, tc::smem_desc(oa + ks * 256, 128, 0, tc::SW_NONE), ID_UPD, ks != 0);
+          tc::commit(&ubar[which]);
+        }
+        __syncwarp();
+      }
+    };
+    auto product_wait = [&](int which) {
+      mbar_wait(&ubar[which], uph[which] & 1);
+      ++uph[which];
+      tc::fence_after();
+    };
+    const uint32_t tq = tmem + ((uint32_t)((uwarp & 3) * 32) << 16);  // this warp's quarter of the lanes
+    auto unload = [&](uint32_t dcol, float* Pr, int group) {
+      if ((uwarp >> 2) == group) {
+        float v8[8];
+        tc::tmem_ld8(tq + dcol, v8);
+        float4* o = reinterpret_cast<float4*>(Pr + ((uwarp & 3) * 32 + lane) * 8);
+        o[0] = make_float4(v8[0], v8[1], v8[2], v8[3]);
+        o[1] = make_float4(v8[4], v8[5], v8[6], v8[7]);
+        tc::fence_before();
+      }
+    };
+    // slots of image `img` (fp32, global) -> this CTA's bf16 operand slh[l] and the fp32 own slice
     auto load_slots0 = [&](int l, int img) {
       const float* src = a.slots0 + (size_t)img * K * D;
       unsigned char* dst = slh_hi(l);
       for (int i = utid; i < K * (D / 2); i += 256) {
         const int slot = i / (D / 2), c2 = i % (D / 2);
         const float2 x = __ldg(reinterpret_cast<const float2*>(src + slot * D + 2 * c2));
-        *reinterpret_cast<uint32_t*>(dst + slot * PITCH + 4 * c2) = pack_bf16x2(x.x, x.y);
+        *reinterpret_cast<uint32_t*>(dst + opnd_off(slot, 2 * c2)) = pack_bf16x2(x.x, x.y);
       }
       float* own = own_of(l);
       for (int i = utid; i < K * DS; i += 256) own[i] = __ldg(src + (i / DS) * D + rank * DS + i % DS);
+      fence_proxy_async();
       upd_sync();
     };
     // q = W_q LN(slots) of lane l for the CTA's slice (slots = slh[l], bf16), all-gathered (times log2 e) into the lane's q operand
     auto q_phase = [&](int l, int q_img, int q_t) {
-      for (int job = uwarp; job < NM2 * NKC; job += 8) {
-        const int mt = job / NKC, kc = job % NKC;
-        mma_job<false>(s_wq, PITCH, DS, s_zrow, mt, kc * (D / 16) / NKC, (kc + 1) * (D / 16) / NKC, slh_hi(l), nullptr, PITCH,
-                       P + kc * NM2 * 128, lane);
-      }
-      row_stats(slh_hi(l), PITCH);
+      product(C::COL_WY, slh_hi(l), D / 16, C::COL_GH, 0);
+      row_stats(slh_hi(l));
       arm(round, (uint32_t)(K * D * 2));
+      product_wait(0);
+      unload(C::COL_GH, P_GH, 1);
       upd_sync();
       for (int i0 = uwarp * 32; i0 < K * DS; i0 += 256) {
         const int i = i0 + lane;
         float val = 0.f;
         if (i < K * DS) {
           const int slot = i / DS, dl = i % DS;
-          float acc = 0.f;
-#pragma unroll
-          for (int kc = 0; kc < NKC; ++kc) acc += P[(kc * NM2 * 16 + dl) * 8 + slot];
+          const float acc = P_GH[(3 * DS + dl) * 8 + slot];
           const float qv = s_rstd[slot] * (acc - s_mean[slot] * s_cq[dl]) + s_bqf[dl];
           if (a.saved != nullptr) saved_at(q_img, q_t)[SL.off_q() + slot * D + rank * DS + dl] = qv;
           val = qv * LOG2E;
         }
-        quad_push_q(round, val, i, qop(l));
+        quad_push(round, val, i, DS, qop(l));
       }
       xwait(round);
       ++round;
@@ -673,7 +730,7 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
       }
     };
 
-    // initial queries of both lanes
+    // initial queries of the lanes
     for (int l = 0; l < NL; ++l)
       if (nops[l] > 0) {
         if (l > 0) load_slots0(l, image_of(l, 0));  // lane 0's were staged during the setup
@@ -690,6 +747,8 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
 #define PP_T(i) do { if (tr_on) a.trace[8 + n * 8 + (i)] = clock64(); } while (0)
       // ============================================================ R1: reduce-scatter of sum w v, all-reduce of sum w
       arm(round, (uint32_t)(K * D * 4 + 32 * CL));
+      // gh = W_hh h only needs the slots that entered the iteration: it runs under the pass and the R1 round trip
+      product(C::COL_WY, slh_hi(l), D / 16, C::COL_GH, 1);
       mbar_wait(u_ready, (uint32_t)(n & 1));
       PP_T(2);
       {
@@ -711,9 +770,6 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(u_free);  // the pass engine may overwrite the staging buffers
-      // gh = W_hh h only needs the slots that entered the iteration: computed under the R1 round trip
-      for (int job = uwarp; job < NMG; job += 8)
-        mma_job<false>(s_whh, PITCH, 3 * DS, s_zrow, job, 0, D / 16, slh_hi(l), nullptr, PITCH, P + NMG * 128, lane);
       xwait(round);
       ++round;
       PP_T(3);
@@ -741,18 +797,18 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
               if (rank == 0 && dl == 0) sv[SL.off_s() + slot] = sw;
             }
           }
-          quad_push(round, val, i, DS, act(round), PITCHX);
+          quad_push(round, val, i, DS, act(round));
         }
       }
       xwait(round);
-      // ---- GRU: gi = W_ih u (k split in two halves: 2 * NMG jobs keep all 8 warps busy; halves summed in the epilogue)
-      for (int job = uwarp; job < 2 * NMG; job += 8) {
-        const int mt = job >> 1, half = job & 1;
-        mma_job<false>(s_wih, PITCH, 3 * DS, s_zrow, mt, half * (D / 32), (half + 1) * (D / 32), act(round), nullptr, PITCHX,
-                       P + (half ? 2 * NMG * 128 : 0), lane);
-      }
+      // ---- GRU: gi = W_ih u
+      product(C::COL_WX, act(round), D / 16, C::COL_GI, 0);
       ++round;
       arm(round, (uint32_t)(K * D * 2));
+      product_wait(1);  // gh
+      product_wait(0);  // gi
+      unload(C::COL_GI, P_GI, 0);
+      unload(C::COL_GH, P_GH, 1);
       upd_sync();
       PP_T(4);
       // ============================================================ R3: all-gather h'
@@ -761,14 +817,11 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
         float hp = 0.f;
         if (i < K * DS) {
           const int slot = i / DS, dl = i % DS;
-          const float* Pi = P;
-          const float* Pj = P + 2 * NMG * 128;  // second k half of W_ih u
-          const float* Ph = P + NMG * 128;
-          const float gir = Pi[(dl) * 8 + slot] + Pj[(dl) * 8 + slot] + s_bih[dl], ghr = Ph[(dl) * 8 + slot] + s_bhh[dl];
-          const float giz = Pi[(DS + dl) * 8 + slot] + Pj[(DS + dl) * 8 + slot] + s_bih[DS + dl];
-          const float ghz = Ph[(DS + dl) * 8 + slot] + s_bhh[DS + dl];
-          const float gin = Pi[(2 * DS + dl) * 8 + slot] + Pj[(2 * DS + dl) * 8 + slot] + s_bih[2 * DS + dl];
-          const float ghn = Ph[(2 * DS + dl) * 8 + slot] + s_bhh[2 * DS + dl];
+          const float gir = P_GI[(dl) * 8 + slot] + s_bih[dl], ghr = P_GH[(dl) * 8 + slot] + s_bhh[dl];
+          const float giz = P_GI[(DS + dl) * 8 + slot] + s_bih[DS + dl];
+          const float ghz = P_GH[(DS + dl) * 8 + slot] + s_bhh[DS + dl];
+          const float gin = P_GI[(2 * DS + dl) * 8 + slot] + s_bih[2 * DS + dl];
+          const float ghn = P_GH[(2 * DS + dl) * 8 + slot] + s_bhh[2 * DS + dl];
           const float r = sigmoidf_(gir + ghr), z = sigmoidf_(giz + ghz);
           const float nn = tanhf(gin + r * ghn);
           hp = (1.f - z) * nn + z * own[i];
@@ -783,18 +836,16 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
             sv[SL.off_hp() + f] = hp;
           }
         }
-        quad_push(round, hp, i, DS, act(round), PITCHX);
+        quad_push(round, hp, i, DS, act(round));
       }
       xwait(round);
       // ---- MLP layer 1 on the raw h' (LayerNorm folded), statistics alongside
-      for (int job = uwarp; job < NM1 * NKC; job += 8) {
-        const int mt = job / NKC, kc = job % NKC;
-        mma_job<false>(s_w1, PITCH, HS, s_zrow, mt, kc * (D / 16) / NKC, (kc + 1) * (D / 16) / NKC, act(round), nullptr, PITCHX,
-                       P + kc * NM1 * 128, lane);
-      }
-      row_stats(act(round), PITCHX);
+      product(C::COL_WX, act(round), D / 16, C::COL_GI, 0);
+      row_stats(act(round));
       ++round;
       arm(round, (uint32_t)(K * H * 2));
+      product_wait(0);
+      unload(C::COL_GI, P_GI, 0);
       upd_sync();
       PP_T(5);
       // ============================================================ R4: all-gather the MLP hidden layer
@@ -803,23 +854,19 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
         float hid = 0.f;
         if (i < K * HS) {
           const int slot = i / HS, hl = i % HS;
-          float acc = 0.f;
-#pragma unroll
-          for (int kc = 0; kc < NKC; ++kc) acc += P[(kc * NM1 * 16 + hl) * 8 + slot];
+          const float acc = P_GI[(3 * DS + hl) * 8 + slot];
           const float pre = s_rstd[slot] * (acc - s_mean[slot] * s_c1[hl]) + s_b1f[hl];
           if (a.saved != nullptr) saved_at(img, t)[SL.off_pre() + slot * H + rank * HS + hl] = pre;
           hid = fmaxf(pre, 0.f);
         }
-        quad_push(round, hid, i, HS, act(round), PITCHX);
+        quad_push(round, hid, i, HS, act(round));
       }
       xwait(round);
-      for (int job = uwarp; job < NM2 * NKC; job += 8) {
-        const int mt = job / NKC, kc = job % NKC;
-        mma_job<false>(s_w2, PITCHH, DS, s_zrow, mt, kc * (H / 16) / NKC, (kc + 1) * (H / 16) / NKC, act(round), nullptr, PITCHX,
-                       P + kc * NM2 * 128, lane);
-      }
+      product(C::COL_WX, act(round), H / 16, C::COL_GI, 0);
       ++round;
       if (!last) arm(round, (uint32_t)(K * D * 2));
+      product_wait(0);
+      unload(C::COL_GI, P_GI, 0);
       upd_sync();
       PP_T(6);
       // ============================================================ R5: all-gather the new slots (or write them out)
@@ -829,14 +876,11 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
         float sn = 0.f;
         if (i < K * DS) {
           const int slot = i / DS, dl = i % DS;
-          float sum = s_b2[dl];
-#pragma unroll
-          for (int kc = 0; kc < NKC; ++kc) sum += P[(kc * NM2 * 16 + dl) * 8 + slot];
-          sn = own[i] + sum;
+          sn = own[i] + (s_b2[dl] + P_GI[(3 * DS + HS + dl) * 8 + slot]);
           own[i] = sn;
           if (last) a.slots_out[((size_t)img * K + slot) * D + rank * DS + dl] = sn;
         }
-        if (!last) quad_push(round, sn, i, DS, slh_hi(l), PITCH);
+        if (!last) quad_push(round, sn, i, DS, slh_hi(l));
       }
       if (!last) {
         xwait(round);
@@ -918,14 +962,14 @@ int sa_iter_fwd_umma_dispatch(const IterFwdArgs& a, cudaStream_t s) {
   }
   if (a.D == 192 && a.H == 192) {
     if (a.K <= 6) {
-      if (a.lanes == 3) return umma::launch_umma<192, 192, 8, 3, 6, 2, 2, 1>(a, s);
-      return umma::launch_umma<192, 192, 8, 2, 6, 2, 2, 2>(a, s);
+      if (a.lanes == 3) return umma::launch_umma<192, 192, 8, 3, 6, 3, 4, 2>(a, s);
+      return umma::launch_umma<192, 192, 8, 2, 6, 3, 4, 2>(a, s);
     }
-    return umma::launch_umma<192, 192, 8, 2, 8, 2, 2, 1>(a, s);
+    return umma::launch_umma<192, 192, 8, 2, 8, 3, 4, 2>(a, s);
   }
   if (a.D == 64 && a.H == 128) {  // the "Slot-Attention (small)" configuration
-    if (a.B >= 48 && a.lanes != 3) return umma::launch_umma<64, 128, 4, 2, 8, 4, 4, 2>(a, s);
-    return umma::launch_umma<64, 128, 8, 3, 8, 4, 4, 2>(a, s);
+    if (a.B >= 48 && a.lanes != 3) return umma::launch_umma<64, 128, 4, 2, 8, 6, 6, 2>(a, s);
+    return umma::launch_umma<64, 128, 8, 3, 8, 6, 6, 2>(a, s);
   }
   set_error("sa_iter_fwd(tcgen05): D=%d H=%d not instantiated", a.D, a.H);
   return OCRL_E_SHAPE;

@@ -238,15 +238,52 @@ def _():
     return im, ops, 32, dict(coded="A2", coff=A_OFF, M=128, N=16)
 
 
+def _tmem_a_case(M, N, sbo_zero=False):
+    """A from tensor memory: word (lane, col) = bf16 pair coded as 0x3F80 + lane*32 + col*2 + half"""
+    im = base_image()
+    if N == 16 and sbo_zero:  # 8 selector rows, second 8-row group aliased onto the first (SBO = 0)
+        for n in range(8):
+            put_bf16(im, B_OFF + n * 16 + (n % 8) * 2, 1.0)  # no-swizzle [k/8][8 n][8]: (n, k=n) -> k chunk 0
+        db = desc(B_OFF, 128, 0, SW_NONE)
+    else:
+        db = b_sel(im, N)
+    tcols = 16
+    lane = np.arange(128, dtype=np.uint32)[:, None]
+    col = np.arange(tcols, dtype=np.uint32)[None, :]
+    lo = 0x3F80 + lane * 32 + col * 2
+    timg = (lo | ((lo + 1) << 16)).astype(np.uint32)
+    ops = [(256, db, idesc(M, N), 0, 0, 0x80000000)]
+    return im, ops, 32, dict(coded="TA", coff=0, M=M, N=N, timage=timg)
+
+
+@case("c20_a_tmem_m128_n16")
+def _():
+    return _tmem_a_case(128, 16)
+
+
+@case("c21_a_tmem_m64_n8")
+def _():
+    return _tmem_a_case(64, 8)
+
+
+@case("c22_a_tmem_m128_n16_sbo0")
+def _():
+    return _tmem_a_case(128, 16, sbo_zero=True)
+
+
 def gen(outdir):
     os.makedirs(outdir, exist_ok=True)
     for name, fn in CASES.items():
-        im, ops, ncols, _ = fn()
+        im, ops, ncols, info = fn()
+        timg = info.get("timage")
         with open(os.path.join(outdir, name + ".case.bin"), "wb") as f:
-            f.write(struct.pack("<4i", im.size, len(ops), ncols, 0))
-            for (da, db, idc, dcol, acc) in ops:
-                f.write(struct.pack("<QQIIII", da, db, idc, dcol, acc, 0))
+            f.write(struct.pack("<4i", im.size, len(ops), ncols, 0 if timg is None else timg.shape[1]))
+            for op in ops:
+                da, db, idc, dcol, acc = op[:5]
+                f.write(struct.pack("<QQIIII", da, db, idc, dcol, acc, op[5] if len(op) > 5 else 0))
             f.write(im.tobytes())
+            if timg is not None:
+                f.write(timg.tobytes())
     print("wrote", len(CASES), "cases to", outdir)
 
 
@@ -267,6 +304,13 @@ def decode(casedir, outdir):
         if info["coded"] == "A2":
             # sum of two coded values; just print a few raw numbers
             print("   D[0][0..3] =", out[0, :4], " D[1][0..3] =", out[1, :4])
+            continue
+        if info["coded"] == "TA":
+            code = (bits >> 16).astype(np.int64) - 0x3F80
+            code[~written] = -1
+            for l in [x for x in (0, 1, 15, 16, 31, 32, 33, 64, 100, 127) if x in set(lanes.tolist())]:
+                print(f"   lane {l:3d}: (src lane, col, half) =", " ".join(
+                    f"({int(cd) // 32},{(int(cd) % 32) // 2},{int(cd) % 2})" if cd >= 0 else "-" for cd in code[l, :N]))
             continue
         offs = ((bits >> 16).astype(np.int64) - 0x3F80) * 2
         offs[~written] = -1

@@ -21,7 +21,8 @@ struct MmaOp {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __global__ void __launch_bounds__(128, 1)
-probe_kernel(const uint8_t* image, int image_bytes, const MmaOp* ops, int nops, float* out, int ncols, float sentinel) {
+probe_kernel(const uint8_t* image, int image_bytes, const MmaOp* ops, int nops, float* out, int ncols, float sentinel,
+             const uint32_t* timage, int tcols) {
   extern __shared__ __align__(1024) unsigned char sm_raw[];
   unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(sm_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar;
@@ -47,6 +48,11 @@ probe_kernel(const uint8_t* image, int image_bytes, const MmaOp* ops, int nops, 
     for (int c = 0; c < ncols; c += 8) {
       asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(trow + c), "r"(s) : "memory");
     }
+    // optional A-operand image: this thread's lane, columns [256, 256 + tcols)
+    for (int c = 0; c < tcols; ++c) {
+      const uint32_t w = timage[(size_t)tid * tcols + c];
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(trow + 256 + c), "r"(w) : "memory");
+    }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -57,11 +63,18 @@ probe_kernel(const uint8_t* image, int image_bytes, const MmaOp* ops, int nops, 
     for (int i = 0; i < nops; ++i) {
       const MmaOp o = ops[i];
       const uint64_t da = o.da + base, db = o.db + base;
-      asm volatile(
-          "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-          "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem + o.dcol),
-          "l"(da), "l"(db), "r"(o.idesc), "r"(o.acc)
-          : "memory");
+      if (o.pad & 0x80000000u)
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem + o.dcol),
+            "r"(tmem + (uint32_t)o.da), "l"(db), "r"(o.idesc), "r"(o.acc)
+            : "memory");
+      else
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem + o.dcol),
+            "l"(da), "l"(db), "r"(o.idesc), "r"(o.acc)
+            : "memory");
     }
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
   }
@@ -104,12 +117,17 @@ int main(int argc, char** argv) {
   if (!f) return 1;
   int32_t hdr[4];
   if (fread(hdr, 4, 4, f) != 4) return 1;
-  const int image_bytes = hdr[0], nops = hdr[1], ncols = hdr[2];
+  const int image_bytes = hdr[0], nops = hdr[1], ncols = hdr[2], tcols = hdr[3];
   std::vector<MmaOp> ops(nops);
   std::vector<uint8_t> image(image_bytes);
   if (fread(ops.data(), sizeof(MmaOp), nops, f) != (size_t)nops) return 1;
   if (fread(image.data(), 1, image_bytes, f) != (size_t)image_bytes) return 1;
+  std::vector<uint32_t> timage((size_t)128 * (tcols > 0 ? tcols : 1));
+  if (tcols > 0 && fread(timage.data(), 4, (size_t)128 * tcols, f) != (size_t)128 * tcols) return 1;
   fclose(f);
+  uint32_t* d_timg;
+  CK(cudaMalloc(&d_timg, timage.size() * 4));
+  CK(cudaMemcpy(d_timg, timage.data(), timage.size() * 4, cudaMemcpyHostToDevice));
   uint8_t* d_img;
   MmaOp* d_ops;
   float* d_out;
@@ -120,7 +138,7 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(d_ops, ops.data(), nops * sizeof(MmaOp), cudaMemcpyHostToDevice));
   const int smem = image_bytes + 2048;
   CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  probe_kernel<<<1, 128, smem>>>(d_img, image_bytes, d_ops, nops, d_out, ncols, 12345.0f);
+  probe_kernel<<<1, 128, smem>>>(d_img, image_bytes, d_ops, nops, d_out, ncols, 12345.0f, d_timg, tcols);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   std::vector<float> out(128 * ncols);
