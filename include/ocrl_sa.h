@@ -41,7 +41,9 @@ enum { OCRL_DT_F32 = 0, OCRL_DT_BF16 = 1 };
 /* x_format: layout / type of the token-stage input */
 enum { OCRL_X_TOKENS_F32 = 0  /* [B,N,C_in] fp32 */,
        OCRL_X_NCHW_F32 = 1    /* CNN feature map [B,C_in,H*W] fp32 (transposed on the way in) */,
-       OCRL_X_TOKENS_BF16 = 2 /* [B,N,C_in] bf16, e.g. a channels-last bf16 feature map (tensor path only) */ };
+       OCRL_X_TOKENS_BF16 = 2 /* [B,N,C_in] bf16, e.g. a channels-last bf16 feature map (tensor path only) */,
+       OCRL_X_PADDED_BF16 = 3 /* bf16 feature map in the padded channels-last layout of ocrl_conv5x5_c64_tc
+                                 (tensor path only; dims->frame_w = W, N = H*W) */ };
 /* math_mode: how the token contractions are evaluated */
 enum { OCRL_MATH_FP32 = 0 /* fp32 FFMA everywhere (parity mode) */,
        OCRL_MATH_TENSOR = 1 /* bf16 operands on tensor cores, fp32 accumulate */ };
@@ -63,6 +65,7 @@ typedef struct ocrl_sa_dims {
   int32_t kv_dtype; /* OCRL_DT_* storage type of k and v */
   int32_t math_mode;/* OCRL_MATH_* */
   int32_t x_format; /* OCRL_X_* (token stage only) */
+  int32_t frame_w;  /* frame width W for OCRL_X_PADDED_BF16 (0 otherwise) */
 } ocrl_sa_dims;
 
 /* Parameters of the iteration loop, fp32, in the reference's state_dict layout
@@ -187,6 +190,23 @@ int ocrl_conv_bias_relu_bf16(void* y, const float* bias, long long npixels, int 
 int ocrl_conv_first_relu_bf16(const float* obs, const float* weight, const float* bias, void* out, int B, int C,
                               int H, int W, int CO, void* stream);
 int ocrl_frames_to_nhwc_bf16(const float* obs, void* out, int B, int C, int H, int W, int CP, void* stream);
+
+/* Layers 2-4 of SlotAttnCNNEncoder (ocrs/common/models.py:100-102: Conv2dBlock(64, 64, 5, 1, 2) x2 and the final
+ * conv2d(64, 64, 5, 1, 2)) as a hand-written tcgen05 implicit GEMM, bf16 operands / fp32 accumulate.
+ * Activations use a PADDED channels-last layout: a flat bf16 array [(2 + B*(H+2)) rows][W+4][64]; image b, pixel (y, x)
+ * sits at row 2 + b*(H+2) + y, column x + 2; every other position is zero (the convolution's zero padding is stored).
+ * The caller allocates ocrl_conv_padded_bytes(B, H, W) bytes per array; no initialisation is needed: both producers
+ * below write every position of their output (real pixels, or zeros at the padding positions).
+ *   ocrl_conv5x5_pack_weights: weight [64,64,5,5] fp32 (OIHW, the reference's state_dict) -> packed bf16 [25][64][64]
+ *     (25*64*64*2 bytes, 128-byte aligned); once per parameter version.
+ *   ocrl_conv5x5_c64_tc: out = conv5x5(in) (+ bias[64] if not NULL) (ReLU if relu != 0); W in {32, 64, 128}.
+ *   ocrl_conv_first_relu_bf16p: ocrl_conv_first_relu_bf16 writing the padded layout. */
+size_t ocrl_conv_padded_bytes(int B, int H, int W);
+int ocrl_conv5x5_pack_weights(const float* weight, void* packed, int CO, int CI, void* stream);
+int ocrl_conv5x5_c64_tc(const void* in_padded, const void* packed_w, const float* bias, void* out_padded, int B, int H,
+                        int W, int relu, void* stream);
+int ocrl_conv_first_relu_bf16p(const float* obs, const float* weight, const float* bias, void* out_padded, int B, int C,
+                               int H, int W, int CO, void* stream);
 
 #ifdef __cplusplus
 }

@@ -16,13 +16,14 @@ LIB_PATH = os.path.join(HERE, "csrc", "libocrl_sa.so")
 
 DT_F32, DT_BF16 = 0, 1
 MATH_FP32, MATH_TENSOR = 0, 1
-X_TOKENS_F32, X_NCHW_F32, X_TOKENS_BF16 = 0, 1, 2
+X_TOKENS_F32, X_NCHW_F32, X_TOKENS_BF16, X_PADDED_BF16 = 0, 1, 2, 3
 
 EXPORTS = [
     "ocrl_version", "ocrl_built_arch", "ocrl_last_error", "ocrl_sa_query_workspace",
     "ocrl_kv_proj_fwd_workspace", "ocrl_kv_proj_fwd", "ocrl_kv_proj_bwd_workspace", "ocrl_kv_proj_bwd",
     "ocrl_sa_iter_fwd", "ocrl_sa_iter_fwd_ex", "ocrl_sa_last_kernel", "ocrl_sa_iter_bwd",
     "ocrl_conv_bias_relu_bf16", "ocrl_frames_to_nhwc_bf16", "ocrl_conv_first_relu_bf16",
+    "ocrl_conv_padded_bytes", "ocrl_conv5x5_pack_weights", "ocrl_conv5x5_c64_tc", "ocrl_conv_first_relu_bf16p",
 ]
 
 # ocrl_sa_launch_opts.variant
@@ -33,7 +34,7 @@ SA_VARIANTS = {"auto": SA_AUTO, "tcgen05": SA_TCGEN05, "pipe": SA_PIPE, "cluster
 class SaDims(Structure):
     _fields_ = [("B", c_int32), ("N", c_int32), ("C_in", c_int32), ("D", c_int32), ("H_mlp", c_int32),
                 ("K", c_int32), ("T", c_int32), ("heads", c_int32), ("eps", c_float), ("ln_eps", c_float),
-                ("kv_dtype", c_int32), ("math_mode", c_int32), ("x_format", c_int32)]
+                ("kv_dtype", c_int32), ("math_mode", c_int32), ("x_format", c_int32), ("frame_w", c_int32)]
 
 
 _SA_W = ["ln_slots_w", "ln_slots_b", "ln_mlp_w", "ln_mlp_b", "wq", "w_ih", "w_hh", "b_ih", "b_hh",
@@ -101,6 +102,14 @@ def lib() -> ctypes.CDLL:
         L.ocrl_conv_first_relu_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                                 c_int, c_void_p]
         L.ocrl_conv_first_relu_bf16.restype = c_int
+        L.ocrl_conv_first_relu_bf16p.argtypes = L.ocrl_conv_first_relu_bf16.argtypes
+        L.ocrl_conv_first_relu_bf16p.restype = c_int
+        L.ocrl_conv_padded_bytes.argtypes = [c_int, c_int, c_int]
+        L.ocrl_conv_padded_bytes.restype = c_size_t
+        L.ocrl_conv5x5_pack_weights.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p]
+        L.ocrl_conv5x5_pack_weights.restype = c_int
+        L.ocrl_conv5x5_c64_tc.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
+        L.ocrl_conv5x5_c64_tc.restype = c_int
         for name in ("ocrl_sa_query_workspace", "ocrl_kv_proj_fwd", "ocrl_kv_proj_bwd", "ocrl_sa_iter_fwd",
                      "ocrl_sa_iter_fwd_ex", "ocrl_sa_iter_bwd", "ocrl_conv_bias_relu_bf16", "ocrl_frames_to_nhwc_bf16"):
             getattr(L, name).restype = c_int
@@ -126,8 +135,8 @@ def stream_ptr() -> c_void_p:
 
 
 def make_dims(B, N, C_in, D, H_mlp, K, T, heads=1, eps=1e-8, ln_eps=1e-5, kv_dtype=DT_F32, math_mode=MATH_FP32,
-              x_format=X_TOKENS_F32):
-    return SaDims(B, N, C_in, D, H_mlp, K, T, heads, eps, ln_eps, kv_dtype, math_mode, x_format)
+              x_format=X_TOKENS_F32, frame_w=0):
+    return SaDims(B, N, C_in, D, H_mlp, K, T, heads, eps, ln_eps, kv_dtype, math_mode, x_format, frame_w)
 
 
 def query_workspace(dims: SaDims):

@@ -139,6 +139,10 @@ int ocrl_kv_proj_fwd(const ocrl_sa_dims* d, const void* x, const float* pos_tabl
     rc = kv_proj_tc_launch(d, x, pos_table, w, y_out, k_out, v_out, workspace, (cudaStream_t)stream);
     if (rc != OCRL_E_SHAPE) return rc;  // shapes the tcgen05 kernel does not cover take the FFMA kernel
   }
+  if (d->x_format == OCRL_X_PADDED_BF16 || d->x_format == OCRL_X_TOKENS_BF16) {
+    set_error("kv_proj_fwd: bf16 token / padded feature-map input is a tensor-path format (bf16 k/v, math_mode TENSOR, workspace)");
+    return OCRL_E_SHAPE;
+  }
   return token_stage_launch(d, x, pos_table, w, y_out, k_out, v_out, (cudaStream_t)stream);
 }
 

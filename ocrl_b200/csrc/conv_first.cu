@@ -27,7 +27,7 @@ constexpr int XP = 8;        // left margin (elements) of a staged row: x = -2 s
 template <int C>
 __global__ void __launch_bounds__(NW * 32, 2) conv_first_kernel(const float* __restrict__ obs, const float* __restrict__ w,
                                                                 const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
-                                                                int B, int H, int W) {
+                                                                int B, int H, int W, int padded) {
   static_assert(C * KS * KS <= KT * 16, "taps must fit the padded K");
   extern __shared__ __align__(16) unsigned char smem[];
   const int RP = W + 2 * XP;  // staged row pitch (elements); columns [XP-2, XP+W+2) are read
@@ -74,6 +74,19 @@ __global__ void __launch_bounds__(NW * 32, 2) conv_first_kernel(const float* __r
   // the margins are written once; the staging below only touches columns [XP, XP + W)
   for (int i = tid; i < C * NR * RP; i += NW * 32) rows[i] = __float2bfloat16_rn(0.f);
 
+  if (padded) {  // padding positions of the output array: whole rows between the images, two columns either side of a row
+    const int WPd = W + 4, rows_total = 2 + B * (H + 2);
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (int g = blockIdx.x * NW + warp; g < rows_total; g += gridDim.x * NW) {
+      uint4* rowp = reinterpret_cast<uint4*>(out + (size_t)g * WPd * CO);
+      const bool real = g >= 2 && ((g - 2) % (H + 2)) < H;
+      if (!real) {
+        for (int i = lane; i < WPd * 8; i += 32) rowp[i] = z;
+      } else {
+        rowp[lane < 16 ? lane : (W + 2) * 8 + (lane - 16)] = z;  // positions 0, 1 and W + 2, W + 3 (8 chunks of 16 B each)
+      }
+    }
+  }
   const int yblocks = (H + RB - 1) / RB;
   const int nblocks = B * yblocks;
   const int W4 = W / 4;
@@ -124,7 +137,10 @@ __global__ void __launch_bounds__(NW * 32, 2) conv_first_kernel(const float* __r
             pack_bf16x2(fmaxf(acc[nt][2] + bv[nt][0], 0.f), fmaxf(acc[nt][3] + bv[nt][1], 0.f));
       }
       __syncwarp();
-      __nv_bfloat16* dst = out + (((size_t)b * H + y0 + ry) * W + x0) * CO;  // 16 pixels x 128 bytes, contiguous
+      // 16 pixels x 128 bytes, contiguous; `padded`: the layout of conv_tc.cu (two zero rows between images, two zero
+      // columns either side of a row -- the zeros are the caller's, only real pixels are written)
+      __nv_bfloat16* dst = padded ? out + (((size_t)2 + (size_t)b * (H + 2) + y0 + ry) * (W + 4) + 2 + x0) * CO
+                                  : out + (((size_t)b * H + y0 + ry) * W + x0) * CO;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int chunk = lane + 32 * i;         // 16-byte chunk of the 2 KB tile
@@ -141,8 +157,8 @@ __global__ void __launch_bounds__(NW * 32, 2) conv_first_kernel(const float* __r
 
 using namespace ocrl;
 
-extern "C" int ocrl_conv_first_relu_bf16(const float* obs, const float* weight, const float* bias, void* out, int B, int C,
-                                         int H, int W, int CO, void* stream) {
+static int conv_first_launch(const float* obs, const float* weight, const float* bias, void* out, int B, int C, int H, int W,
+                             int CO, int padded, void* stream) {
   if (!obs || !weight || !bias || !out || (reinterpret_cast<uintptr_t>(out) & 15u)) {
     set_error("conv_first: null or unaligned pointer");
     return OCRL_E_ALIGN;
@@ -160,7 +176,17 @@ extern "C" int ocrl_conv_first_relu_bf16(const float* obs, const float* weight, 
   if (smem > 48 * 1024) OCRL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nblocks = B * ((H + conv1::RB - 1) / conv1::RB);
   const int grid = nblocks < 148 * 2 ? nblocks : 148 * 2;  // one wave at 2 CTAs (16 warps) per SM; the weight fragments are built once per CTA
-  kern<<<grid, conv1::NW * 32, smem, (cudaStream_t)stream>>>(obs, weight, bias, reinterpret_cast<__nv_bfloat16*>(out), B, H, W);
+  kern<<<grid, conv1::NW * 32, smem, (cudaStream_t)stream>>>(obs, weight, bias, reinterpret_cast<__nv_bfloat16*>(out), B, H, W,
+                                                              padded);
   OCRL_CHECK_CUDA(cudaGetLastError());
   return OCRL_OK;
+}
+
+extern "C" int ocrl_conv_first_relu_bf16(const float* obs, const float* weight, const float* bias, void* out, int B, int C,
+                                         int H, int W, int CO, void* stream) {
+  return conv_first_launch(obs, weight, bias, out, B, C, H, W, CO, 0, stream);
+}
+extern "C" int ocrl_conv_first_relu_bf16p(const float* obs, const float* weight, const float* bias, void* out_padded, int B,
+                                          int C, int H, int W, int CO, void* stream) {
+  return conv_first_launch(obs, weight, bias, out_padded, B, C, H, W, CO, 1, stream);
 }

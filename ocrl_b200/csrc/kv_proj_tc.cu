@@ -33,6 +33,7 @@ struct ProjTcParams {
   long long* trace;                               // optional clock64 stamps of CTA 0 / thread 0 (development aid)
   int has_mlp, x_format, N, D;
   int pos_tiles;                                  // 1: the position table arrives as bf16 [N][64] tiles through TMA (tm_pos)
+  int pad_w, pad_h;                               // > 0: bf16 tokens come from the padded layout of conv_tc.cu (frame W x H)
   long long M;
   int ntiles;
   float ln_eps;
@@ -246,7 +247,14 @@ kv_proj_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           const int b = (int)(m0 / p.N), n0 = (int)(m0 % p.N);
           tma_load_2d(dst, &tm_x, n0, b * PT_C, &full[s]);           // [64 ch][128 tokens] fp32
         } else if (p.x_format == OCRL_X_TOKENS_BF16) {
-          tma_load_2d(dst, &tm_x, 0, (int)(tile * PT_TM), &full[s]);  // [128 tokens][64] bf16, swizzled
+          if (p.pad_w > 0) {  // 128 tokens = 128 / W image rows of the padded feature map, one box of W positions each
+            const long long m0 = tile * PT_TM;
+            const int b = (int)(m0 / p.N), y0 = (int)(m0 % p.N) / p.pad_w;
+            for (int j = 0; j < PT_TM / p.pad_w; ++j)
+              tma_load_2d(dst + j * p.pad_w * 128, &tm_x, 0, (2 + b * (p.pad_h + 2) + y0 + j) * (p.pad_w + 4) + 2, &full[s]);
+          } else {
+            tma_load_2d(dst, &tm_x, 0, (int)(tile * PT_TM), &full[s]);  // [128 tokens][64] bf16, swizzled
+          }
           if (p.pos_tiles)  // the matching rows of the bf16 position table ride in the unused half of the stage
             tma_load_2d(dst + X_BYTES / 2, &tm_pos, 0, (int)((tile * PT_TM) % p.N), &full[s]);
         } else {
@@ -522,13 +530,19 @@ int kv_proj_tc_launch(const ocrl_sa_dims* d, const void* x, const float* pos, co
   const long long M = (long long)d->B * d->N;
   if (d->C_in != PT_C || (D != 64 && D != 128 && D != 192) || workspace == nullptr) return OCRL_E_SHAPE;
   if (d->x_format == OCRL_X_NCHW_F32 && (d->N % PT_TM) != 0) return OCRL_E_SHAPE;  // a tile must not straddle two images
+  const bool padded = (d->x_format == OCRL_X_PADDED_BF16);
+  const int pw = padded ? d->frame_w : 0, ph = (padded && pw > 0) ? d->N / pw : 0;
+  if (padded && ((pw != 32 && pw != 64 && pw != 128) || d->N % pw != 0 || d->N % PT_TM != 0)) {
+    set_error("kv_proj(tensor): padded feature map needs frame_w in {32, 64, 128} and N a multiple of 128 (frame_w=%d, N=%d)", pw, d->N);
+    return OCRL_E_SHAPE;
+  }
   if (!encode_fn()) return OCRL_E_SHAPE;
   __nv_bfloat16* w1b = reinterpret_cast<__nv_bfloat16*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
   __nv_bfloat16* w2b = w1b + 64 * 64;
   __nv_bfloat16* wkvb = w2b + 64 * 64;
   const bool has_mlp = w->mlp_w1 != nullptr;
   // bf16 tokens with a position table whose tiles never straddle two images: the table goes through TMA as well
-  const bool pos_tiles = (d->x_format == OCRL_X_TOKENS_BF16 && pos != nullptr && d->N % PT_TM == 0);
+  const bool pos_tiles = ((d->x_format == OCRL_X_TOKENS_BF16 || padded) && pos != nullptr && d->N % PT_TM == 0);
   __nv_bfloat16* posb = wkvb + (size_t)2 * D * 64;
   const int prep_threads = (pos_tiles && 8 * d->N > D * 64) ? 8 * d->N : D * 64;
   proj_tc_prep_kernel<<<(prep_threads + 255) / 256, 256, 0, stream>>>(w->mlp_w1, w->mlp_w2, w->wk, w->wv, w1b, w2b, wkvb, D,
@@ -541,6 +555,9 @@ int kv_proj_tc_launch(const ocrl_sa_dims* d, const void* x, const float* pos, co
   if (d->x_format == OCRL_X_NCHW_F32)  // NCHW feature map viewed as [B*64][N]; box = 128 tokens x 64 channels
     ok &= make_map(&tm_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, (uint64_t)d->N, (uint64_t)d->B * PT_C,
                    (uint64_t)d->N * 4, PT_TM, PT_C, CU_TENSOR_MAP_SWIZZLE_NONE);
+  else if (padded)  // flat positions [(2 + B (H + 2)) (W + 4)][64] bf16: boxes of W positions (one image row)
+    ok &= make_map(&tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, x, PT_C, (uint64_t)(2 + (uint64_t)d->B * (ph + 2)) * (pw + 4),
+                   PT_C * 2, PT_C, (uint32_t)pw, CU_TENSOR_MAP_SWIZZLE_128B);
   else if (d->x_format == OCRL_X_TOKENS_BF16)  // bf16 tokens [M][64]: one 128-byte-swizzled box of 128 rows
     ok &= make_map(&tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, x, PT_C, (uint64_t)M, PT_C * 2, PT_C, PT_TM,
                    CU_TENSOR_MAP_SWIZZLE_128B);
@@ -569,7 +586,8 @@ int kv_proj_tc_launch(const ocrl_sa_dims* d, const void* x, const float* pos, co
   p.in_ln_w = w->in_ln_w; p.in_ln_b = w->in_ln_b; p.pos = pos; p.y_out = y_out;
   p.trace = nullptr;
   p.pos_tiles = pos_tiles ? 1 : 0;
-  p.has_mlp = has_mlp ? 1 : 0; p.x_format = d->x_format; p.N = d->N; p.D = D; p.M = M;
+  p.has_mlp = has_mlp ? 1 : 0; p.x_format = padded ? OCRL_X_TOKENS_BF16 : d->x_format; p.N = d->N; p.D = D; p.M = M;
+  p.pad_w = pw; p.pad_h = ph;
   p.ntiles = (int)((M + PT_TM - 1) / PT_TM);
   p.ln_eps = d->ln_eps;
   int dev = 0, sms = 148;

@@ -29,6 +29,8 @@ int sa_iter_fwd_launch(const ocrl_sa_dims* d, const void* k, const void* v, cons
   a.eps = d->eps; a.ln_eps = d->ln_eps;
   a.trace = nullptr;
   a.wb16 = nullptr;
+  a.workspace = workspace;
+  a.workspace_bytes = workspace ? sa_iter_tc_workspace(d) : 0;
   a.max_clusters = o.max_clusters;
   a.lanes = o.lanes;
   if (o.trace && workspace != nullptr)  // last 4 KB of the workspace: phase timestamps

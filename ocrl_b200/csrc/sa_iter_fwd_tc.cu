@@ -631,7 +631,12 @@ __global__ void iter_tc_prep_kernel(ocrl_sa_weights w, __nv_bfloat16* out, int D
 }
 
 size_t sa_iter_tc_workspace(const ocrl_sa_dims* d) {
-  return sizeof(__nv_bfloat16) * ((size_t)7 * d->D * d->D + (size_t)2 * d->H_mlp * d->D) + 256 + 4096;
+  // bf16 weight copies of the per-image cluster kernel, or the tensor-memory blocks of the tcgen05 kernel
+  // ([<= 8 ranks][2][max(D,H)/2 words][128 rows] + folded-LayerNorm constants), whichever is larger; + alignment, trace slots
+  const size_t tc = sizeof(__nv_bfloat16) * ((size_t)7 * d->D * d->D + (size_t)2 * d->H_mlp * d->D);
+  const int lx = d->D > d->H_mlp ? d->D : d->H_mlp;
+  const size_t um = (size_t)8 * 2 * (lx / 2) * 128 * 4 + (size_t)(2 * d->H_mlp + 2 * d->D) * 4;
+  return (tc > um ? tc : um) + 256 + 4096;
 }
 
 // converts the weights into `workspace`; returns the bf16 pointer (256-byte aligned) or null

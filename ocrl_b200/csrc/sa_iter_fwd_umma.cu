@@ -8,7 +8,7 @@
 // leaves the shared memory to the k/v ring: seven 24 KB slots instead of four.  The pass engine is
 //   * warp 4 / warp 6, one lane each: TMA producers of the k ring and the v ring (64-token half tiles,
 //     [D/64][64 rows][128 B] with the 128-byte swizzle = the canonical UMMA layouts: K-major for k, MN-major for v);
-//   * warp 5, one lane: issues  logits[64 x 8] = k_half . q^T  (M = 64; the two halves of a 128-token pair land in
+//   * warps 5 and 7, one lane each: issue  logits[64 x 8] = k_half . q^T  (M = 64; the two halves of a 128-token pair land in
 //     the lower / upper 16 lanes of every 32-lane quarter of one tensor-memory buffer) and
 //     U^T[D x 16] += v_half^T . w  (M = 128 for features 0-127, M = 64 for 128-191), tcgen05.commit frees the ring
 //     slots and signals the softmax warps;
@@ -41,6 +41,7 @@ struct Cfg {
   static constexpr int DS = D / CL, HS = H / CL;
   // weight blocks in tensor memory (row = lane): X = W_ih (3 DS rows) | W1' (HS) | W2 (DS);  Y = W_hh (3 DS) | Wq' (DS)
   static constexpr int RX = 3 * DS + HS + DS, RY = 3 * DS + DS;
+  static constexpr int WPB = LX / 2;  // 32-bit words (bf16 pairs) per weight row in the prepared copy
   static constexpr int UP = D + 4;
   static constexpr int MA = NCH >= 2 ? 128 : 64;   // U product, features [0, 128) (or all 64)
   static constexpr bool HAS_B = NCH == 3;          // second U product, features [128, 192)
@@ -92,6 +93,10 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
   const int K = a.K, N = a.N, T = a.T, B = a.B;
   const bool tracer = (a.trace != nullptr && blockIdx.x == 0);
 #define PP_TRACE(i) do { if (tracer) a.trace[(i)] = clock64(); } while (0)
+  // kernel start / end of setup / kernel end of the first and the last cluster's CTA 0: trace[1..3], trace[4..6]
+  const bool tracer2 = (a.trace != nullptr && blockIdx.x == gridDim.x - CL && tid == 0);
+  if (tracer && tid == 0) a.trace[1] = clock64();
+  if (tracer2) a.trace[4] = clock64();
 
   unsigned char* kring = sm + C::OFF_KRING;
   unsigned char* vring = sm + C::OFF_VRING;
@@ -293,60 +298,31 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
   tc::fence_after();
   const uint32_t tmem = *tmem_slot;
   {
-    // The CTA's weight slices, fp32 global -> bf16 pairs in tensor memory, one weight row per thread (= lane):
-    // warps 0-3 fill block X, warps 8-11 block Y.  LayerNorm folded into the product that follows it:
-    // W LN(x) = rstd (W' x - mean c) + W beta,  W' = W diag(gamma),  c = row sums of the (bf16-rounded) W'.
+    // The CTA's weight slices -> tensor memory, one weight row per thread (= lane): warps 0-3 fill block X, warps 8-11
+    // block Y, from the bf16 pairs umma_prep_kernel laid out column-major ([word][row]: coalesced 4-byte loads).
     const bool fill_x = warp < 4, fill_y = (warp >= 8 && warp < 12);
     if (fill_x || fill_y) {
       const int r = (warp & 3) * 32 + lane;
-      const float* src = a.w.w_ih;
-      const float* gam = a.w.ln_mlp_w;
-      const float* bet = a.w.ln_mlp_b;
-      int len = 0, fold = 0;  // fold: 1 = W1' row, 2 = Wq' row
-      if (fill_x) {
-        if (r < 3 * DS) { src = a.w.w_ih + ((size_t)(r / DS) * D + rank * DS + r % DS) * D; len = D; }
-        else if (r < 3 * DS + HS) { src = a.w.w1 + ((size_t)rank * HS + (r - 3 * DS)) * D; len = D; fold = 1; }
-        else if (r < C::RX) { src = a.w.w2 + ((size_t)rank * DS + (r - 3 * DS - HS)) * H; len = H; }
-      } else {
-        if (r < 3 * DS) { src = a.w.w_hh + ((size_t)(r / DS) * D + rank * DS + r % DS) * D; len = D; }
-        else if (r < C::RY) { src = a.w.wq + ((size_t)rank * DS + (r - 3 * DS)) * D; len = D; fold = 2; gam = a.w.ln_slots_w; bet = a.w.ln_slots_b; }
-      }
-      const int lmax = fill_x ? C::LX : D;
+      const uint32_t* wsrc = a.wprep + ((size_t)(rank * 2 + (fill_x ? 0 : 1)) * C::WPB) * 128 + r;
+      const int nwords = fill_x ? C::LX / 2 : D / 2;
       const uint32_t tcol = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (fill_x ? C::COL_WX : C::COL_WY);
-      float csum = 0.f, bsum = 0.f;
-      for (int k0 = 0; k0 < lmax; k0 += 64) {  // 64 features per batch: sixteen 16-byte loads in flight
-        float4 x[16];
+      for (int w0 = 0; w0 < nwords; w0 += 32) {  // 32 loads in flight, then four stores of one k step (8 columns) each
+        uint32_t wv[32];
 #pragma unroll
-        for (int u = 0; u < 16; ++u)
-          x[u] = (k0 + 4 * u < len) ? __ldg(reinterpret_cast<const float4*>(src + k0) + u) : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (fold && k0 < len) {
+        for (int j = 0; j < 32; ++j) wv[j] = __ldg(wsrc + (size_t)(w0 + j) * 128);
 #pragma unroll
-          for (int u = 0; u < 16; ++u) {
-            const float4 g = __ldg(reinterpret_cast<const float4*>(gam + k0) + u);
-            const float4 b = __ldg(reinterpret_cast<const float4*>(bet + k0) + u);
-            bsum = fmaf(x[u].x, b.x, fmaf(x[u].y, b.y, fmaf(x[u].z, b.z, fmaf(x[u].w, b.w, bsum))));
-            x[u] = make_float4(x[u].x * g.x, x[u].y * g.y, x[u].z * g.z, x[u].w * g.w);
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {  // one k step (16 features = 8 columns) per store
-          uint32_t wv[8];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float4 v4 = x[4 * q + e];
-            const __nv_bfloat162 lo = __floats2bfloat162_rn(v4.x, v4.y), hi = __floats2bfloat162_rn(v4.z, v4.w);
-            csum += (__low2float(lo) + __high2float(lo)) + (__low2float(hi) + __high2float(hi));
-            wv[2 * e] = *reinterpret_cast<const uint32_t*>(&lo);
-            wv[2 * e + 1] = *reinterpret_cast<const uint32_t*>(&hi);
-          }
-          asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(tcol + (uint32_t)(k0 / 2 + 8 * q)),
-                       "r"(wv[0]), "r"(wv[1]), "r"(wv[2]), "r"(wv[3]), "r"(wv[4]), "r"(wv[5]), "r"(wv[6]), "r"(wv[7])
+        for (int q = 0; q < 4; ++q)
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(tcol + (uint32_t)(w0 + 8 * q)),
+                       "r"(wv[8 * q]), "r"(wv[8 * q + 1]), "r"(wv[8 * q + 2]), "r"(wv[8 * q + 3]), "r"(wv[8 * q + 4]),
+                       "r"(wv[8 * q + 5]), "r"(wv[8 * q + 6]), "r"(wv[8 * q + 7])
                        : "memory");
-        }
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      if (fold == 1) { s_c1[r - 3 * DS] = csum; s_b1f[r - 3 * DS] = bsum + a.w.b1[rank * HS + (r - 3 * DS)]; }
-      if (fold == 2) { s_cq[r - 3 * DS] = csum; s_bqf[r - 3 * DS] = bsum; }
+    }
+    {  // constants of the folded LayerNorms: c1[HS] b1'[HS] cq[DS] bq'[DS]
+      const float* cs = a.wprep_consts + (size_t)rank * (2 * HS + 2 * DS);
+      for (int i = tid; i < HS; i += C::NT) { s_c1[i] = __ldg(cs + i); s_b1f[i] = __ldg(cs + HS + i); }
+      for (int i = tid; i < DS; i += C::NT) { s_cq[i] = __ldg(cs + 2 * HS + i); s_bqf[i] = __ldg(cs + 2 * HS + DS + i); }
     }
     for (int i = tid; i < 3 * DS; i += C::NT) {
       const int gate = i / DS, dl = i % DS;
@@ -381,6 +357,7 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
   }
   cluster.sync();  // every CTA's barriers are initialised before any peer signals them
   if (tid == 0) PP_TRACE(0);
+  if (tracer2) a.trace[5] = clock64();
 
   if (warp < 8) {
     // ==================================================================================== PASS ENGINE
@@ -501,96 +478,98 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
       // ---- TMA producers: the rest of the stream (the first ring-full was issued during the setup)
       while (pj < total_ht) produce();
     } else if (warp == 5) {
-      // ---- MMA issuer: the whole warp runs the control flow (uniform operands), one elected lane issues
-      {
-        const bool leader = tc::elect_one();
-        constexpr uint32_t ID_LG = tc::idesc_bf16(64, 8);
-        constexpr uint32_t ID_UA = tc::idesc_bf16(C::MA, 16, 1, 0);
-        constexpr uint32_t ID_UB = tc::idesc_bf16(64, 16, 1, 0);
-        uint32_t gp = 0, gu = 0;  // pairs whose logit / U products have been issued
-        int jk = 0, jv = 0;       // half tiles consumed from the k / v rings
-        for (int n = 0; n < total_ops; ++n) {
-          int l, c;
-          op_of(n, l, c);
-          if (NP == 0) continue;
-          mbar_wait(&q_ready[l], (uint32_t)(c & 1));
-          fence_proxy_async();
-          tc::fence_after();
-          const uint32_t qa = smem_u32(qop(l));
-          const uint32_t ucol = tmem + C::COL_U + C::U_STRIDE * (n & 1);
-          const bool tn = tracer && lane == 0 && n == TRACE_OP;
-          auto logits = [&](int p) {
-            const uint32_t lb = gp & 1;
-            if (tn && p < 4) a.trace[340 + p * 12 + 6] = clock64();
-            if (gp >= 2) {
-              mbar_wait(&lg_empty[lb], ((gp >> 1) - 1) & 1);
-              tc::fence_after();
-            }
-            for (int h = 0; h < 2 && 2 * p + h < TP; ++h) {
-              const int s = jk % NKS;
-              mbar_wait(&k_full[s], (uint32_t)((jk / NKS) & 1));
-              tc::fence_after();
-              const uint32_t ka = smem_u32(kring + (size_t)s * C::HT_BYTES);
-              const uint32_t dcol = tmem + C::COL_LG + C::LG_STRIDE * lb + ((uint32_t)(16 * h) << 16);
-#pragma unroll
-              for (int ch = 0; ch < NCH; ++ch)
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                  if (leader)
-                    tc::mma_bf16(dcol, tc::smem_desc(ka + ch * C::CH_BYTES + ks * 32, 16, 1024, tc::SW_128),
-                                 tc::smem_desc(qa + (ch * 4 + ks) * 256, 128, 128, tc::SW_NONE), ID_LG, (ch | ks) != 0);
-              if (leader) tc::commit(&k_empty[s]);
-              __syncwarp();
-              ++jk;
-            }
-            if (leader) tc::commit(&lg_full[lb]);
-            __syncwarp();
-            ++gp;
-            if (tn && p < 4) a.trace[340 + p * 12 + 7] = clock64();
-          };
-          auto uprod = [&](int p) {
-            const uint32_t wb = gu % NWB;
-            if (tn && p < 4) a.trace[340 + p * 12 + 8] = clock64();
-            mbar_wait(&w_full[wb], (gu / NWB) & 1);
-            if (tn && p < 4) a.trace[340 + p * 12 + 9] = clock64();
+      // ---- MMA issuer of the logits: the whole warp runs the control flow (uniform operands), one elected lane issues.
+      // (The U products have an issuer warp of their own: an mbarrier wait costs ~100 cycles even when it is already
+      // complete, and a single issuer spent as long in its six waits per 128-token pair as in the MMAs.)
+      const bool leader = tc::elect_one();
+      constexpr uint32_t ID_LG = tc::idesc_bf16(64, 8);
+      uint32_t gp = 0;  // pairs whose logit products have been issued
+      int jk = 0;       // half tiles consumed from the k ring
+      for (int n = 0; n < total_ops; ++n) {
+        int l, c;
+        op_of(n, l, c);
+        if (NP == 0) continue;
+        mbar_wait(&q_ready[l], (uint32_t)(c & 1));
+        fence_proxy_async();
+        tc::fence_after();
+        const uint32_t qa = smem_u32(qop(l));
+        const bool tn = tracer && lane == 0 && n == TRACE_OP;
+        for (int p = 0; p < NP; ++p, ++gp) {
+          const uint32_t lb = gp & 1;
+          if (tn && p < 4) a.trace[340 + p * 12 + 6] = clock64();
+          if (gp >= 2) {
+            mbar_wait(&lg_empty[lb], ((gp >> 1) - 1) & 1);
             tc::fence_after();
-            if (p == 0 && n >= 2) {  // the accumulator was last used by op n - 2
-              mbar_wait(&u_accfree[n & 1], (uint32_t)(((n >> 1) - 1) & 1));
-              tc::fence_after();
-            }
-            for (int h = 0; h < 2 && 2 * p + h < TP; ++h) {
-              const int s = jv % NVS;
-              mbar_wait(&v_full[s], (uint32_t)((jv / NVS) & 1));
-              tc::fence_after();
-              const uint32_t va = smem_u32(vring + (size_t)s * C::HT_BYTES);
-              const uint32_t wa = smem_u32(wtiles + wb * C::WP_BYTES + h * C::WH_BYTES);
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {  // 16 tokens per step: two 8-token groups 1024 B apart, next step +2048 B
-                const uint32_t acc = (p | h | ks) != 0;
-                const uint64_t db = tc::smem_desc(wa + ks * 512, 256, 128, tc::SW_NONE);
-                if (leader) {
-                  tc::mma_bf16(ucol, tc::smem_desc(va + ks * 2048, C::CH_BYTES, 1024, tc::SW_128), db, ID_UA, acc);
-                  if (C::HAS_B)
-                    tc::mma_bf16(ucol + C::U_B, tc::smem_desc(va + 2 * C::CH_BYTES + ks * 2048, C::CH_BYTES, 1024, tc::SW_128), db, ID_UB, acc);
-                }
-              }
-              if (leader) tc::commit(&v_empty[s]);
-              __syncwarp();
-              ++jv;
-            }
-            if (leader) tc::commit(&w_empty[wb]);
-            __syncwarp();
-            ++gu;
-            if (tn && p < 4) a.trace[340 + p * 12 + 10] = clock64();
-          };
-          for (int p = 0; p < NP; ++p) {
-            logits(p);
-            if (p > 0) uprod(p - 1);
           }
-          uprod(NP - 1);
-          if (leader) tc::commit(&u_full[n & 1]);
+          for (int h = 0; h < 2 && 2 * p + h < TP; ++h) {
+            const int s = jk % NKS;
+            mbar_wait(&k_full[s], (uint32_t)((jk / NKS) & 1));
+            tc::fence_after();
+            const uint32_t ka = smem_u32(kring + (size_t)s * C::HT_BYTES);
+            const uint32_t dcol = tmem + C::COL_LG + C::LG_STRIDE * lb + ((uint32_t)(16 * h) << 16);
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                if (leader)
+                  tc::mma_bf16(dcol, tc::smem_desc(ka + ch * C::CH_BYTES + ks * 32, 16, 1024, tc::SW_128),
+                               tc::smem_desc(qa + (ch * 4 + ks) * 256, 128, 128, tc::SW_NONE), ID_LG, (ch | ks) != 0);
+            if (leader) tc::commit(&k_empty[s]);
+            __syncwarp();
+            ++jk;
+          }
+          if (leader) tc::commit(&lg_full[lb]);
           __syncwarp();
+          if (tn && p < 4) a.trace[340 + p * 12 + 7] = clock64();
         }
+      }
+    } else if (warp == 7) {
+      // ---- MMA issuer of U^T += v^T w
+      const bool leader = tc::elect_one();
+      constexpr uint32_t ID_UA = tc::idesc_bf16(C::MA, 16, 1, 0);
+      constexpr uint32_t ID_UB = tc::idesc_bf16(64, 16, 1, 0);
+      uint32_t gu = 0;  // pairs whose U products have been issued
+      int jv = 0;       // half tiles consumed from the v ring
+      for (int n = 0; n < total_ops; ++n) {
+        if (NP == 0) continue;
+        const uint32_t ucol = tmem + C::COL_U + C::U_STRIDE * (n & 1);
+        const bool tn = tracer && lane == 0 && n == TRACE_OP;
+        for (int p = 0; p < NP; ++p, ++gu) {
+          const uint32_t wb = gu % NWB;
+          if (tn && p < 4) a.trace[340 + p * 12 + 8] = clock64();
+          mbar_wait(&w_full[wb], (gu / NWB) & 1);
+          if (tn && p < 4) a.trace[340 + p * 12 + 9] = clock64();
+          tc::fence_after();
+          if (p == 0 && n >= 2) {  // the accumulator was last used by op n - 2
+            mbar_wait(&u_accfree[n & 1], (uint32_t)(((n >> 1) - 1) & 1));
+            tc::fence_after();
+          }
+          for (int h = 0; h < 2 && 2 * p + h < TP; ++h) {
+            const int s = jv % NVS;
+            mbar_wait(&v_full[s], (uint32_t)((jv / NVS) & 1));
+            tc::fence_after();
+            const uint32_t va = smem_u32(vring + (size_t)s * C::HT_BYTES);
+            const uint32_t wa = smem_u32(wtiles + wb * C::WP_BYTES + h * C::WH_BYTES);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {  // 16 tokens per step: two 8-token groups 1024 B apart, next step +2048 B
+              const uint32_t acc = (p | h | ks) != 0;
+              const uint64_t db = tc::smem_desc(wa + ks * 512, 256, 128, tc::SW_NONE);
+              if (leader) {
+                tc::mma_bf16(ucol, tc::smem_desc(va + ks * 2048, C::CH_BYTES, 1024, tc::SW_128), db, ID_UA, acc);
+                if (C::HAS_B)
+                  tc::mma_bf16(ucol + C::U_B, tc::smem_desc(va + 2 * C::CH_BYTES + ks * 2048, C::CH_BYTES, 1024, tc::SW_128), db, ID_UB, acc);
+              }
+            }
+            if (leader) tc::commit(&v_empty[s]);
+            __syncwarp();
+            ++jv;
+          }
+          if (leader) tc::commit(&w_empty[wb]);
+          __syncwarp();
+          if (tn && p < 4) a.trace[340 + p * 12 + 10] = clock64();
+        }
+        if (leader) tc::commit(&u_full[n & 1]);
+        __syncwarp();
       }
     }
     __syncwarp();
@@ -898,14 +877,86 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
   }
   tc::fence_before();
   __syncthreads();
+  if (tracer && tid == 0) a.trace[3] = clock64();
+  if (tracer2) a.trace[6] = clock64();
   if (warp == 7) tc::tmem_dealloc<C::TMEM_COLS>(tmem);
   cluster.sync();  // no CTA leaves while a peer may still address its shared memory
 }
 
 
+// Weight preparation, once per call: for every CTA rank the two tensor-memory blocks as bf16 pairs, column-major
+// ([rank][block][word][128 rows]) so that the main kernel's row threads read them coalesced, plus the constants of the
+// folded LayerNorms (W LN(x) = rstd (W' x - mean c) + W beta, W' = W diag(gamma), c = row sums of the rounded W').
+// One warp per weight row.
+template <int D, int H, int CL>
+__global__ void __launch_bounds__(256) umma_prep_kernel(const ocrl_sa_weights w, uint32_t* __restrict__ words, float* __restrict__ consts) {
+  constexpr int DS = D / CL, HS = H / CL, LX = D > H ? D : H, WPB = LX / 2;
+  constexpr int RX = 3 * DS + HS + DS, RY = 3 * DS + DS;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw >= CL * 2 * 128) return;
+  const int r = gw & 127, blk = (gw >> 7) & 1, rank = gw >> 8;
+  const float* src = nullptr;
+  const float* gam = nullptr;
+  const float* bet = nullptr;
+  int len = 0, fold = 0;
+  if (blk == 0) {
+    if (r < 3 * DS) { src = w.w_ih + ((size_t)(r / DS) * D + rank * DS + r % DS) * D; len = D; }
+    else if (r < 3 * DS + HS) { src = w.w1 + ((size_t)rank * HS + (r - 3 * DS)) * D; len = D; fold = 1; gam = w.ln_mlp_w; bet = w.ln_mlp_b; }
+    else if (r < RX) { src = w.w2 + ((size_t)rank * DS + (r - 3 * DS - HS)) * H; len = H; }
+  } else {
+    if (r < 3 * DS) { src = w.w_hh + ((size_t)(r / DS) * D + rank * DS + r % DS) * D; len = D; }
+    else if (r < RY) { src = w.wq + ((size_t)rank * DS + (r - 3 * DS)) * D; len = D; fold = 2; gam = w.ln_slots_w; bet = w.ln_slots_b; }
+  }
+  uint32_t* dst = words + ((size_t)(rank * 2 + blk) * WPB) * 128 + r;
+  float csum = 0.f, bsum = 0.f;
+  for (int w0 = 0; w0 < WPB; w0 += 32) {
+    const int f = 2 * (w0 + lane);
+    float2 x = make_float2(0.f, 0.f);
+    if (f < len) {
+      x = __ldg(reinterpret_cast<const float2*>(src + f));
+      if (fold) {
+        const float2 g = __ldg(reinterpret_cast<const float2*>(gam + f)), b = __ldg(reinterpret_cast<const float2*>(bet + f));
+        bsum = fmaf(x.x, b.x, fmaf(x.y, b.y, bsum));
+        x = make_float2(x.x * g.x, x.y * g.y);
+      }
+    }
+    const __nv_bfloat162 pr = __floats2bfloat162_rn(x.x, x.y);
+    csum += __low2float(pr) + __high2float(pr);
+    dst[(size_t)(w0 + lane) * 128] = *reinterpret_cast<const uint32_t*>(&pr);
+  }
+  if (fold) {
+    csum = warp_sum(csum);
+    bsum = warp_sum(bsum);
+    if (lane == 0) {
+      float* cs = consts + (size_t)rank * (2 * HS + 2 * DS);
+      const int i = r - 3 * DS;
+      if (fold == 1) { cs[i] = csum; cs[HS + i] = bsum + w.b1[rank * HS + i]; }
+      else { cs[2 * HS + i] = csum; cs[2 * HS + DS + i] = bsum; }
+    }
+  }
+}
+
+template <int D, int H, int CL>
+static size_t umma_prep_bytes() {
+  constexpr int LX = D > H ? D : H;
+  return (size_t)CL * 2 * (LX / 2) * 128 * 4 + (size_t)CL * (2 * (H / CL) + 2 * (D / CL)) * 4;
+}
+
 template <int D, int H, int CL, int NL, int KB, int NKS, int NVS, int NWB>
-static int launch_umma(const IterFwdArgs& a, cudaStream_t stream) {
+static int launch_umma(const IterFwdArgs& a_in, cudaStream_t stream) {
   using C = Cfg<D, H, CL, NL, KB, NKS, NVS, NWB>;
+  IterFwdArgs a = a_in;
+  if (a.workspace == nullptr || a.workspace_bytes < umma_prep_bytes<D, H, CL>() + 4096 + 256) {
+    set_error("sa_iter_fwd(tcgen05): needs the workspace of ocrl_sa_query_workspace (bf16 weight copies)");
+    return OCRL_E_SHAPE;
+  }
+  {
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(a.workspace) + 255) & ~uintptr_t(255));
+    a.wprep = reinterpret_cast<uint32_t*>(base);
+    a.wprep_consts = reinterpret_cast<float*>(base + (size_t)CL * 2 * C::WPB * 128 * 4);
+    umma_prep_kernel<D, H, CL><<<CL * 2 * 128 / 8, 256, 0, stream>>>(a.w, const_cast<uint32_t*>(a.wprep), const_cast<float*>(a.wprep_consts));
+    OCRL_CHECK_CUDA(cudaGetLastError());
+  }
   auto kern = sa_iter_fwd_umma_kernel<D, H, CL, NL, KB, NKS, NVS, NWB>;
   static_assert(C::SMEM_BYTES <= 227 * 1024, "shared memory budget");
   CUtensorMap tm_k, tm_v;
@@ -961,11 +1012,14 @@ int sa_iter_fwd_umma_dispatch(const IterFwdArgs& a, cudaStream_t s) {
     return OCRL_E_SHAPE;
   }
   if (a.D == 192 && a.H == 192) {
+    // three lanes hide the slot update completely (B = 64: 122 against 133 us with two); two keep the k/v of the images
+    // in flight inside the L2 (compulsory DRAM traffic only)
     if (a.K <= 6) {
-      if (a.lanes == 3) return umma::launch_umma<192, 192, 8, 3, 6, 3, 4, 2>(a, s);
-      return umma::launch_umma<192, 192, 8, 2, 6, 3, 4, 2>(a, s);
+      if (a.lanes == 2) return umma::launch_umma<192, 192, 8, 2, 6, 3, 4, 2>(a, s);
+      return umma::launch_umma<192, 192, 8, 3, 6, 3, 4, 2>(a, s);
     }
-    return umma::launch_umma<192, 192, 8, 2, 8, 3, 4, 2>(a, s);
+    if (a.lanes == 2) return umma::launch_umma<192, 192, 8, 2, 8, 3, 4, 2>(a, s);
+    return umma::launch_umma<192, 192, 8, 3, 8, 3, 4, 2>(a, s);
   }
   if (a.D == 64 && a.H == 128) {  // the "Slot-Attention (small)" configuration
     if (a.B >= 48 && a.lanes != 3) return umma::launch_umma<64, 128, 4, 2, 8, 6, 6, 2>(a, s);

@@ -34,6 +34,10 @@ struct IterFwdArgs {
   float eps, ln_eps;
   long long* trace;  // optional: clock64() at phase boundaries of CTA 0 (development aid), else null
   const __nv_bfloat16* wb16;  // optional bf16 copies [wq | w_ih | w_hh | w1 | w2] for the tensor-core slot update
+  void* workspace = nullptr;         // caller's fwd workspace (ocrl_sa_query_workspace) and its size
+  size_t workspace_bytes = 0;
+  const uint32_t* wprep = nullptr;   // tcgen05 kernel: prepared weight words / folded-LayerNorm constants (inside the workspace)
+  const float* wprep_consts = nullptr;
   int max_clusters = 0;  // ocrl_sa_launch_opts: cap on the resident clusters of the persistent kernels (0 = launcher's choice)
   int lanes = 0;         // ocrl_sa_launch_opts: images in flight per cluster (0 = default)
 };

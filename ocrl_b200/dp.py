@@ -73,6 +73,11 @@ class GradientReducer:
 
     def _on_grad(self, p):
         i = self._bucket_of[id(p)]
+        if self._work[i] is not None:
+            # the bucket is already in flight with the first backward's gradients: a second backward before finish()
+            # (gradient accumulation) would be reduced partially
+            raise RuntimeError("GradientReducer: backward() ran twice before finish(); call finish() (or update()) "
+                               "after every backward, or accumulate micro-batches before the hooks fire")
         self._pending[i] -= 1
         if self._pending[i] == 0:
             self._launch(i)
@@ -81,15 +86,19 @@ class GradientReducer:
         bucket = self.buckets[i]
         grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in bucket]
         dev = grads[0].device
+        # one flag per parameter rides at the end of the bucket: did THIS rank produce a gradient?  Parameters no rank
+        # touched (e.g. the dVAE / transformer decoder when use_bcdec is on) keep grad = None, as on a single GPU, so
+        # the optimizer state matches a 1-GPU run
+        flags = torch.tensor([0.0 if p.grad is None else 1.0 for p in bucket], device=dev, dtype=grads[0].dtype)
         if dev.type == "cuda":
             if self._stream is None:
                 self._stream = torch.cuda.Stream(device=dev)
             self._stream.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(self._stream):
-                flat = torch.cat([g.reshape(-1) for g in grads])
+                flat = torch.cat([g.reshape(-1) for g in grads] + [flags])
                 self._work[i] = dist.all_reduce(flat, async_op=True)
         else:
-            flat = torch.cat([g.reshape(-1) for g in grads])
+            flat = torch.cat([g.reshape(-1) for g in grads] + [flags])
             self._work[i] = dist.all_reduce(flat, async_op=True)
         self._flat[i] = flat
 
@@ -105,13 +114,15 @@ class GradientReducer:
             flat = self._flat[i]
             if flat.is_cuda:
                 torch.cuda.current_stream(flat.device).wait_stream(self._stream)
+            touched = (flat[-len(bucket):] > 0).tolist()  # some rank produced a gradient for the parameter
             flat.div_(self.world)
             off = 0
-            for p in bucket:
+            for p, hit in zip(bucket, touched):
                 n = p.numel()
-                if p.grad is None:
-                    p.grad = torch.empty_like(p)
-                p.grad.copy_(flat[off:off + n].view_as(p))
+                if hit:
+                    if p.grad is None:
+                        p.grad = torch.empty_like(p)
+                    p.grad.copy_(flat[off:off + n].view_as(p))
                 off += n
         self.reset()
 

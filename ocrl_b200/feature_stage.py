@@ -2,8 +2,10 @@
 ocrs/common/utils.py:10-33): 4x conv5x5 (ReLU on the first three) and the linear-ramp position
 embedding.  Same module/parameter names as the reference.
 
-The convolutions currently call cuDNN through torch (library code); the
-position-table add and the NCHW -> token-major transpose are fused into the token-stage kernel.
+In bf16 mode the four convolutions are hand-written kernels (csrc/conv_first.cu: mma.sync first layer;
+csrc/conv_tc.cu: tcgen05 implicit GEMM for the 64 -> 64 layers) that hand a padded channels-last feature map to the
+token-stage kernel; the fp32 parity mode and the training path call cuDNN through torch.  The position-table add and
+the NCHW -> token-major transpose are fused into the token-stage kernel.
 """
 import torch
 import torch.nn as nn
@@ -25,6 +27,26 @@ class SlotAttnCNNEncoder(nn.Module):
         return self._encoder(obs)
 
 
+class PaddedMap:
+    """A bf16 feature map in the padded channels-last layout of ocrl_conv5x5_c64_tc (include/ocrl_sa.h):
+    ``data`` is the flat position array [(2 + B (H + 2)) (W + 4), 64]."""
+
+    def __init__(self, data, B, H, W):
+        self.data, self.B, self.H, self.W = data, B, H, W
+        self.shape = (B, data.shape[1], H, W)
+        self.is_cuda, self.device, self.dtype = data.is_cuda, data.device, data.dtype
+        self.requires_grad = False
+
+    def dim(self):
+        return 4
+
+    def to_nchw(self):
+        """[B, 64, H, W] view-copy (tests / debugging)."""
+        rows = self.data.view(-1, self.W + 4, self.data.shape[1])[2:]
+        rows = rows.view(self.B, self.H + 2, self.W + 4, -1)[:, : self.H, 2: self.W + 2]
+        return rows.permute(0, 3, 1, 2)
+
+
 class FusedBf16Encoder:
     """Inference fast path of SlotAttnCNNEncoder in bf16: channels-last tensors, weights cast once and cached until
     a parameter changes, the 3 input channels zero-padded to 8 so that the first layer also takes a tensor-core
@@ -35,11 +57,15 @@ class FusedBf16Encoder:
     pass instead (measured on B200: 82 + 11 us per layer against 94 us fused -- cuDNN picks a slower tile shape
     for the plain convolution, so the fused call wins by a hair end to end: 0.584 vs 0.612 ms per step)."""
 
-    def __init__(self, enc: "SlotAttnCNNEncoder"):
+    def __init__(self, enc: "SlotAttnCNNEncoder", convs: str = "ocrl"):
+        """convs: 'ocrl' = hand-written kernels for all four layers where the shape allows (3 -> 64 -> 64 channels,
+        frame width 32 / 64 / 128), returning a PaddedMap; 'cudnn' = the library path for layers 2-4."""
         self._enc = enc
         self._key = None
         self._w = None
         self._b = None
+        self._convs = convs
+        self._packed = None
 
     def _refresh(self):
         convs = [self._enc._encoder[i].m for i in range(3)] + [self._enc._encoder[3]]
@@ -56,6 +82,58 @@ class FusedBf16Encoder:
         self._w, self._b, self._key = ws, bs, key
         self._b16 = [b.to(torch.bfloat16) for b in bs]
         self._w0_f32 = convs[0].weight.detach().float().contiguous()  # the hand-written first layer rounds it itself
+        self._packed = None  # bf16 [25][64][64] copies for the tcgen05 layers, rebuilt on demand
+
+    def _packed_weights(self):
+        import ctypes
+
+        from . import abi
+
+        if self._packed is None:
+            convs = [self._enc._encoder[i].m for i in range(1, 3)] + [self._enc._encoder[3]]
+            out = []
+            for c in convs:
+                w = c.weight.detach().float().contiguous()
+                pk = torch.empty(25 * 64 * 64, device=w.device, dtype=torch.bfloat16)
+                abi.check(abi.lib().ocrl_conv5x5_pack_weights(abi.ptr(w), ctypes.c_void_p(pk.data_ptr()), w.shape[0], w.shape[1],
+                                                              abi.stream_ptr()), "ocrl_conv5x5_pack_weights")
+                out.append(pk)
+            self._packed = out
+        return self._packed
+
+    def _own_path_ok(self, obs):
+        B, C, H, W = obs.shape
+        hidden = [self._enc._encoder[i].m for i in range(3)] + [self._enc._encoder[3]]
+        return (self._convs == "ocrl" and C == 3 and W in (32, 64, 128) and (H * W) % 128 == 0
+                and obs.dtype == torch.float32 and obs.is_contiguous()
+                and all(tuple(c.weight.shape[2:]) == (5, 5) and c.weight.shape[0] == 64 for c in hidden)
+                and all(c.weight.shape[1] == 64 for c in hidden[1:]))
+
+    def _own_path(self, obs):
+        """All four layers hand-written: conv_first (mma.sync) -> three tcgen05 implicit-GEMM layers, activations in the
+        padded channels-last layout (fresh buffers per call: nothing to keep consistent between calls or CUDA graphs)."""
+        import ctypes
+
+        from . import abi
+
+        L = abi.lib()
+        B, C, H, W = obs.shape
+        nbytes = L.ocrl_conv_padded_bytes(B, H, W)
+        bufs = [torch.empty(nbytes // 128, 64, device=obs.device, dtype=torch.bfloat16) for _ in range(2)]
+        pk = self._packed_weights()
+        st = abi.stream_ptr()
+        abi.check(L.ocrl_conv_first_relu_bf16p(abi.ptr(obs), abi.ptr(self._w0_f32), abi.ptr(self._b[0]),
+                                               ctypes.c_void_p(bufs[0].data_ptr()), B, C, H, W, 64, st),
+                  "ocrl_conv_first_relu_bf16p")
+        src = 0
+        for i in range(3):  # layers 2, 3 (bias + ReLU) and 4 (bias rides on the position table, no ReLU)
+            last = i == 2
+            abi.check(L.ocrl_conv5x5_c64_tc(ctypes.c_void_p(bufs[src].data_ptr()), ctypes.c_void_p(pk[i].data_ptr()),
+                                            None if last else abi.ptr(self._b[i + 1]),
+                                            ctypes.c_void_p(bufs[1 - src].data_ptr()), B, H, W, 0 if last else 1, st),
+                      "ocrl_conv5x5_c64_tc")
+            src = 1 - src
+        return PaddedMap(bufs[src], B, H, W)
 
     @property
     def last_bias(self):
@@ -69,6 +147,8 @@ class FusedBf16Encoder:
         from . import abi
 
         self._refresh()
+        if self._own_path_ok(obs):
+            return self._own_path(obs)
         B, C, H, W = obs.shape
         cin = self._w[0].shape[1]
         use_cudnn_epilogue = os.environ.get("OCRL_CONV_EPILOGUE", "cudnn") == "cudnn"

@@ -107,7 +107,14 @@ def kv_project(x: Tensor, p: Dict[str, Tensor], *, kv: str = "fp32", enc: Option
     """
     _require_cuda(x, "kv_project")
     x_format = abi.X_TOKENS_F32
-    if x.dim() == 4:  # CNN feature map [B,C,H,W]
+    frame_w = 0
+    if hasattr(x, "to_nchw"):  # feature_stage.PaddedMap: padded channels-last bf16 map of the hand-written convolutions
+        if not (kv == "bf16" and _math_mode(abi.DT_BF16) == abi.MATH_TENSOR):
+            raise RuntimeError("kv_project: a padded bf16 feature map is an input of the bf16 / tensor-core mode only")
+        B, C, N, frame_w = x.B, x.data.shape[1], x.H * x.W, x.W
+        x = x.data
+        x_format = abi.X_PADDED_BF16
+    elif x.dim() == 4:  # CNN feature map [B,C,H,W]
         B, C = x.shape[0], x.shape[1]
         N = x.shape[2] * x.shape[3]
         if not x.is_contiguous() and x.permute(0, 2, 3, 1).is_contiguous():
@@ -127,7 +134,7 @@ def kv_project(x: Tensor, p: Dict[str, Tensor], *, kv: str = "fp32", enc: Option
     D = p["project_k.weight"].shape[0]
     dt_code, dt = _KV_DTYPES[kv]
     dims = abi.make_dims(B, N, C, D, D, 1, 1, kv_dtype=dt_code, ln_eps=ln_eps, math_mode=_math_mode(dt_code),
-                         x_format=x_format)
+                         x_format=x_format, frame_w=frame_w)
     ws = None
     if dims.math_mode == abi.MATH_TENSOR:  # bf16 weight copies for the tcgen05 kernel
         ws = torch.empty(abi.lib().ocrl_kv_proj_fwd_workspace(ctypes.byref(dims)), device=x.device, dtype=torch.uint8)

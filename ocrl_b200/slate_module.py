@@ -157,9 +157,12 @@ class SLATE_Module(nn.Module):
             with torch.no_grad():
                 if self._conv_mode() == "bf16" and os.environ.get("OCRL_CONV_FUSED", "1") != "0":
                     # fused bias+ReLU convolutions; the last conv's bias rides on the position table
+                    # conv_impl: 'ocrl' (default) = all four layers hand-written (mma.sync first layer + tcgen05 implicit
+                    # GEMM), 'cudnn' = library convolutions for layers 2-4
+                    impl = getattr(self, "conv_impl", "ocrl")
                     fast = self.__dict__.get("_fast_enc")
-                    if fast is None:
-                        fast = self.__dict__["_fast_enc"] = FusedBf16Encoder(self._enc)
+                    if fast is None or fast._convs != impl:
+                        fast = self.__dict__["_fast_enc"] = FusedBf16Encoder(self._enc, convs=impl)
                     return self._slotattn(fast(obs), _pos_table=self._pos_table_with_bias(fast))
                 return self._slotattn(self._encode_features(obs), _pos_table=self._enc_pos.table())
         fmap = self._enc(obs)

@@ -35,7 +35,7 @@ def main():
     k, v, _ = F.kv_project(x, p, kv="bf16")
     bytes_img = 2 * N * D * 2 + N * K * 4 + 2 * K * D * 4
     ref = None
-    for name, kw in [("tcgen05", dict(variant="tcgen05")), ("tcgen05_3lanes", dict(variant="tcgen05", lanes=3)),
+    for name, kw in [("tcgen05", dict(variant="tcgen05")), ("tcgen05_2lanes", dict(variant="tcgen05", lanes=2)),
                      ("pipe", dict(variant="pipe")), ("pipe_2lanes", dict(variant="pipe", lanes=2))]:
         opts = abi.launch_opts(strict=True, **kw)
         try:

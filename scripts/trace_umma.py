@@ -24,6 +24,8 @@ torch.cuda.synchronize()
 tr = ws[nbytes - 4096:].view(torch.int64).cpu().tolist()
 t0 = tr[0]
 print(f"B={B} lanes={lanes}: cycles since the post-setup cluster sync")
+print(f"first cluster: setup {tr[0]-tr[1]} cycles, main loop {tr[3]-tr[0]}; last cluster: setup {tr[5]-tr[4]}, main loop {tr[6]-tr[5]}; "
+      f"last cluster started {tr[4]-tr[1]} cycles after the first (different SM clocks: indicative only)")
 for n in range(40):
     b = tr[8 + n * 8: 16 + n * 8]
     if b[0] == 0:

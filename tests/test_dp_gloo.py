@@ -54,6 +54,8 @@ def _worker(rank, world, port, obs, expect, out):
     metrics = model.update(dp.shard(obs, rank, world), None, 0)
     got = {k: v.detach().clone() for k, v in model._module.state_dict().items()}
     ok = all(torch.allclose(got[k], expect[k], atol=1e-6) for k in expect)
+    # a parameter no rank touched keeps grad None (and no Adam state), exactly as in the single-process run
+    ok = ok and model._module.unused.grad is None and model._module.unused not in model._opt.state
     out[rank] = (ok, float(metrics["norm"]))
     dist.barrier()
     dist.destroy_process_group()

@@ -14,7 +14,7 @@ from tests.golden_io import load_case, rel_err
 
 pytestmark = pytest.mark.gpu
 BF16_TOL = 2e-2
-VARIANTS = {"tcgen05": dict(variant="tcgen05", strict=True), "tcgen05_3lanes": dict(variant="tcgen05", lanes=3, strict=True),
+VARIANTS = {"tcgen05": dict(variant="tcgen05", strict=True), "tcgen05_2lanes": dict(variant="tcgen05", lanes=2, strict=True),
             "tcgen05_2clusters": dict(variant="tcgen05", max_clusters=2, strict=True),
             "pipe": dict(variant="pipe", strict=True), "pipe_2lanes": dict(variant="pipe", lanes=2, strict=True)}
 

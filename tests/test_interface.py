@@ -77,7 +77,7 @@ def test_abi_exports_every_declared_symbol():
     for name in declared:
         assert getattr(lib, name) is not None
     assert lib.ocrl_version() == 4 and lib.ocrl_built_arch() == b"sm_100a"
-    assert ctypes.sizeof(abi.SaDims) == 52 and ctypes.sizeof(abi.SaWeights) == 13 * 8
+    assert ctypes.sizeof(abi.SaDims) == 56 and ctypes.sizeof(abi.SaWeights) == 13 * 8
     assert ctypes.sizeof(abi.TokenWeights) == 10 * 8 and ctypes.sizeof(abi.LaunchOpts) == 20
 
 
