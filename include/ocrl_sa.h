@@ -106,6 +106,8 @@ int ocrl_version(void);
 /* "sm_100a": the only architecture the library contains code for. */
 const char* ocrl_built_arch(void);
 const char* ocrl_last_error(void);
+/* Number of kernels this library has launched (or captured into a CUDA graph) in this process so far. */
+unsigned long long ocrl_launch_count(void);
 
 /* Bytes the caller must provide: `fwd_ws`/`bwd_ws` scratch for the iteration kernels and
  * `saved` for the per-iteration state kept for the backward (slots_in, updates, row sums). */

@@ -19,7 +19,7 @@ MATH_FP32, MATH_TENSOR = 0, 1
 X_TOKENS_F32, X_NCHW_F32, X_TOKENS_BF16, X_PADDED_BF16 = 0, 1, 2, 3
 
 EXPORTS = [
-    "ocrl_version", "ocrl_built_arch", "ocrl_last_error", "ocrl_sa_query_workspace",
+    "ocrl_version", "ocrl_built_arch", "ocrl_last_error", "ocrl_launch_count", "ocrl_sa_query_workspace",
     "ocrl_kv_proj_fwd_workspace", "ocrl_kv_proj_fwd", "ocrl_kv_proj_bwd_workspace", "ocrl_kv_proj_bwd",
     "ocrl_sa_iter_fwd", "ocrl_sa_iter_fwd_ex", "ocrl_sa_last_kernel", "ocrl_sa_iter_bwd",
     "ocrl_conv_bias_relu_bf16", "ocrl_frames_to_nhwc_bf16", "ocrl_conv_first_relu_bf16",
@@ -80,6 +80,7 @@ def lib() -> ctypes.CDLL:
         L.ocrl_version.restype = c_int
         L.ocrl_built_arch.restype = c_char_p
         L.ocrl_last_error.restype = c_char_p
+        L.ocrl_launch_count.restype = ctypes.c_ulonglong
         L.ocrl_sa_query_workspace.argtypes = [POINTER(SaDims), POINTER(c_size_t), POINTER(c_size_t), POINTER(c_size_t)]
         L.ocrl_kv_proj_fwd.argtypes = [POINTER(SaDims), c_void_p, c_void_p, POINTER(TokenWeights), c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p]

@@ -8,6 +8,8 @@
 namespace ocrl {
 
 static thread_local char g_err[512] = "";
+static unsigned long long g_launches = 0;  // kernels this library launched (or captured into a CUDA graph) so far
+void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -105,6 +107,7 @@ extern "C" {
 int ocrl_version(void) { return OCRL_ABI_VERSION; }
 const char* ocrl_built_arch(void) { return "sm_100a"; }
 const char* ocrl_last_error(void) { return g_err; }
+unsigned long long ocrl_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 int ocrl_sa_query_workspace(const ocrl_sa_dims* d, size_t* fwd_ws, size_t* bwd_ws, size_t* saved) {
   int rc = check_dims(d);

@@ -13,6 +13,7 @@ namespace cg = cooperative_groups;
 namespace ocrl {
 
 void set_error(const char* fmt, ...);
+void count_launch();  // one call per kernel launch of this library (ocrl_launch_count)
 
 #define OCRL_CHECK_CUDA(expr)                                                         \
   do {                                                                                \

@@ -178,6 +178,7 @@ static int conv_first_launch(const float* obs, const float* weight, const float*
   const int grid = nblocks < 148 * 2 ? nblocks : 148 * 2;  // one wave at 2 CTAs (16 warps) per SM; the weight fragments are built once per CTA
   kern<<<grid, conv1::NW * 32, smem, (cudaStream_t)stream>>>(obs, weight, bias, reinterpret_cast<__nv_bfloat16*>(out), B, H, W,
                                                               padded);
+  ocrl::count_launch();
   OCRL_CHECK_CUDA(cudaGetLastError());
   return OCRL_OK;
 }

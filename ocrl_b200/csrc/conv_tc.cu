@@ -25,12 +25,13 @@
 namespace ocrl {
 namespace convtc {
 
+static long long* g_conv_trace = nullptr;  // development aid (ocrl_dev_conv_trace)
+
 constexpr int C = 64;          // channels in and out
-constexpr int NWST = 4;        // weight ring stages
 constexpr int TAP_BYTES = C * C * 2;
 constexpr int NT = 192;
 
-template <int WP, int G>
+template <int WP, int G, int NWST>
 struct Cfg {
   static constexpr int NEED = 128 * G + 4 * WP + 4;           // positions a unit's taps touch
   static constexpr int BOX = ((NEED + 23) / 24) * 8;          // rows per TMA box (three boxes per slab, 1024-byte multiples)
@@ -56,13 +57,14 @@ struct Params {
   long long p_first;   // flat position of the first tile
   long long n_pos;     // positions of the whole array (rows of the tensor maps)
   int n_tiles;
+  long long* trace;    // development aid: clock64 stamps of CTA 0 (null in production)
 };
 
-template <int WP, int G>
+template <int WP, int G, int NWST>
 __global__ void __launch_bounds__(NT, 1)
 conv5x5_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w,
                   const __grid_constant__ CUtensorMap tm_out, const Params p) {
-  using CF = Cfg<WP, G>;
+  using CF = Cfg<WP, G, NWST>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* slab = sm + CF::OFF_SLAB;
@@ -78,6 +80,7 @@ conv5x5_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + CF::OFF_TMEM);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (p.trace != nullptr && blockIdx.x == 0 && tid == 0) p.trace[0] = clock64();
 
   if (tid < C) s_bias[tid] = p.bias ? __ldg(p.bias + tid) : 0.f;
   if (tid == 0) {
@@ -140,17 +143,24 @@ conv5x5_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
     const bool leader = tc::elect_one();
     constexpr uint32_t IDESC = tc::idesc_bf16(128, C);
     int wc = 0;
+    const bool tr = (p.trace != nullptr && blockIdx.x == 0 && lane == 0);
     for (int u = 0; u < n_units; ++u) {
       const int sb = u & 1;
       const int g = min(G, t_end - (t_begin + u * G));
+      if (tr && u < 8) p.trace[16 + u * 8 + 0] = clock64();
       mbar_wait(&slab_full[sb], (uint32_t)((u >> 1) & 1));
+      if (tr && u < 8) p.trace[16 + u * 8 + 1] = clock64();
       if (u >= 2) mbar_wait(&acc_empty[sb], (uint32_t)(((u >> 1) - 1) & 1));
+      if (tr && u < 8) p.trace[16 + u * 8 + 2] = clock64();
+      long long wsum = 0;
       tc::fence_after();
       const uint32_t sa = smem_u32(slab + sb * CF::SLAB_BYTES);
       const uint32_t acc = tmem + (uint32_t)sb * CF::ACC_COLS;
       for (int tap = 0; tap < 25; ++tap) {
         const int st = wc % NWST;
+        const long long tw0 = tr ? clock64() : 0;
         mbar_wait(&w_full[st], (uint32_t)((wc / NWST) & 1));
+        if (tr) wsum += clock64() - tw0;
         tc::fence_after();
         const uint32_t wa = smem_u32(wst + st * TAP_BYTES);
         const uint32_t rowoff = (uint32_t)((tap / 5) * WP + tap % 5) * 128u;
@@ -171,6 +181,7 @@ conv5x5_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
         tc::commit(&slab_empty[sb]);
       }
       __syncwarp();
+      if (tr && u < 8) { p.trace[16 + u * 8 + 3] = clock64(); p.trace[16 + u * 8 + 4] = wsum; }
     }
   } else {
     // ================================================================ epilogue: one output position per thread
@@ -180,7 +191,10 @@ conv5x5_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
     for (int u = 0; u < n_units; ++u) {
       const int ab = u & 1;
       const int g = min(G, t_end - (t_begin + u * G));
+      const bool tre = (p.trace != nullptr && blockIdx.x == 0 && e0);
+      if (tre && u < 8) p.trace[16 + u * 8 + 5] = clock64();
       mbar_wait(&acc_full[ab], (uint32_t)((u >> 1) & 1));
+      if (tre && u < 8) p.trace[16 + u * 8 + 6] = clock64();
       tc::fence_after();
       for (int i = 0; i < g; ++i) {
         uint32_t r0[32], r1[32];
@@ -222,8 +236,10 @@ conv5x5_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
           tc::tma_store_wait_read<0>();
         }
       }
+      if (tre && u < 8) p.trace[16 + u * 8 + 7] = clock64();
     }
     if (e0) tc::tma_store_wait_all<0>();
+    if (p.trace != nullptr && blockIdx.x == 0 && e0) p.trace[1] = clock64();
   }
   tc::fence_before();
   __syncthreads();
@@ -238,9 +254,9 @@ __global__ void conv5x5_pack_kernel(const float* __restrict__ w, __nv_bfloat16* 
   out[i] = __float2bfloat16_rn(__ldg(w + ((size_t)(co * C + ci) * 25) + tap));
 }
 
-template <int WP, int G>
+template <int WP, int G, int NWST>
 static int launch(const void* in, const void* wpk, const float* bias, void* out, int B, int H, int W, int relu, cudaStream_t stream) {
-  using CF = Cfg<WP, G>;
+  using CF = Cfg<WP, G, NWST>;
   Params p;
   p.bias = bias; p.relu = relu; p.B = B; p.H = H; p.W = W;
   // the tiles cover EVERY position of the output array (padding positions are written as zeros), so the caller never has
@@ -248,6 +264,7 @@ static int launch(const void* in, const void* wpk, const float* bias, void* out,
   p.p_first = 0;
   p.n_pos = (2LL + (long long)B * (H + 2)) * WP;
   p.n_tiles = (int)((p.n_pos + 127) / 128);
+  p.trace = g_conv_trace;
   CUtensorMap tm_in, tm_w, tm_out;
   if (!tc::make_map_bf16_sw128(&tm_in, in, C, (uint64_t)p.n_pos, C * 2, CF::BOX) ||
       !tc::make_map_bf16_sw128(&tm_w, wpk, C, 25 * C, C * 2, C) ||
@@ -255,7 +272,7 @@ static int launch(const void* in, const void* wpk, const float* bias, void* out,
     set_error("conv5x5_tc: cuTensorMapEncodeTiled failed");
     return OCRL_E_LAUNCH;
   }
-  auto kern = conv5x5_tc_kernel<WP, G>;
+  auto kern = conv5x5_tc_kernel<WP, G, NWST>;
   static bool configured = false;
   if (!configured) {
     OCRL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM_BYTES));
@@ -267,6 +284,7 @@ static int launch(const void* in, const void* wpk, const float* bias, void* out,
   const int units = (p.n_tiles + G - 1) / G;
   const int grid = units < sms ? units : sms;
   kern<<<grid, NT, CF::SMEM_BYTES, stream>>>(tm_in, tm_w, tm_out, p);
+  ocrl::count_launch();
   OCRL_CHECK_CUDA(cudaGetLastError());
   return OCRL_OK;
 }
@@ -275,6 +293,10 @@ static int launch(const void* in, const void* wpk, const float* bias, void* out,
 }  // namespace ocrl
 
 using namespace ocrl;
+
+extern "C" void ocrl_dev_conv_trace(long long* p) { convtc::g_conv_trace = p; }
+static int g_conv_variant = 0;
+extern "C" void ocrl_dev_conv_variant(int v) { g_conv_variant = v; }  // development knob (scripts/quick_conv.py), not in the header
 
 extern "C" size_t ocrl_conv_padded_bytes(int B, int H, int W) {
   if (B < 0 || H < 1 || W < 1) return 0;
@@ -292,6 +314,7 @@ extern "C" int ocrl_conv5x5_pack_weights(const float* weight, void* packed, int 
   }
   convtc::conv5x5_pack_kernel<<<(25 * convtc::C * convtc::C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
       weight, reinterpret_cast<__nv_bfloat16*>(packed));
+  ocrl::count_launch();
   OCRL_CHECK_CUDA(cudaGetLastError());
   return OCRL_OK;
 }
@@ -314,9 +337,13 @@ extern "C" int ocrl_conv5x5_c64_tc(const void* in_padded, const void* packed_w, 
   }
   cudaStream_t s = (cudaStream_t)stream;
   switch (W) {
-    case 32: return convtc::launch<36, 3>(in_padded, packed_w, bias, out_padded, B, H, W, relu, s);
-    case 64: return convtc::launch<68, 3>(in_padded, packed_w, bias, out_padded, B, H, W, relu, s);
-    case 128: return convtc::launch<132, 1>(in_padded, packed_w, bias, out_padded, B, H, W, relu, s);
+    case 32: return convtc::launch<36, 3, 4>(in_padded, packed_w, bias, out_padded, B, H, W, relu, s);
+    case 64:
+      if (g_conv_variant == 1) return convtc::launch<68, 3, 5>(in_padded, packed_w, bias, out_padded, B, H, W, relu, s);
+      if (g_conv_variant == 2) return convtc::launch<68, 2, 8>(in_padded, packed_w, bias, out_padded, B, H, W, relu, s);
+      if (g_conv_variant == 3) return convtc::launch<68, 2, 6>(in_padded, packed_w, bias, out_padded, B, H, W, relu, s);
+      return convtc::launch<68, 3, 4>(in_padded, packed_w, bias, out_padded, B, H, W, relu, s);
+    case 128: return convtc::launch<132, 1, 4>(in_padded, packed_w, bias, out_padded, B, H, W, relu, s);
     default:
       set_error("conv5x5_c64_tc: W=%d not instantiated (32, 64, 128)", W);
       return OCRL_E_SHAPE;

@@ -64,8 +64,8 @@ int ocrl_conv_bias_relu_bf16(void* y, const float* bias, long long npixels, int 
   const size_t nvec = (size_t)npixels * channels / 8;
   const int grid = (int)((nvec + 255) / 256 < 148 * 8 ? (nvec + 255) / 256 : 148 * 8);
   switch (channels) {
-    case 64: bias_relu_bf16_kernel<64><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<__nv_bfloat16*>(y), bias, nvec); break;
-    case 128: bias_relu_bf16_kernel<128><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<__nv_bfloat16*>(y), bias, nvec); break;
+    case 64: bias_relu_bf16_kernel<64><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<__nv_bfloat16*>(y), bias, nvec); ocrl::count_launch(); break;
+    case 128: bias_relu_bf16_kernel<128><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<__nv_bfloat16*>(y), bias, nvec); ocrl::count_launch(); break;
     default:
       set_error("conv_bias_relu: channels=%d not supported (64, 128)", channels);
       return OCRL_E_SHAPE;
@@ -87,6 +87,7 @@ int ocrl_frames_to_nhwc_bf16(const float* obs, void* out, int B, int C, int H, i
   if (npix == 0) return OCRL_OK;
   const int grid = (int)((npix + 255) / 256 < 148 * 8 ? (npix + 255) / 256 : 148 * 8);
   frames_to_nhwc_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(obs, reinterpret_cast<__nv_bfloat16*>(out), C, H * W, npix);
+  ocrl::count_launch();
   OCRL_CHECK_CUDA(cudaGetLastError());
   return OCRL_OK;
 }

@@ -207,14 +207,17 @@ int kv_proj_bwd_launch(const ocrl_sa_dims* d, const float* x, const ocrl_token_w
     case 64:
       OCRL_CHECK_CUDA(cudaFuncSetAttribute(kv_proj_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       kv_proj_bwd_kernel<64><<<grid, PB_NT, smem, stream>>>(a);
+      ocrl::count_launch();
       break;
     case 128:
       OCRL_CHECK_CUDA(cudaFuncSetAttribute(kv_proj_bwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       kv_proj_bwd_kernel<128><<<grid, PB_NT, smem, stream>>>(a);
+      ocrl::count_launch();
       break;
     case 192:
       OCRL_CHECK_CUDA(cudaFuncSetAttribute(kv_proj_bwd_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       kv_proj_bwd_kernel<192><<<grid, PB_NT, smem, stream>>>(a);
+      ocrl::count_launch();
       break;
     default:
       set_error("kv_proj_bwd: slot_size=%d not supported (64, 128, 192)", d->D);
@@ -222,6 +225,7 @@ int kv_proj_bwd_launch(const ocrl_sa_dims* d, const float* x, const ocrl_token_w
   }
   OCRL_CHECK_CUDA(cudaGetLastError());
   kv_proj_bwd_reduce_kernel<<<32, 256, 0, stream>>>(a.partial, grid, d->D, a.kscale, dwk, dwv, d_ln_w, d_ln_b);
+  ocrl::count_launch();
   OCRL_CHECK_CUDA(cudaGetLastError());
   return OCRL_OK;
 }

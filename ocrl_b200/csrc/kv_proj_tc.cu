@@ -548,6 +548,7 @@ int kv_proj_tc_launch(const ocrl_sa_dims* d, const void* x, const float* pos, co
   proj_tc_prep_kernel<<<(prep_threads + 255) / 256, 256, 0, stream>>>(w->mlp_w1, w->mlp_w2, w->wk, w->wv, w1b, w2b, wkvb, D,
                                                                  1.0f / sqrtf((float)D), pos, pos_tiles ? posb : nullptr,
                                                                  d->N);
+  ocrl::count_launch();
   OCRL_CHECK_CUDA(cudaGetLastError());
 
   CUtensorMap tm_x, tm_w1, tm_w2, tm_wkv, tm_k, tm_v, tm_pos;
@@ -600,7 +601,7 @@ int kv_proj_tc_launch(const ocrl_sa_dims* d, const void* x, const float* pos, co
   do {                                                                                                           \
     OCRL_CHECK_CUDA(cudaFuncSetAttribute(kv_proj_tc_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                          (int)smem));                                                            \
-    kv_proj_tc_kernel<DD><<<grid, PT_NT, smem, stream>>>(tm_x, tm_w1, tm_w2, tm_wkv, tm_k, tm_v, tm_pos, p);              \
+    kv_proj_tc_kernel<DD><<<grid, PT_NT, smem, stream>>>(tm_x, tm_w1, tm_w2, tm_wkv, tm_k, tm_v, tm_pos, p); ocrl::count_launch(); \
   } while (0)
   if (D == 64) OCRL_LAUNCH_PT(64);
   else if (D == 128) OCRL_LAUNCH_PT(128);

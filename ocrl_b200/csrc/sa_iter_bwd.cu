@@ -130,14 +130,15 @@ int sa_iter_bwd_launch(const ocrl_sa_dims* d, const void* k, const void* v, cons
   const long long tokens = (long long)d->B * d->N;
   const int blocks = (int)((tokens + 7) / 8 < 148 * 8 ? (tokens + 7) / 8 : 148 * 8);
   switch (d->D) {
-    case 64: expand_coef_kernel<64><<<blocks, 256, 0, stream>>>(a.coef, saved, a.gm, dk, dv, d->B, d->N, d->K, d->H_mlp, d->T); break;
-    case 128: expand_coef_kernel<128><<<blocks, 256, 0, stream>>>(a.coef, saved, a.gm, dk, dv, d->B, d->N, d->K, d->H_mlp, d->T); break;
-    default: expand_coef_kernel<192><<<blocks, 256, 0, stream>>>(a.coef, saved, a.gm, dk, dv, d->B, d->N, d->K, d->H_mlp, d->T); break;
+    case 64: expand_coef_kernel<64><<<blocks, 256, 0, stream>>>(a.coef, saved, a.gm, dk, dv, d->B, d->N, d->K, d->H_mlp, d->T); ocrl::count_launch(); break;
+    case 128: expand_coef_kernel<128><<<blocks, 256, 0, stream>>>(a.coef, saved, a.gm, dk, dv, d->B, d->N, d->K, d->H_mlp, d->T); ocrl::count_launch(); break;
+    default: expand_coef_kernel<192><<<blocks, 256, 0, stream>>>(a.coef, saved, a.gm, dk, dv, d->B, d->N, d->K, d->H_mlp, d->T); ocrl::count_launch(); break;
   }
   OCRL_CHECK_CUDA(cudaGetLastError());
   reduce_partials_kernel<<<148, 256, 0, stream>>>(a.wgrad, a.NCL, WG.total(), dw->wq, dw->w_ih, dw->w_hh, dw->b_ih,
                                                   dw->b_hh, dw->w1, dw->b1, dw->w2, dw->b2, dw->ln_slots_w,
                                                   dw->ln_slots_b, dw->ln_mlp_w, dw->ln_mlp_b, d->D, d->H_mlp);
+  ocrl::count_launch();
   OCRL_CHECK_CUDA(cudaGetLastError());
   return OCRL_OK;
 }

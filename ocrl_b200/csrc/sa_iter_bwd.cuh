@@ -629,6 +629,7 @@ static int launch_bwd(const IterBwdArgs& a, cudaStream_t stream) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   OCRL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+  ocrl::count_launch();
   return OCRL_OK;
 }
 

@@ -403,6 +403,7 @@ static int launch_fwd_nw(const IterFwdArgs& a, cudaStream_t stream) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   OCRL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+  ocrl::count_launch();
   return OCRL_OK;
 }
 

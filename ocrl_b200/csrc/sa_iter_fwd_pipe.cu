@@ -905,6 +905,7 @@ static int launch_pipe(const IterFwdArgs& a, cudaStream_t stream) {
   }
   cfg.gridDim = dim3((unsigned)(ncl * CL));
   OCRL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, a, tm_k, tm_v));
+  ocrl::count_launch();
   return OCRL_OK;
 }
 

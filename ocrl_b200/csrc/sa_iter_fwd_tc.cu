@@ -598,6 +598,7 @@ static int launch_tc(const IterFwdArgs& a, cudaStream_t stream) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   OCRL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+  ocrl::count_launch();
   return OCRL_OK;
 }
 
@@ -645,6 +646,7 @@ const __nv_bfloat16* sa_iter_tc_prepare(const ocrl_sa_dims* d, const ocrl_sa_wei
   if (workspace == nullptr) return nullptr;
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
   iter_tc_prep_kernel<<<148, 256, 0, stream>>>(*w, out, d->D, d->H_mlp);
+  ocrl::count_launch();
   return out;
 }
 

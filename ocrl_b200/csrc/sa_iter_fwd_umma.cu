@@ -955,6 +955,7 @@ static int launch_umma(const IterFwdArgs& a_in, cudaStream_t stream) {
     a.wprep = reinterpret_cast<uint32_t*>(base);
     a.wprep_consts = reinterpret_cast<float*>(base + (size_t)CL * 2 * C::WPB * 128 * 4);
     umma_prep_kernel<D, H, CL><<<CL * 2 * 128 / 8, 256, 0, stream>>>(a.w, const_cast<uint32_t*>(a.wprep), const_cast<float*>(a.wprep_consts));
+    ocrl::count_launch();
     OCRL_CHECK_CUDA(cudaGetLastError());
   }
   auto kern = sa_iter_fwd_umma_kernel<D, H, CL, NL, KB, NKS, NVS, NWB>;
@@ -1000,6 +1001,7 @@ static int launch_umma(const IterFwdArgs& a_in, cudaStream_t stream) {
   }
   cfg.gridDim = dim3((unsigned)(ncl * CL));
   OCRL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, a, tm_k, tm_v));
+  ocrl::count_launch();
   return OCRL_OK;
 }
 

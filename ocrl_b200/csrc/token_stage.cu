@@ -226,9 +226,11 @@ int token_stage_launch(const ocrl_sa_dims* d, const void* x, const float* pos, c
   if (d->kv_dtype == OCRL_DT_F32) {
     OCRL_CHECK_CUDA(cudaFuncSetAttribute(token_stage_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     token_stage_kernel<float><<<grid, TS_NT, smem, stream>>>(a);
+    ocrl::count_launch();
   } else {
     OCRL_CHECK_CUDA(cudaFuncSetAttribute(token_stage_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     token_stage_kernel<__nv_bfloat16><<<grid, TS_NT, smem, stream>>>(a);
+    ocrl::count_launch();
   }
   OCRL_CHECK_CUDA(cudaGetLastError());
   return OCRL_OK;

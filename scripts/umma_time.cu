@@ -107,6 +107,11 @@ int main() {
   SWEEP("M128 N16 MN-major sw128 A", 16, 128, 32, a_mn, b16, idesc(128, 16, 1))
   SWEEP("M64  N16 MN-major sw128 A", 16, 128, 32, a_mn, b16, idesc(64, 16, 1))
   SWEEP("M128 N64 K-major sw128 A, sw128 B", 64, 2, 2, a_k, b64, idesc(128, 64, 0))
+  run<48, 4, 64, 2, 2>("M128 N64, A start shifted by 1 row (128 B)", desc(128, 16, 1024, 2), b64, idesc(128, 64, 0));
+  run<48, 4, 64, 2, 2>("M128 N64, A start shifted by 5 rows", desc(640, 16, 1024, 2), b64, idesc(128, 64, 0));
+  run<48, 4, 64, 2, 2>("M128 N64, A start shifted by 4 rows", desc(512, 16, 1024, 2), b64, idesc(128, 64, 0));
+  run<48, 4, 64, 2, 2>("M128 N64, A start shifted by 68 rows", desc(68 * 128, 16, 1024, 2), b64, idesc(128, 64, 0));
+  run<48, 4, 64, 2, 2>("M128 N64, A no swizzle (LBO 16 KB... K-chunk planes)", desc(0, 16384, 128, 0), b64, idesc(128, 64, 0));
   run<48, 2, 128, 2, 2>("M128 N128 K-major sw128 both", a_k, b64, idesc(128, 128, 0));
   run<48, 2, 256, 2, 2>("M128 N256 K-major sw128 both", a_k, b64, idesc(128, 256, 0));
   run<48, 1, 256, 2, 2>("M128 N256 K-major sw128 both", a_k, b64, idesc(128, 256, 0));
