@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define OCRL_ABI_VERSION 4
+#define OCRL_ABI_VERSION 5
 
 enum {
   OCRL_OK = 0,
@@ -154,6 +154,9 @@ int ocrl_sa_iter_fwd(const ocrl_sa_dims* dims, const void* k, const void* v, con
  *   strict        != 0: return OCRL_E_SHAPE when `variant` (or, with OCRL_SA_AUTO, the tcgen05 kernel) does not cover the
  *                 shape instead of running a slower kernel
  *   trace         != 0: the kernel writes clock64() phase stamps of CTA 0 to the last 4 KB of `workspace` (development aid)
+ *   prepared      != 0: `workspace` still holds the prepared (bf16, LayerNorm-folded) weight copies an earlier call with
+ *                 the same dims, weights and workspace left there; the weight-preparation launch is skipped.  The caller
+ *                 owns the invariant (inference with frozen weights: prepare once, then pass prepared = 1)
  */
 enum { OCRL_SA_AUTO = 0, OCRL_SA_TCGEN05 = 1, OCRL_SA_PIPE = 2, OCRL_SA_CLUSTER_TC = 3, OCRL_SA_FFMA = 4 };
 typedef struct ocrl_sa_launch_opts {
@@ -162,6 +165,7 @@ typedef struct ocrl_sa_launch_opts {
   int32_t lanes;
   int32_t strict;
   int32_t trace;
+  int32_t prepared;
 } ocrl_sa_launch_opts;
 int ocrl_sa_iter_fwd_ex(const ocrl_sa_dims* dims, const void* k, const void* v, const float* slots0,
                         const ocrl_sa_weights* w, float* slots_out, float* attn_vis_out,

@@ -49,13 +49,14 @@ class SaWeights(Structure):
 class LaunchOpts(Structure):
     """ocrl_sa_launch_opts (include/ocrl_sa.h): per-call kernel selection of the iteration loop."""
     _fields_ = [("variant", c_int32), ("max_clusters", c_int32), ("lanes", c_int32), ("strict", c_int32),
-                ("trace", c_int32)]
+                ("trace", c_int32), ("prepared", c_int32)]
 
 
-def launch_opts(variant="auto", max_clusters=0, lanes=0, strict=False, trace=False) -> LaunchOpts:
+def launch_opts(variant="auto", max_clusters=0, lanes=0, strict=False, trace=False, prepared=False) -> LaunchOpts:
     if isinstance(variant, str):
         variant = SA_VARIANTS[variant]
-    return LaunchOpts(int(variant), int(max_clusters or 0), int(lanes or 0), int(bool(strict)), int(bool(trace)))
+    return LaunchOpts(int(variant), int(max_clusters or 0), int(lanes or 0), int(bool(strict)), int(bool(trace)),
+                      int(bool(prepared)))
 
 
 class SaWeightGrads(Structure):

@@ -21,7 +21,7 @@ const char* sa_iter_last_kernel() { return g_last_kernel; }
 int sa_iter_fwd_launch(const ocrl_sa_dims* d, const void* k, const void* v, const float* slots0,
                        const ocrl_sa_weights* w, float* slots_out, float* attn_out, float* saved,
                        void* workspace, const ocrl_sa_launch_opts* opts, cudaStream_t stream) {
-  ocrl_sa_launch_opts o = {OCRL_SA_AUTO, 0, 0, 0, 0};
+  ocrl_sa_launch_opts o = {OCRL_SA_AUTO, 0, 0, 0, 0, 0};
   if (opts) o = *opts;
   IterFwdArgs a;
   a.k = k; a.v = v; a.slots0 = slots0; a.w = *w; a.slots_out = slots_out; a.attn_out = attn_out; a.saved = saved;
@@ -33,6 +33,7 @@ int sa_iter_fwd_launch(const ocrl_sa_dims* d, const void* k, const void* v, cons
   a.workspace_bytes = workspace ? sa_iter_tc_workspace(d) : 0;
   a.max_clusters = o.max_clusters;
   a.lanes = o.lanes;
+  a.prepared = o.prepared;
   if (o.trace && workspace != nullptr)  // last 4 KB of the workspace: phase timestamps
     a.trace = reinterpret_cast<long long*>(reinterpret_cast<unsigned char*>(workspace) + sa_iter_tc_workspace(d) - 4096);
   a.CL = sa_iter_pick_cluster(d);

@@ -28,11 +28,16 @@ using namespace pc;
 #define TRACE_OP 2
 #endif
 
-template <int D_, int H_, int CL_, int NL_, int KB_, int NKS_, int NVS_, int NWB_>
+template <int D_, int H_, int CL_, int NL_, int KB_, int NKS_, int NVS_, int NWB_, int NUS_, int DEFER_ = 0>
 struct Cfg {
   // NL image lanes per cluster; KB rows in the slot-indexed buffers; NKS / NVS ring slots for k / v half tiles;
   // NWB buffers for the softmax weights of a 128-token pair
   static constexpr int D = D_, H = H_, CL = CL_, NL = NL_, KB = KB_, NKS = NKS_, NVS = NVS_, NWB = NWB_;
+  // NUS update streams: the eight update warps are split into NUS groups that run the slot updates of different ops
+  // concurrently (op n -> stream n % NUS); an update is a chain of exchange rounds, bound by latency, not by work
+  static constexpr int NUS = NUS_, UW = 8 / NUS, UT = 32 * UW;
+  static constexpr bool DEFER = DEFER_ != 0;  // drain an op's U accumulator after the next op's first softmax
+  static_assert((NUS == 1 || NUS == 2) && NL <= 3, "update streams, lanes");
   static constexpr int NT = 512, HT = 64, NCH = D / 64;
   static constexpr int LX = D > H ? D : H;
   static constexpr int CH_BYTES = HT * 128, HT_BYTES = NCH * CH_BYTES;  // one 64-wide feature chunk / one half tile
@@ -51,37 +56,40 @@ struct Cfg {
   // product over several accumulators: back-to-back MMAs into the same columns issue at full rate, scripts/umma_time.cu.)
   static constexpr uint32_t COL_LG = 0, LG_STRIDE = 16, COL_U = 32, U_STRIDE = 32, U_B = 16, COL_GI = 96, COL_GH = 112;
   static constexpr uint32_t COL_WX = 128, COL_WY = COL_WX + LX / 2, TMEM_COLS = 512;
-  static_assert(COL_WY + D / 2 <= 512, "tensor memory");
+  static constexpr uint32_t COL_GI2 = COL_WY + D / 2, COL_GH2 = COL_GI2 + 16;  // accumulators of the second update stream
+  static_assert(COL_GH2 + 16 <= 512, "tensor memory");
 
   static constexpr int OFF_KRING = 0;
   static constexpr int OFF_VRING = OFF_KRING + NKS * HT_BYTES;
   static constexpr int OFF_WT = OFF_VRING + NVS * HT_BYTES;
   static constexpr int OFF_BIAS = OFF_WT + NWB * WP_BYTES;  // (the LayerNorm affine parameters are folded into W1', Wq')
   // fp32 constants: b_ih[3DS] b_hh[3DS] b1'[HS] b2[DS] c1[HS] cq[DS] bq'[DS] + LayerNorm stats mean[8] rstd[8]
-  static constexpr int NCONST = 9 * DS + 2 * HS + 16;
+  static constexpr int NCONST = 9 * DS + 2 * HS + 16 * NUS;
   static constexpr int XBUF_BYTES = KB * D * 4 + 32 * CL;          // R1 receive buffer (fp32 partial sums), single
   static constexpr int OFF_XBUF = (OFF_BIAS + NCONST * 4 + 15) & ~15;
-  static constexpr int OFF_ACT = (OFF_XBUF + XBUF_BYTES + 127) & ~127;  // bf16 all-gather targets (operands), by round parity
-  static constexpr int OFF_UST = OFF_ACT + 2 * OPX_BYTES;          // U staging (pass -> update hand-off)
-  static constexpr int OFF_LANE = (OFF_UST + KB * UP * 4 + 127) & ~127;  // per lane: q operand, slots operand, own slice (fp32)
+  static constexpr int OFF_ACT = (OFF_XBUF + NUS * XBUF_BYTES + 127) & ~127;  // bf16 all-gather targets (operands), by round parity
+  static constexpr int OFF_UST = OFF_ACT + NUS * 2 * OPX_BYTES;    // U staging (pass -> update hand-off), one per stream
+  static constexpr int UST_BYTES = (KB * UP * 4 + 127) & ~127;
+  static constexpr int OFF_LANE = (OFF_UST + NUS * UST_BYTES + 127) & ~127;  // per lane: q operand, slots operand, own slice (fp32)
   static constexpr int LANE_BYTES = (2 * OPD_BYTES + KB * DS * 4 + 127) & ~127;
   static constexpr int OFF_P = (OFF_LANE + NL * LANE_BYTES + 15) & ~15;   // product outputs, fp32 [2][128 rows][8 slots]
-  static constexpr int OFF_SRED = OFF_P + 2 * 128 * 32;            // [4][8] token sums of the softmax warps
-  // k_full k_empty [NKS] v_full v_empty [NVS] lg_full lg_empty w_full w_empty u_full u_accfree [2 each] xbar[2]
-  // u_ready u_free ubar[2] q_ready[NL]
-  static constexpr int OFF_BAR = OFF_SRED + 128;
-  static constexpr int NBAR = 2 * NKS + 2 * NVS + 12 + 2 + 4 + NL;
+  static constexpr int OFF_SRED = OFF_P + NUS * 2 * 128 * 32;      // [4][8] token sums of the softmax warps, per stream
+  // k_full k_empty [NKS] v_full v_empty [NVS] lg_full lg_empty w_full w_empty u_full u_accfree [2 each]
+  // per stream: xbar[2] u_ready u_free ubar[2];  q_ready[NL]
+  static constexpr int OFF_BAR = OFF_SRED + NUS * 128;
+  static constexpr int NBAR = 2 * NKS + 2 * NVS + 12 + 6 * NUS + NL;
   static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
   static constexpr int SMEM_BYTES = OFF_TMEM + 16;
 };
 
-__device__ __forceinline__ void upd_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// barrier of one update stream (ids 1, 2)
+__device__ __forceinline__ void upd_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-template <int D, int H, int CL, int NL, int KB, int NKS, int NVS, int NWB>
+template <int D, int H, int CL, int NL, int KB, int NKS, int NVS, int NWB, int NUS, int DEFER>
 __global__ void __launch_bounds__(512, 1)
 sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v) {
-  using C = Cfg<D, H, CL, NL, KB, NKS, NVS, NWB>;
-  constexpr int DS = C::DS, HS = C::HS, UP = C::UP, HT = C::HT, NCH = C::NCH;
+  using C = Cfg<D, H, CL, NL, KB, NKS, NVS, NWB, NUS, DEFER>;
+  constexpr int DS = C::DS, HS = C::HS, UP = C::UP, HT = C::HT, NCH = C::NCH, UW = C::UW, UT = C::UT;
   constexpr float LOG2E = 1.4426950408889634f;
 
   extern __shared__ __align__(1024) unsigned char sm[];  // swizzled TMA tiles need 1024-byte alignment
@@ -109,14 +117,16 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
   float* s_c1 = s_bias + 7 * DS + HS;        // row sums of the folded bf16 W1'
   float* s_cq = s_bias + 7 * DS + 2 * HS;    // row sums of the folded bf16 Wq'
   float* s_bqf = s_bias + 8 * DS + 2 * HS;   // Wq . beta_slots
-  float* s_mean = s_bias + 9 * DS + 2 * HS;  // LayerNorm statistics of the round in flight
+  // update stream of this warp (warps 8..15; the pass warps address the per-stream hand-off buffers by op)
+  const int us = (warp >= 8) ? (warp - 8) / UW : 0;
+  float* s_mean = s_bias + 9 * DS + 2 * HS + 16 * us;  // LayerNorm statistics of the round in flight
   float* s_rstd = s_mean + 8;
-  unsigned char* xbuf = sm + C::OFF_XBUF;
-  auto act = [&](uint32_t r) { return sm + C::OFF_ACT + (r & 1) * C::OPX_BYTES; };  // operand [LX/8][8 slots][8] bf16
-  float* P_GI = reinterpret_cast<float*>(sm + C::OFF_P);  // [128 rows of block X][8 slots]
-  float* P_GH = P_GI + 128 * 8;                           // [128 rows of block Y][8 slots]
-  float* ustage = reinterpret_cast<float*>(sm + C::OFF_UST);
-  float* sred = reinterpret_cast<float*>(sm + C::OFF_SRED);
+  unsigned char* xbuf = sm + C::OFF_XBUF + us * C::XBUF_BYTES;
+  auto act = [&](uint32_t r) { return sm + C::OFF_ACT + (2 * us + (r & 1)) * C::OPX_BYTES; };  // operand [LX/8][8 slots][8] bf16
+  float* P_GI = reinterpret_cast<float*>(sm + C::OFF_P) + us * 2 * 128 * 8;  // [128 rows of block X][8 slots]
+  float* P_GH = P_GI + 128 * 8;                                              // [128 rows of block Y][8 slots]
+  auto ustage_of = [&](int s) { return reinterpret_cast<float*>(sm + C::OFF_UST + s * C::UST_BYTES); };
+  auto sred_of = [&](int s) { return reinterpret_cast<float*>(sm + C::OFF_SRED + s * 128); };
   auto qop = [&](int l) { return sm + C::OFF_LANE + l * C::LANE_BYTES; };
   auto slh_hi = [&](int l) { return sm + C::OFF_LANE + l * C::LANE_BYTES + C::OPD_BYTES; };  // the lane's slots, operand layout
   auto own_of = [&](int l) { return reinterpret_cast<float*>(sm + C::OFF_LANE + l * C::LANE_BYTES + 2 * C::OPD_BYTES); };
@@ -133,12 +143,14 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
   uint64_t* w_empty = w_full + 2;      // [2] the U products that read them are complete
   uint64_t* u_full = w_empty + 2;      // [2] U accumulator of an op is complete
   uint64_t* u_accfree = u_full + 2;    // [2] ... and has been drained
-  uint64_t* xbar = u_accfree + 2;
-  uint64_t* u_ready = xbar + 2;
-  uint64_t* u_free = u_ready + 1;
-  uint64_t* ubar = u_free + 1;         // [2] a product of the update engine is complete ([1]: W_hh h, which overlaps others)
-  uint64_t* q_ready = ubar + 2;
+  uint64_t* sbars = u_accfree + 2;     // per update stream: xbar[2] u_ready u_free ubar[2]
+  uint64_t* xbar = sbars + 6 * us;
+  auto u_ready_of = [&](int s) { return sbars + 6 * s + 2; };
+  auto u_free_of = [&](int s) { return sbars + 6 * s + 3; };
+  uint64_t* ubar = sbars + 6 * us + 4;  // [2] a product of the stream is complete ([1]: W_hh h, which overlaps others)
+  uint64_t* q_ready = sbars + 6 * NUS;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + C::OFF_TMEM);
+  uint32_t* q_count = tmem_slot + 1;  // [NL <= 3] queries published per lane (read by the update streams)
 
   // ------------------------------------------------------------------ work assignment (NL lanes per cluster)
   // Images are dealt to clusters round-robin (newest first: the projection kernel left them in L2) and a cluster
@@ -274,13 +286,15 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
       mbar_init(&u_full[s], 1);
       mbar_init(&u_accfree[s], 4);
     }
-    mbar_init(&xbar[0], 1);
-    mbar_init(&xbar[1], 1);
-    mbar_init(u_ready, 4);
-    mbar_init(u_free, 8);
-    mbar_init(&ubar[0], 1);
-    mbar_init(&ubar[1], 1);
-    for (int l = 0; l < NL; ++l) mbar_init(&q_ready[l], 1);
+    for (int s = 0; s < NUS; ++s) {
+      mbar_init(sbars + 6 * s + 0, 1);
+      mbar_init(sbars + 6 * s + 1, 1);
+      mbar_init(u_ready_of(s), 4);
+      mbar_init(u_free_of(s), UW);
+      mbar_init(sbars + 6 * s + 4, 1);
+      mbar_init(sbars + 6 * s + 5, 1);
+    }
+    for (int l = 0; l < NL; ++l) { mbar_init(&q_ready[l], 1); q_count[l] = 0u; }
     mbar_fence_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_k) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_v) : "memory");
@@ -332,7 +346,7 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
     for (int i = tid; i < DS; i += C::NT) s_bias[6 * DS + HS + i] = a.w.b2[rank * DS + i];
     // operand rows of the padded slots are never written; keep them zero.  The w tiles' slot rows 8..15 and the
     // operands' rows K..7 stay zero for the whole kernel.
-    for (int i = tid; i < (2 * C::OPX_BYTES) / 4; i += C::NT) reinterpret_cast<uint32_t*>(sm + C::OFF_ACT)[i] = 0u;
+    for (int i = tid; i < (NUS * 2 * C::OPX_BYTES) / 4; i += C::NT) reinterpret_cast<uint32_t*>(sm + C::OFF_ACT)[i] = 0u;
     for (int i = tid; i < (NL * C::LANE_BYTES) / 4; i += C::NT) reinterpret_cast<uint32_t*>(sm + C::OFF_LANE)[i] = 0u;
     for (int i = tid; i < (NWB * C::WP_BYTES) / 4; i += C::NT) reinterpret_cast<uint32_t*>(wtiles)[i] = 0u;
     fence_proxy_async();  // the zero rows are read by tcgen05.mma (async proxy)
@@ -368,6 +382,49 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
       const int tih = warp * 16 + r16;  // token inside its half
       const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
       uint32_t gp = 0;  // pairs handled so far (selects the logit / w buffers and their phases)
+      // Drain of an op's U accumulator into the staging buffer of the update engine.  It is DEFERRED: the softmax of the
+      // next op's first pair runs first, so the U issuer always has softmax weights waiting when the previous op's
+      // products retire and the tensor pipe does not idle across op boundaries.
+      auto drain = [&](int n, const float (&S)[8]) {
+        float ua[8], ub[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { ua[i] = 0.f; ub[i] = 0.f; }
+        if (NP > 0) {
+          mbar_wait(&u_full[n & 1], (n >> 1) & 1);
+          tc::fence_after();
+          const uint32_t ucol = tlane + C::COL_U + C::U_STRIDE * (n & 1);
+          tc::tmem_ld8(ucol, ua);
+          if (C::HAS_B) tc::tmem_ld8(ucol + C::U_B, ub);
+          tc::fence_before();
+          __syncwarp();
+          if (lane == 0) tc::arrive(&u_accfree[n & 1]);
+        }
+        const int sx = n % NUS;  // the op's update stream
+        float* ustage = ustage_of(sx);
+        float* sred = sred_of(sx);
+        if (n >= NUS) mbar_wait(u_free_of(sx), (uint32_t)((n / NUS - 1) & 1));  // the stream's previous update has read sred / the U staging
+        {
+          // features: M = 128 block -> lane index 32 w + lane; M = 64 blocks -> lanes 0-15 of every quarter
+          const int da = (C::MA == 128) ? warp * 32 + lane : warp * 16 + r16;
+          const bool oka = (C::MA == 128) || lane < 16;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (i < KB && oka) ustage[i * UP + da] = ua[i];
+          if (C::HAS_B && lane < 16) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (i < KB) ustage[i * UP + 128 + warp * 16 + r16] = ub[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (lane == i) sred[warp * 8 + i] = S[i];
+        }
+        if (tid == 0 && n < 40) PP_TRACE(8 + n * 8 + 1);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(u_ready_of(sx));
+      };
+      float Sprev[8];
+      int n_prev = -1;
       for (int n = 0; n < total_ops; ++n) {
         int l, c;
         op_of(n, l, c);
@@ -436,43 +493,27 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
           __syncwarp();
           if (lane == 0) tc::arrive(&w_full[wb]);
           if (tt) a.trace[340 + p * 12 + 5] = clock64();
+          if (n_prev >= 0 && p == 0) {  // the previous op's accumulator, one softmax later
+            drain(n_prev, Sprev);
+            n_prev = -1;
+          }
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) Sl[i] = warp_sum(Sl[i]);
-        // ---- drain the op's U accumulator into the staging buffer of the update engine
-        float ua[8], ub[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { ua[i] = 0.f; ub[i] = 0.f; }
-        if (NP > 0) {
-          mbar_wait(&u_full[n & 1], (n >> 1) & 1);
-          tc::fence_after();
-          const uint32_t ucol = tlane + C::COL_U + C::U_STRIDE * (n & 1);
-          tc::tmem_ld8(ucol, ua);
-          if (C::HAS_B) tc::tmem_ld8(ucol + C::U_B, ub);
-          tc::fence_before();
-          __syncwarp();
-          if (lane == 0) tc::arrive(&u_accfree[n & 1]);
+        if (n_prev >= 0) {  // (only when this op had no pair)
+          drain(n_prev, Sprev);
+          n_prev = -1;
         }
-        if (n > 0) mbar_wait(u_free, (uint32_t)((n - 1) & 1));  // the previous update has read sred / the U staging
-        {
-          // features: M = 128 block -> lane index 32 w + lane; M = 64 blocks -> lanes 0-15 of every quarter
-          const int da = (C::MA == 128) ? warp * 32 + lane : warp * 16 + r16;
-          const bool oka = (C::MA == 128) || lane < 16;
+        // defer only when the next op belongs to another lane: a lane's next pass needs the query its own update produces
+        int l_next = -1, c_next = 0;
+        if (n + 1 < total_ops) op_of(n + 1, l_next, c_next);
+        if (C::DEFER && l_next >= 0 && l_next != l && NP > 0) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (i < KB && oka) ustage[i * UP + da] = ua[i];
-          if (C::HAS_B && lane < 16) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (i < KB) ustage[i * UP + 128 + warp * 16 + r16] = ub[i];
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (lane == i) sred[warp * 8 + i] = Sl[i];
+          for (int i = 0; i < 8; ++i) Sprev[i] = Sl[i];
+          n_prev = n;
+        } else {
+          drain(n, Sl);
         }
-        if (tid == 0 && n < 40) PP_TRACE(8 + n * 8 + 1);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(u_ready);
       }
     } else if (warp == 4 || warp == 6) {
       // ---- TMA producers: the rest of the stream (the first ring-full was issued during the setup)
@@ -579,7 +620,13 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
     // -> epilogue (= next push): all-gather payloads travel as bf16 straight into the receivers' MMA operand buffers
     // (act[parity], the lane's slots and q operands); the LayerNorms are folded into the products that follow them
     // (statistics from the received rows).
-    const int utid = tid - 256, uwarp = warp - 8;
+    const int utid = tid - 256 - us * UT, uwarp = warp - 8 - us * UW;  // thread / warp inside the stream
+    auto upd_sync = [&]() { ocrl::umma::upd_sync(1 + us, UT); };
+    const uint32_t col_gi = us ? C::COL_GI2 : C::COL_GI, col_gh = us ? C::COL_GH2 : C::COL_GH;
+    float* ustage = ustage_of(us);
+    float* sred = sred_of(us);
+    uint64_t* u_ready = u_ready_of(us);
+    uint64_t* u_free = u_free_of(us);
     uint32_t round = 0;
     // training: per-(image, iteration) state for the fused backward (SavedLayout, slot_math.cuh); every CTA writes
     // its own feature slice
@@ -610,12 +657,12 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
     };
     // mean / rstd of the K rows (bf16, length D, operand layout) that just arrived: one warp per row
     auto row_stats = [&](const unsigned char* opnd) {
-      if (uwarp < K) {
+      for (int row = uwarp; row < K; row += UW) {
         float2 x[NCH];
         float s = 0.f;
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
-          const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(opnd + opnd_off(uwarp, 64 * c + 2 * lane));
+          const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(opnd + opnd_off(row, 64 * c + 2 * lane));
           x[c] = make_float2(__low2float(v), __high2float(v));
           s += x[c].x + x[c].y;
         }
@@ -627,7 +674,7 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
           q = fmaf(dx, dx, fmaf(dy, dy, q));
         }
         const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + a.ln_eps);
-        if (lane == 0) { s_mean[uwarp] = mean; s_rstd[uwarp] = rstd; }
+        if (lane == 0) { s_mean[row] = mean; s_rstd[row] = rstd; }
       }
     };
     // Products: D[128 weight rows x 16] = W block (tensor memory, `wcol`) x operand (K-major [k/8][8 slots][8] bf16,
@@ -658,7 +705,7 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
     };
     const uint32_t tq = tmem + ((uint32_t)((uwarp & 3) * 32) << 16);  // this warp's quarter of the lanes
     auto unload = [&](uint32_t dcol, float* Pr, int group) {
-      if ((uwarp >> 2) == group) {
+      if (UW == 4 || (uwarp >> 2) == group) {  // four warps cover the 128 lanes; eight split the two accumulators
         float v8[8];
         tc::tmem_ld8(tq + dcol, v8);
         float4* o = reinterpret_cast<float4*>(Pr + ((uwarp & 3) * 32 + lane) * 8);
@@ -671,25 +718,25 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
     auto load_slots0 = [&](int l, int img) {
       const float* src = a.slots0 + (size_t)img * K * D;
       unsigned char* dst = slh_hi(l);
-      for (int i = utid; i < K * (D / 2); i += 256) {
+      for (int i = utid; i < K * (D / 2); i += UT) {
         const int slot = i / (D / 2), c2 = i % (D / 2);
         const float2 x = __ldg(reinterpret_cast<const float2*>(src + slot * D + 2 * c2));
         *reinterpret_cast<uint32_t*>(dst + opnd_off(slot, 2 * c2)) = pack_bf16x2(x.x, x.y);
       }
       float* own = own_of(l);
-      for (int i = utid; i < K * DS; i += 256) own[i] = __ldg(src + (i / DS) * D + rank * DS + i % DS);
+      for (int i = utid; i < K * DS; i += UT) own[i] = __ldg(src + (i / DS) * D + rank * DS + i % DS);
       fence_proxy_async();
       upd_sync();
     };
     // q = W_q LN(slots) of lane l for the CTA's slice (slots = slh[l], bf16), all-gathered (times log2 e) into the lane's q operand
     auto q_phase = [&](int l, int q_img, int q_t) {
-      product(C::COL_WY, slh_hi(l), D / 16, C::COL_GH, 0);
+      product(C::COL_WY, slh_hi(l), D / 16, col_gh, 0);
       row_stats(slh_hi(l));
       arm(round, (uint32_t)(K * D * 2));
       product_wait(0);
-      unload(C::COL_GH, P_GH, 1);
+      unload(col_gh, P_GH, 1);
       upd_sync();
-      for (int i0 = uwarp * 32; i0 < K * DS; i0 += 256) {
+      for (int i0 = uwarp * 32; i0 < K * DS; i0 += UT) {
         const int i = i0 + lane;
         float val = 0.f;
         if (i < K * DS) {
@@ -705,18 +752,23 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
       ++round;
       if (utid == 0) {  // the MMA issuer may read lane l's q operand (tcgen05.mma reads it through the async proxy)
         fence_proxy_async();
+        if (NUS > 1) {  // one writer at a time per lane (a lane's updates are ordered), so a plain increment is enough
+          const uint32_t cnt = q_count[l] + 1u;
+          asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(&q_count[l])), "r"(cnt) : "memory");
+        }
         mbar_arrive(&q_ready[l]);
       }
     };
 
     // initial queries of the lanes
-    for (int l = 0; l < NL; ++l)
+    for (int l = us; l < NL; l += NUS)
       if (nops[l] > 0) {
         if (l > 0) load_slots0(l, image_of(l, 0));  // lane 0's were staged during the setup
         q_phase(l, image_of(l, 0), 0);
       }
 
-    for (int n = 0; n < total_ops; ++n) {
+    for (int n = us; n < total_ops; n += NUS) {  // the stream's ops
+      const int ns = n / NUS;  // ... counted per stream (barrier phases)
       int l, c;
       op_of(n, l, c);
       const int t = c % T, m = c / T, img = image_of(l, m);
@@ -726,14 +778,23 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
 #define PP_T(i) do { if (tr_on) a.trace[8 + n * 8 + (i)] = clock64(); } while (0)
       // ============================================================ R1: reduce-scatter of sum w v, all-reduce of sum w
       arm(round, (uint32_t)(K * D * 4 + 32 * CL));
-      // gh = W_hh h only needs the slots that entered the iteration: it runs under the pass and the R1 round trip
-      product(C::COL_WY, slh_hi(l), D / 16, C::COL_GH, 1);
-      mbar_wait(u_ready, (uint32_t)(n & 1));
+      // gh = W_hh h only needs the slots that entered the iteration: it runs under the pass and the R1 round trip.
+      // The lane's previous update may have run on the other stream: its last act was the lane's query for this op
+      // (phase c of q_ready[l]).  A parity wait cannot tell how far the barrier is -- this stream may come here one phase
+      // early or one phase late -- so the streams follow a per-lane count of the queries published so far.
+      if (NUS > 1) {
+        uint32_t seen;
+        do {
+          asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(&q_count[l])) : "memory");
+        } while (seen < (uint32_t)(c + 1));
+      }
+      product(C::COL_WY, slh_hi(l), D / 16, col_gh, 1);
+      mbar_wait(u_ready, (uint32_t)(ns & 1));
       PP_T(2);
       {
         const uint32_t lbuf = smem_u32(xb), lbar = smem_u32(&xbar[round & 1]);
         constexpr int QPR = D / 4;
-        for (int i = utid; i < K * QPR; i += 256) {
+        for (int i = utid; i < K * QPR; i += UT) {
           const int slot = i / QPR, d = 4 * (i % QPR);
           const int dest = d / DS, dl = d % DS;
           const float4 val = *reinterpret_cast<const float4*>(ustage + slot * UP + d);
@@ -757,7 +818,7 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
       {
         const float* rs = reinterpret_cast<const float*>(xb);
         const float* ss = rs + KB * D;
-        for (int i0 = uwarp * 32; i0 < K * DS; i0 += 256) {
+        for (int i0 = uwarp * 32; i0 < K * DS; i0 += UT) {
           const int i = i0 + lane;
           float val = 0.f;
           if (i < K * DS) {
@@ -781,17 +842,17 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
       }
       xwait(round);
       // ---- GRU: gi = W_ih u
-      product(C::COL_WX, act(round), D / 16, C::COL_GI, 0);
+      product(C::COL_WX, act(round), D / 16, col_gi, 0);
       ++round;
       arm(round, (uint32_t)(K * D * 2));
       product_wait(1);  // gh
       product_wait(0);  // gi
-      unload(C::COL_GI, P_GI, 0);
-      unload(C::COL_GH, P_GH, 1);
+      unload(col_gi, P_GI, 0);
+      unload(col_gh, P_GH, 1);
       upd_sync();
       PP_T(4);
       // ============================================================ R3: all-gather h'
-      for (int i0 = uwarp * 32; i0 < K * DS; i0 += 256) {
+      for (int i0 = uwarp * 32; i0 < K * DS; i0 += UT) {
         const int i = i0 + lane;
         float hp = 0.f;
         if (i < K * DS) {
@@ -819,16 +880,16 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
       }
       xwait(round);
       // ---- MLP layer 1 on the raw h' (LayerNorm folded), statistics alongside
-      product(C::COL_WX, act(round), D / 16, C::COL_GI, 0);
+      product(C::COL_WX, act(round), D / 16, col_gi, 0);
       row_stats(act(round));
       ++round;
       arm(round, (uint32_t)(K * H * 2));
       product_wait(0);
-      unload(C::COL_GI, P_GI, 0);
+      unload(col_gi, P_GI, 0);
       upd_sync();
       PP_T(5);
       // ============================================================ R4: all-gather the MLP hidden layer
-      for (int i0 = uwarp * 32; i0 < K * HS; i0 += 256) {
+      for (int i0 = uwarp * 32; i0 < K * HS; i0 += UT) {
         const int i = i0 + lane;
         float hid = 0.f;
         if (i < K * HS) {
@@ -841,16 +902,16 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
         quad_push(round, hid, i, HS, act(round));
       }
       xwait(round);
-      product(C::COL_WX, act(round), H / 16, C::COL_GI, 0);
+      product(C::COL_WX, act(round), H / 16, col_gi, 0);
       ++round;
       if (!last) arm(round, (uint32_t)(K * D * 2));
       product_wait(0);
-      unload(C::COL_GI, P_GI, 0);
+      unload(col_gi, P_GI, 0);
       upd_sync();
       PP_T(6);
       // ============================================================ R5: all-gather the new slots (or write them out)
       const bool more = last && (m + 1 < nimg_of(l));
-      for (int i0 = uwarp * 32; i0 < K * DS; i0 += 256) {
+      for (int i0 = uwarp * 32; i0 < K * DS; i0 += UT) {
         const int i = i0 + lane;
         float sn = 0.f;
         if (i < K * DS) {
@@ -942,9 +1003,9 @@ static size_t umma_prep_bytes() {
   return (size_t)CL * 2 * (LX / 2) * 128 * 4 + (size_t)CL * (2 * (H / CL) + 2 * (D / CL)) * 4;
 }
 
-template <int D, int H, int CL, int NL, int KB, int NKS, int NVS, int NWB>
+template <int D, int H, int CL, int NL, int KB, int NKS, int NVS, int NWB, int NUS, int DEFER = 0>
 static int launch_umma(const IterFwdArgs& a_in, cudaStream_t stream) {
-  using C = Cfg<D, H, CL, NL, KB, NKS, NVS, NWB>;
+  using C = Cfg<D, H, CL, NL, KB, NKS, NVS, NWB, NUS, DEFER>;
   IterFwdArgs a = a_in;
   if (a.workspace == nullptr || a.workspace_bytes < umma_prep_bytes<D, H, CL>() + 4096 + 256) {
     set_error("sa_iter_fwd(tcgen05): needs the workspace of ocrl_sa_query_workspace (bf16 weight copies)");
@@ -954,11 +1015,13 @@ static int launch_umma(const IterFwdArgs& a_in, cudaStream_t stream) {
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(a.workspace) + 255) & ~uintptr_t(255));
     a.wprep = reinterpret_cast<uint32_t*>(base);
     a.wprep_consts = reinterpret_cast<float*>(base + (size_t)CL * 2 * C::WPB * 128 * 4);
-    umma_prep_kernel<D, H, CL><<<CL * 2 * 128 / 8, 256, 0, stream>>>(a.w, const_cast<uint32_t*>(a.wprep), const_cast<float*>(a.wprep_consts));
-    ocrl::count_launch();
-    OCRL_CHECK_CUDA(cudaGetLastError());
+    if (!a.prepared) {
+      umma_prep_kernel<D, H, CL><<<CL * 2 * 128 / 8, 256, 0, stream>>>(a.w, const_cast<uint32_t*>(a.wprep), const_cast<float*>(a.wprep_consts));
+      ocrl::count_launch();
+      OCRL_CHECK_CUDA(cudaGetLastError());
+    }
   }
-  auto kern = sa_iter_fwd_umma_kernel<D, H, CL, NL, KB, NKS, NVS, NWB>;
+  auto kern = sa_iter_fwd_umma_kernel<D, H, CL, NL, KB, NKS, NVS, NWB, NUS, DEFER>;
   static_assert(C::SMEM_BYTES <= 227 * 1024, "shared memory budget");
   CUtensorMap tm_k, tm_v;
   const uint64_t rows = (uint64_t)a.B * a.N;
@@ -1007,6 +1070,9 @@ static int launch_umma(const IterFwdArgs& a_in, cudaStream_t stream) {
 
 }  // namespace umma
 
+static int g_dev_variant = 0;
+extern "C" void ocrl_dev_iter_variant(int v) { g_dev_variant = v; }  // development knob (scripts/quick_iter.py), not in the header
+
 // Returns OCRL_E_SHAPE (without launching) for shapes this kernel does not cover.
 int sa_iter_fwd_umma_dispatch(const IterFwdArgs& a, cudaStream_t s) {
   if (a.K > 8) {
@@ -1017,15 +1083,18 @@ int sa_iter_fwd_umma_dispatch(const IterFwdArgs& a, cudaStream_t s) {
     // three lanes hide the slot update completely (B = 64: 122 against 133 us with two); two keep the k/v of the images
     // in flight inside the L2 (compulsory DRAM traffic only)
     if (a.K <= 6) {
-      if (a.lanes == 2) return umma::launch_umma<192, 192, 8, 2, 6, 3, 4, 2>(a, s);
-      return umma::launch_umma<192, 192, 8, 3, 6, 3, 4, 2>(a, s);
+      // measured at B = 64 (us, three lanes / two lanes): one update stream, 4 v slots 124 / 133; two streams, 3 v slots
+      // 118 / 140; two streams + deferred drain 125 / 162
+      if (a.lanes == 2) return umma::launch_umma<192, 192, 8, 2, 6, 3, 4, 2, 1, 0>(a, s);
+      if (g_dev_variant == 1) return umma::launch_umma<192, 192, 8, 3, 6, 3, 3, 2, 2, 1>(a, s);
+      return umma::launch_umma<192, 192, 8, 3, 6, 3, 3, 2, 2, 0>(a, s);
     }
-    if (a.lanes == 2) return umma::launch_umma<192, 192, 8, 2, 8, 3, 4, 2>(a, s);
-    return umma::launch_umma<192, 192, 8, 3, 8, 3, 4, 2>(a, s);
+    if (a.lanes == 2) return umma::launch_umma<192, 192, 8, 2, 8, 3, 3, 2, 2>(a, s);
+    return umma::launch_umma<192, 192, 8, 3, 8, 3, 3, 2, 2>(a, s);
   }
   if (a.D == 64 && a.H == 128) {  // the "Slot-Attention (small)" configuration
-    if (a.B >= 48 && a.lanes != 3) return umma::launch_umma<64, 128, 4, 2, 8, 6, 6, 2>(a, s);
-    return umma::launch_umma<64, 128, 8, 3, 8, 6, 6, 2>(a, s);
+    if (a.B >= 48 && a.lanes != 3) return umma::launch_umma<64, 128, 4, 2, 8, 6, 6, 2, 1>(a, s);
+    return umma::launch_umma<64, 128, 8, 3, 8, 6, 6, 2, 1>(a, s);
   }
   set_error("sa_iter_fwd(tcgen05): D=%d H=%d not instantiated", a.D, a.H);
   return OCRL_E_SHAPE;

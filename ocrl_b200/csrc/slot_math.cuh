@@ -40,6 +40,7 @@ struct IterFwdArgs {
   const float* wprep_consts = nullptr;
   int max_clusters = 0;  // ocrl_sa_launch_opts: cap on the resident clusters of the persistent kernels (0 = launcher's choice)
   int lanes = 0;         // ocrl_sa_launch_opts: images in flight per cluster (0 = default)
+  int prepared = 0;      // ocrl_sa_launch_opts: the workspace already holds the prepared weights
 };
 
 // out[j*ldo + out_off + row] = dot(W[row0+row, 0:L], vec[j, 0:L]) for row < nrows, j < KP.

@@ -22,17 +22,42 @@ class GraphedEncoder:
         assert example_obs.is_cuda, "GraphedEncoder captures a CUDA graph"
         self._ocr = ocr
         self._with_masks = with_masks
+        self._warmup = warmup
+        self._iter_clusters = iter_clusters
         self.static_obs = example_obs.clone()
-        side = torch.cuda.Stream(device=example_obs.device)
-        side.wait_stream(torch.cuda.current_stream(example_obs.device))
-        with torch.cuda.stream(side), torch.no_grad():
-            for _ in range(warmup):  # warm up allocator, cuDNN autotuner, lazy module state
+        self._capture()
+
+    def _params(self):
+        mod = getattr(self._ocr, "_module", self._ocr)
+        return list(mod.parameters()) if hasattr(mod, "parameters") else []
+
+    def _weights_key(self):
+        """The captured graph reads device copies derived from the parameters (bf16 convolution weights, position table,
+        exp(log sigma), the iteration kernel's prepared weights): it is valid for exactly this set of parameter versions."""
+        return tuple((p.data_ptr(), p._version) for p in self._params())
+
+    def _capture(self):
+        dev = self.static_obs.device
+        opts = lambda: F.launch_options(max_clusters=self._iter_clusters or 0)  # noqa: E731 (single-use context managers)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with opts(), torch.cuda.stream(side), torch.no_grad():
+            for _ in range(self._warmup):  # warm up allocator, lazy module state, the weight caches the graph will read
                 self._call()
-        torch.cuda.current_stream(example_obs.device).wait_stream(side)
-        torch.cuda.synchronize(example_obs.device)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
-        with F.launch_options(max_clusters=iter_clusters or 0), torch.cuda.graph(self.graph), torch.no_grad():
+        with opts(), torch.cuda.graph(self.graph), torch.no_grad():
             self.static_out = self._call()
+        self._key = self._weights_key()
+
+    def stale(self) -> bool:
+        """True when a parameter changed (optimizer step, load_state_dict, .to()) since the graph was captured."""
+        return self._key != self._weights_key()
+
+    def recapture(self):
+        torch.cuda.synchronize(self.static_obs.device)
+        self._capture()
 
     def _call(self):
         if self._with_masks:
@@ -41,7 +66,9 @@ class GraphedEncoder:
 
     def __call__(self, obs: torch.Tensor):
         """Copies ``obs`` (host or device) into the static input, replays, returns the static output
-        (valid until the next call)."""
+        (valid until the next call).  A graph whose parameters changed since the capture is captured again first."""
+        if self.stale():
+            self.recapture()
         self.static_obs.copy_(obs, non_blocking=True)
         self.graph.replay()
         return self.static_out
@@ -89,12 +116,18 @@ class StreamedEncoder:
         s = self._i % self._nb
         self._i += 1
         enc = self._enc[s]
+        if enc.stale():  # parameters changed since the capture: drain the pipeline, capture every buffer again
+            self.synchronize()
+            for e in self._enc:
+                e.recapture()
         caller = torch.cuda.current_stream(self._dev)
         main = self._compute[s] if self._compute is not None else caller
         if self._compute is not None and not self._used[s]:
             main.wait_stream(caller)                # work the caller queued before the first submit
         if self._used[s]:
             self._in.wait_event(self._ev_done[s])   # the graph that read this input buffer has finished
+        if obs_host.is_cuda:
+            self._in.wait_stream(caller)            # a device input may still be in production on the caller's stream
         with torch.cuda.stream(self._in):
             enc.static_obs.copy_(obs_host, non_blocking=True)
             self._ev_in[s].record(self._in)

@@ -91,8 +91,12 @@ class SlotAttention(nn.Module):
             inputs.requires_grad or slots.requires_grad or any(t.requires_grad for t in p.values()))
         if not needs_grad:
             with torch.no_grad():
+                prep = self.__dict__.get("_prepared")
+                if prep is None:
+                    prep = self.__dict__["_prepared"] = F.PreparedWeights()
                 return F.slot_attention(inputs, slots, p, self.num_iterations, epsilon=self.epsilon,
-                                        kv=self.kv_dtype, enc=_enc, pos_table=_pos_table, opts=self.launch_opts)
+                                        kv=self.kv_dtype, enc=_enc, pos_table=_pos_table, opts=self.launch_opts,
+                                        prepared=prep)
         assert _enc is None and _pos_table is None, "fused token stage is an inference-only path"
         return F.SlotAttentionFunction.apply(inputs, slots, self.num_iterations, self.epsilon, self.kv_dtype,
                                              *[p[n] for n in F.SA_PARAM_ORDER])

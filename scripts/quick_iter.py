@@ -35,8 +35,13 @@ def main():
     k, v, _ = F.kv_project(x, p, kv="bf16")
     bytes_img = 2 * N * D * 2 + N * K * 4 + 2 * K * D * 4
     ref = None
-    for name, kw in [("tcgen05", dict(variant="tcgen05")), ("tcgen05_2lanes", dict(variant="tcgen05", lanes=2)),
-                     ("pipe", dict(variant="pipe")), ("pipe_2lanes", dict(variant="pipe", lanes=2))]:
+    dev = [int(x) for x in os.environ.get("OCRL_DEV_VARIANTS", "0").split(",")]
+    cases = []
+    for dv in dev:
+        cases += [(f"tcgen05_v{dv}", dict(variant="tcgen05"), dv), (f"tcgen05_2lanes_v{dv}", dict(variant="tcgen05", lanes=2), dv)]
+    cases += [("pipe", dict(variant="pipe"), 0)]
+    for name, kw, dv in cases:
+        abi.lib().ocrl_dev_iter_variant(dv)
         opts = abi.launch_opts(strict=True, **kw)
         try:
             s, at, _ = F.iterate(k, v, s0, p, T, opts=opts)

@@ -76,9 +76,9 @@ def test_abi_exports_every_declared_symbol():
     assert declared == set(abi.EXPORTS), declared ^ set(abi.EXPORTS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.ocrl_version() == 4 and lib.ocrl_built_arch() == b"sm_100a"
+    assert lib.ocrl_version() == 5 and lib.ocrl_built_arch() == b"sm_100a"
     assert ctypes.sizeof(abi.SaDims) == 56 and ctypes.sizeof(abi.SaWeights) == 13 * 8
-    assert ctypes.sizeof(abi.TokenWeights) == 10 * 8 and ctypes.sizeof(abi.LaunchOpts) == 20
+    assert ctypes.sizeof(abi.TokenWeights) == 10 * 8 and ctypes.sizeof(abi.LaunchOpts) == 24
 
 
 def test_abi_rejects_bad_dims_without_a_gpu():

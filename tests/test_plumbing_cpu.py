@@ -13,7 +13,7 @@ from tests.golden_io import load_case, rel_err
 
 
 def _oracle_slot_attention(inputs, slots0, p, T, *, epsilon=1e-8, kv="fp32", enc=None, pos_table=None,
-                           want_attn=True, opts=None):
+                           want_attn=True, opts=None, prepared=None):
     if pos_table is not None:
         B, C, H, W = inputs.shape
         inputs = (inputs + pos_table.view(1, C, H, W)).permute(0, 2, 3, 1).flatten(1, 2)
