@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the short SLATE training-step measurement")
     ap.add_argument("--pool", type=int, default=512, help="distinct frames in the synthetic pool")
+    ap.add_argument("--sustain", type=float, default=1.2, help="seconds of the extra sustained run (0: skip)")
     return ap.parse_args()
 
 
@@ -58,7 +59,7 @@ def workload(a):
     return {"workload": f"SLATE encode, {a.size}x{a.size} random-N5C4S4S2 frames (N={a.size * a.size} tokens), "
                         f"K={a.slots}, T={a.iters}, D={a.slot_size}, batch {a.batch}/GPU",
             "frame": a.size, "tokens": a.size * a.size, "num_slots": a.slots, "num_iterations": a.iters,
-            "slot_size": a.slot_size, "batch_per_gpu": a.batch, "mode": a.mode,
+            "slot_size": a.slot_size, "batch_per_gpu": a.batch,
             "weights": "seeded random-init (pretrained_encoders/slate.pth absent from the reference checkout)"}
 
 
@@ -98,6 +99,39 @@ def time_cpu(a, frames_u8, steps, warmup):
     return a.batch * steps / dt, dt / steps * 1e3, cores
 
 
+def time_cpu_train(a, frames_u8, batch=8, steps=2):
+    """The reference's training step (ocrs/base.py:60-74: get_loss + backward + inf-norm clip + Adam) on the host cores:
+    the module wiring of ocrl_b200.SLATE with the slot-attention operators replaced by the oracle port (the CPU leg is
+    the one place bench.py may execute oracle/), bounded sample of `batch` frames."""
+    import ocrl_b200
+    from ocrl_b200 import functional as F, slot_attn
+    from ocrl_b200.config import slate_config
+    from oracle import slot_oracle as so
+
+    class _OracleFn:
+        @staticmethod
+        def apply(inputs, slots0, T, epsilon, kv, *params):
+            return so.slot_attention(inputs, slots0, dict(zip(F.SA_PARAM_ORDER, params)), T, epsilon)
+
+    saved = (F.SlotAttentionFunction, slot_attn.SlotAttention._check)
+    F.SlotAttentionFunction = _OracleFn
+    slot_attn.SlotAttention._check = lambda self, inputs, slots, fmap=False: None
+    try:
+        torch.manual_seed(0)
+        model = ocrl_b200.SLATE(*slate_config(num_slots=a.slots, num_iterations=a.iters, slot_size=a.slot_size,
+                                              mlp_hidden_size=a.slot_size, obs_size=a.size))
+        model.train()
+        obs = frames_u8[:batch].permute(0, 3, 1, 2).float() / 255.0
+        model.update(obs, None, 1000)
+        t0 = time.perf_counter()
+        for i in range(steps):
+            model.update(obs, None, 1001 + i)
+        dt = (time.perf_counter() - t0) / steps
+    finally:
+        F.SlotAttentionFunction, slot_attn.SlotAttention._check = saved
+    return batch / dt, dt * 1e3, batch
+
+
 def run_reference(a, rank, out=sys.stdout):
     """--impl reference: the reference's CPU path for the same metric and config."""
     if rank != 0:
@@ -107,13 +141,22 @@ def run_reference(a, rank, out=sys.stdout):
     frames = torch.from_numpy(synth.random_objs_frames(max(a.batch, 64), a.size, seed=0))
     steps = max(1, a.steps)
     ips, ms, cores = time_cpu(a, frames, steps, max(1, min(a.warmup, 2)))
+    train = None
+    if not a.no_train:
+        try:
+            tips, tms, tb = time_cpu_train(a, frames)
+            train = {"value": tips, "unit": "images/s", "ms_per_step": tms, "cores": cores, "kind": "port",
+                     "sample": f"2 steps of SLATE.update on {tb} frames (get_loss + backward + clip + Adam), torch CPU ops "
+                               f"with the oracle port of the slot-attention loop, fp32, {cores} threads"}
+        except Exception as exc:
+            train = {"error": repr(exc)[:300]}
     sample = f"{steps} steps of one {a.batch}-frame batch, oracle port (torch CPU ops, fp32), {cores} threads"
     line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
             "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload(a),
             "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, "train_step": train}
     print(json.dumps(line), file=out, flush=True)
 
 
@@ -166,7 +209,7 @@ class Clocks:
 
 
 # ------------------------------------------------------------------------------------------------
-def measure(a, mode, steps, warmup, dev, dist, rank, world, pool_host, pool_dev, want_events=True):
+def measure(a, mode, steps, warmup, dev, dist, rank, world, pool_host, pool_dev, want_events=True, sustain_s=0.0):
     """One precision mode: eager loop (kernel events -> roofline), CUDA-graph resident loop (value) and
     CUDA-graph end-to-end loop from pinned host frames (e2e)."""
     import ocrl_b200
@@ -224,6 +267,13 @@ def measure(a, mode, steps, warmup, dev, dist, rank, world, pool_host, pool_dev,
             return model(batch_dev(i))
 
     ms_eager, events = timed(step_eager, steps, warmup, kernel_timers=want_events)
+    # kernels of libocrl_sa.so per step: the library counts its own launches (ocrl_launch_count); one warm eager step
+    # launches what one graph replay holds as kernel nodes (the graphs are captured from the same call)
+    from ocrl_b200 import abi
+    c0 = abi.lib().ocrl_launch_count()
+    step_eager(0)
+    torch.cuda.synchronize()
+    own_per_step = int(abi.lib().ocrl_launch_count() - c0)
 
     out_host = torch.empty(a.batch, a.slots, a.slot_size, dtype=torch.float32).pin_memory()
     graphed = None
@@ -266,21 +316,35 @@ def measure(a, mode, steps, warmup, dev, dist, rank, world, pool_host, pool_dev,
     ms_res, _ = timed(step_resident, steps, warmup, join=e2e_join)
     ms_single = timed(step_single, steps, warmup)[0] if step_single is not None else None
     ms_e2e, _ = timed(step_e2e, steps, max(3, warmup), join=e2e_join)
+    sustained = None
+    if sustain_s > 0:  # the same resident loop for >= sustain_s seconds, with its own clock samples (rank 0)
+        n_sus = max(steps, int(sustain_s * 1e3 / max(ms_res / steps, 1e-3)) + 1)
+        clk = Clocks(dev.index if dev.index is not None else 0)
+        if rank == 0:
+            clk.start()
+        ms_sus, _ = timed(step_resident, n_sus, 3, join=e2e_join)
+        ms_sus_e2e, _ = timed(step_e2e, n_sus, 3, join=e2e_join)
+        sustained = {"value": a.batch * n_sus * world / ms_sus * 1e3, "e2e_value": a.batch * n_sus * world / ms_sus_e2e * 1e3,
+                     "unit": UNIT, "steps": n_sus, "seconds": ms_sus / 1e3, "e2e_seconds": ms_sus_e2e / 1e3,
+                     "clocks": clk.stop() if rank == 0 else None}
     images = a.batch * steps * world
     res = {"value": images / ms_res * 1e3, "ms_per_step": ms_res / steps, "eager_value": images / ms_eager * 1e3,
            "e2e_value": images / ms_e2e * 1e3, "e2e_ms_per_step": ms_e2e / steps, "graph": graphed is not None,
            "single_stream_value": (images / ms_single * 1e3) if ms_single else None,
-           "events": events or []}
+           "events": events or [], "own_per_step": own_per_step, "sustained": sustained}
     return res
 
 
-def measure_train(a, dev, pool_dev, steps=8, warmup=3):
-    """SLATE OCR training step (BASELINE.json config 3: num_slots 6, num_iterations 3, bf16 k/v) on one GPU:
-    ``SLATE.update`` = get_loss + backward + inf-norm clip + Adam.  The slot-attention loop and the k/v projection
-    run the hand-written forward and backward kernels; the dVAE, the transformer decoder, the CNN encoder's
-    backward and the optimizer are torch / cuDNN (library code), so this is a context number, not a roofline."""
+def measure_train(a, dev, pool_dev, dist, rank, world, steps=8, warmup=3):
+    """SLATE OCR training step (BASELINE.json config 3: num_slots 6, num_iterations 3, bf16 k/v), batch per GPU as in
+    the encode metric: ``SLATE.update`` = get_loss + backward + gradient all-reduce (N > 1) + inf-norm clip + Adam.
+    The slot-attention loop and the k/v projection run the hand-written forward and backward kernels; the dVAE, the
+    transformer decoder, the CNN encoder's backward and the optimizer are torch / cuDNN (library code), so this is a
+    context number, not a roofline.  N > 1: data parallel over NCCL (ocrl_b200.dp: bucketed all-reduce launched from
+    gradient hooks on a side stream, under the rest of the backward); ``exposed_comm_ms`` is what the compute stream
+    still waits for when the backward has finished (CUDA events around the join), max over ranks."""
     import ocrl_b200
-    from ocrl_b200 import functional as F
+    from ocrl_b200 import dp, functional as F
     from ocrl_b200.config import slate_config
 
     os.environ["OCRL_KV_DTYPE"] = "bf16"
@@ -291,6 +355,21 @@ def measure_train(a, dev, pool_dev, steps=8, warmup=3):
                                           mlp_hidden_size=a.slot_size, obs_size=a.size))
     model.to(dev)
     model.train()
+    comm_events, reduce_bytes = [], 0
+    if world > 1:
+        dp.make_data_parallel(model)
+        reducer = model._grad_reducer
+        reduce_bytes = sum((sum(p.numel() for p in b) + len(b)) * 4 for b in reducer.buckets)
+        finish = reducer.finish
+
+        def timed_finish():
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            finish()
+            e1.record()
+            comm_events.append((e0, e1))
+
+        model._after_backward = timed_finish
     nb = a.pool // a.batch
 
     def step(i):
@@ -298,22 +377,36 @@ def measure_train(a, dev, pool_dev, steps=8, warmup=3):
 
     for i in range(warmup):
         step(i)
+    if dist is not None:
+        dist.barrier()
     torch.cuda.synchronize()
+    comm_events.clear()
     F.KERNEL_EVENTS = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
         m = step(warmup + i)
     e1.record()
+    if dist is not None:
+        dist.barrier()
     torch.cuda.synchronize()
     ev, F.KERNEL_EVENTS = F.KERNEL_EVENTS, None
     ms = e0.elapsed_time(e1) / steps
+    comm_ms = sum(x.elapsed_time(y) for x, y in comm_events) / steps if comm_events else 0.0
+    if dist is not None:
+        t = torch.tensor([ms, comm_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, comm_ms = float(t[0]), float(t[1])
     per = {}
     for name, s0, s1 in ev:
         per.setdefault(name, []).append(s0.elapsed_time(s1))
-    return {"value": a.batch / ms * 1e3, "unit": "images/s", "ms_per_step": ms, "steps": steps,
+    return {"value": a.batch * world / ms * 1e3, "unit": "images/s", "ms_per_step": ms, "steps": steps, "n_gpus": world,
+            "scaling": "weak", "batch_per_gpu": a.batch,
             "loss": float(m["loss"].detach()), "kernels_ms": {k: sum(v) / len(v) for k, v in per.items()},
-            "config": "SLATE.update (get_loss + backward + clip + Adam), bf16 k/v, batch %d, eager launches; "
+            "allreduce_bytes_per_step": reduce_bytes, "exposed_comm_ms": comm_ms,
+            "collective": ("NCCL all-reduce of %d gradient buckets per step, launched from gradient hooks on a side stream"
+                           % len(model._grad_reducer.buckets)) if world > 1 else None,
+            "config": "SLATE.update (get_loss + backward + clip + Adam), bf16 k/v, batch %d per GPU, eager launches; "
                       "slot-attention fwd/bwd + k/v projection hand-written, dVAE / decoder / CNN backward library code "
                       "(torch defaults: cuDNN TF32 on, fp32 matmul)"
                       % a.batch}
@@ -332,22 +425,26 @@ def roofline_of(a, mode, events):
             peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured"
     except Exception:
         pass
-    # DRAM traffic per launch of the same kernels from the committed `ncu --set full` capture (profiles/, per mode);
-    # it is a property of the kernel build, not re-measured here (a number taken under a profiler is never timed)
+    # DRAM traffic per launch (dram__bytes_read + write) from the `ncu --set full` capture under profiles/r2/ -- used only
+    # when that capture was taken from THIS build (digest of the kernel sources) and this configuration, else null:
+    # a number taken under a profiler is never timed here, and a capture of another build says nothing about this one
     traffic, tok_traffic = None, None
     try:
-        with open(os.path.join(ROOT, "profiles", "r1", f"traffic_{mode}.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2", f"traffic_{mode}.json")) as f:
             tj = json.load(f)
-        if (a.batch, N, D, K, a.iters) == (64, 4096, 192, 6, 3):  # the capture's configuration
-            traffic = tj.get("sa_iter_fwd_pipe_kernel", {}).get("traffic_bytes")
-            tok_traffic = tj.get("kv_proj_tc_kernel", {}).get("traffic_bytes")
+        with open(os.path.join(ROOT, "ocrl_b200", "csrc", "build", "digest.txt")) as f:
+            digest = f.read().strip()
+        if tj.get("build_digest") == digest and tj.get("config") == [a.batch, N, D, K, a.iters]:
+            traffic = tj.get("sa_iter_fwd", {}).get("traffic_bytes")
+            tok_traffic = tj.get("kv_proj_fwd", {}).get("traffic_bytes")
     except Exception:
         pass
     it_avg = sum(it_ms) / max(1, len(it_ms))
     tk_avg = sum(tk_ms) / max(1, len(tk_ms))
     achieved = a.batch * bytes_img / (it_avg * 1e-3) / 1e9 if it_ms else None
     tok_achieved = a.batch * tok_bytes_img / (tk_avg * 1e-3) / 1e9 if tk_ms else None
-    return {"kernel": "sa_iter_fwd_pipe_kernel (two-engine persistent clusters, TMA ring, mma.sync bf16)" if mode == "bf16" else "sa_iter_fwd_kernel (fp32 FFMA)",
+    return {"kernel": ("sa_iter_fwd_umma_kernel (persistent clusters, TMA ring, tcgen05 token pass with TMEM accumulators, "
+                       "two update streams)") if mode == "bf16" else "sa_iter_fwd_kernel (fp32 FFMA)",
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": (achieved / peak if achieved else None), "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": a.batch * bytes_img,
@@ -397,44 +494,52 @@ def main():
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
-    main_res = measure(a, a.mode, a.steps, a.warmup, dev, dist, rank, world, pool_host, pool_dev)
+    main_res = measure(a, a.mode, a.steps, a.warmup, dev, dist, rank, world, pool_host, pool_dev, sustain_s=a.sustain)
     clk = clocks.stop() if rank == 0 else None
     other = None
     if not a.no_other_mode:
         om = "fp32" if a.mode == "bf16" else "bf16"
         other = (om, measure(a, om, max(5, a.steps // 3), 3, dev, dist, rank, world, pool_host, pool_dev))
 
+    train = None
+    if not a.no_train:  # every rank takes part (gradient all-reduce when N > 1)
+        try:
+            train = measure_train(a, dev, pool_dev, dist, rank, world)
+        except Exception as exc:  # the encode metric stands on its own
+            train = {"error": repr(exc)[:300]}
+
     if rank == 0:
         N, D = a.size * a.size, a.slot_size
         esz = 2 if a.mode == "bf16" else 4
-        # own kernel launches per step (each replay holds them as graph kernel nodes; `launches_bf16_mode_v5.txt` lists
-        # them once per step): the C-ABI calls seen by the kernel timers of the eager loop, plus the extra launch each
-        # tensor-path projection makes for its bf16 weight / position-table preparation, plus the first conv layer
-        own = ({"ocrl::proj_tc_prep_kernel": 1, "ocrl::kv_proj_tc_kernel": 1, "pipe::sa_iter_fwd_pipe_kernel": 1,
-                "conv1::conv_first_kernel": 1} if a.mode == "bf16" else
-               {"ocrl::token_stage_kernel": 1, "ocrl::sa_iter_fwd_kernel": 1})
         abi_calls = len(main_res["events"]) // max(a.steps, 1)   # kv_proj_fwd + sa_iter_fwd per eager step
-        assert abi_calls >= 2, "the hand-written kernels did not run in the step"
-        mine = [None] * (a.steps * sum(own.values()))
+        assert abi_calls >= 2 and main_res["own_per_step"] >= 2, "the hand-written kernels did not run in the step"
         line = {"metric": METRIC, "value": main_res["value"], "unit": UNIT, "n_gpus": world, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None,
                 "dtype": ("bf16 (bf16 convs / k / v / tensor-core operands, f32 accumulate, f32 slot update)"
                           if a.mode == "bf16" else "f32"),
                 "data": "synthetic",
-                "config": dict(workload(a), l2="k/v working set per step %.0f MB > 126 MB L2; frame pool of %d rotates"
-                               % (a.batch * 2 * N * D * esz / 1e6, a.pool),
-                               cnn="cuDNN via torch (library call, fused bias+ReLU in bf16 mode); token stage + iteration loop hand-written CUDA",
-                               launch=("CUDA graph replays of SLATE.__call__, three batches in flight on three streams "
-                                       "(single_stream_value: one replay at a time)") if main_res["graph"] else "eager launches",
-                               e2e="ocrl_b200.StreamedEncoder: per step H2D from pinned frames, graph replay, D2H to pinned "
-                                   "slots; copies of neighbouring steps overlap the replays (three buffers)"),
+                "config": workload(a),
+                "notes": {"mode": a.mode,
+                          "l2": "k/v working set per step %.0f MB > 126 MB L2; frame pool of %d rotates"
+                                % (a.batch * 2 * N * D * esz / 1e6, a.pool),
+                          "kernels": "every kernel of the step is hand-written CUDA in libocrl_sa.so (bf16 mode: mma.sync first "
+                                     "convolution, tcgen05 implicit-GEMM 64->64 convolutions, tcgen05 token stage, tcgen05 "
+                                     "iteration kernel); torch only draws the slot noise" if a.mode == "bf16" else
+                                     "fp32 parity mode: cuDNN convolutions (library), FFMA token stage and iteration kernel",
+                          "launch": ("CUDA graph replays of SLATE.__call__, three batches in flight on three streams "
+                                     "(single_stream_value: one replay at a time)") if main_res["graph"] else "eager launches",
+                          "e2e": "ocrl_b200.StreamedEncoder: per step H2D from pinned frames, graph replay, D2H to pinned "
+                                 "slots; copies of neighbouring steps overlap the replays (three buffers)"},
                 "clocks": clk,
                 "e2e": {"value": main_res["e2e_value"], "unit": UNIT, "ms_per_step": main_res["e2e_ms_per_step"],
                         "h2d_bytes_per_step": a.batch * 3 * a.size * a.size * 4,
                         "d2h_bytes_per_step": a.batch * a.slots * a.slot_size * 4},
-                "gpu_launches": len(mine), "own_kernels_per_step": own, "eager_value": main_res["eager_value"],
+                # launches of the library's own kernels inside the timed region of `value`, all ranks
+                "gpu_launches": main_res["own_per_step"] * a.steps * world,
+                "own_kernels_per_step": main_res["own_per_step"], "eager_value": main_res["eager_value"],
                 "single_stream_value": main_res["single_stream_value"],
+                "sustained": main_res["sustained"],
                 "roofline": roofline_of(a, a.mode, main_res["events"])}
         if other is not None:
             om, r = other
@@ -442,11 +547,8 @@ def main():
             line["other_mode"] = {"mode": om, "value": r["value"], "e2e": r["e2e_value"], "unit": UNIT,
                                   "ms_per_step": r["ms_per_step"], "roofline_frac": rf["frac"],
                                   "iter_kernel_ms": rf["avg_launch_ms"], "token_stage_ms": rf["token_stage"]["avg_launch_ms"]}
-        if world == 1 and not a.no_train:
-            try:
-                line["train_step"] = measure_train(a, dev, pool_dev)
-            except Exception as exc:  # the encode metric stands on its own
-                line["train_step"] = {"error": repr(exc)[:300]}
+        if train is not None:
+            line["train_step"] = train
         if world == 1 and not a.no_cpu_baseline:
             csteps = 6
             ips, cms, cores = time_cpu(a, pool_u8, csteps, 1)

@@ -62,6 +62,15 @@ class GradientReducer:
         self._work = [None] * len(self.buckets)
         self._stream = None
         self._hooks = []
+        # which parameters of a bucket produce a gradient is a property of the model (use_bcdec leaves the dVAE and the
+        # transformer decoder untouched), not of the step: the per-bucket flag vectors and the all-rank verdict are
+        # computed once and reused while this rank's pattern stays the same (re-checked every `recheck` steps), so a
+        # steady-state step has no host <-> device synchronisation between backward and the optimizer
+        self._pattern = [None] * len(self.buckets)
+        self._flags = [None] * len(self.buckets)
+        self._touched = [None] * len(self.buckets)
+        self._steps = 0
+        self.recheck = 256
         if self.world > 1:
             for p in self.params:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
@@ -89,7 +98,12 @@ class GradientReducer:
         # one flag per parameter rides at the end of the bucket: did THIS rank produce a gradient?  Parameters no rank
         # touched (e.g. the dVAE / transformer decoder when use_bcdec is on) keep grad = None, as on a single GPU, so
         # the optimizer state matches a 1-GPU run
-        flags = torch.tensor([0.0 if p.grad is None else 1.0 for p in bucket], device=dev, dtype=grads[0].dtype)
+        pattern = tuple(p.grad is not None for p in bucket)
+        if pattern != self._pattern[i] or self._flags[i] is None or self._steps % self.recheck == 0:
+            self._pattern[i] = pattern
+            self._flags[i] = torch.tensor([1.0 if hit else 0.0 for hit in pattern], device=dev, dtype=grads[0].dtype)
+            self._touched[i] = None  # decided again from the reduced flags
+        flags = self._flags[i]
         if dev.type == "cuda":
             if self._stream is None:
                 self._stream = torch.cuda.Stream(device=dev)
@@ -114,16 +128,21 @@ class GradientReducer:
             flat = self._flat[i]
             if flat.is_cuda:
                 torch.cuda.current_stream(flat.device).wait_stream(self._stream)
-            touched = (flat[-len(bucket):] > 0).tolist()  # some rank produced a gradient for the parameter
+            if self._touched[i] is None:  # some rank produced a gradient for the parameter (host sync, first step only)
+                self._touched[i] = (flat[-len(bucket):] > 0).tolist()
             flat.div_(self.world)
-            off = 0
-            for p, hit in zip(bucket, touched):
+            off, dst, src = 0, [], []
+            for p, hit in zip(bucket, self._touched[i]):
                 n = p.numel()
                 if hit:
                     if p.grad is None:
                         p.grad = torch.empty_like(p)
-                    p.grad.copy_(flat[off:off + n].view_as(p))
+                    dst.append(p.grad)
+                    src.append(flat[off:off + n].view_as(p))
                 off += n
+            if dst:
+                torch._foreach_copy_(dst, src)  # one fused copy per bucket
+        self._steps += 1
         self.reset()
 
 

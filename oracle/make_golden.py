@@ -183,6 +183,70 @@ def make_training_case(ref, name, *, B, S, seed, steps, use_bcdec):
     print(name, "loss", float(loss))
 
 
+class preset_exponential:
+    """Context manager: ``Tensor.exponential_`` returns the given tensors in order (the gumbel noise of
+    ocrs/common/utils.py:75-85 is ``-log(exponential_())``) -- the one source of randomness of ``get_loss`` that cannot
+    be frozen by a seed across CPU and CUDA generators.  With ``record=True`` it keeps the draws instead."""
+
+    def __init__(self, draws=None, record=False):
+        self.draws, self.record, self.i = ([] if draws is None else list(draws)), record, 0
+
+    def __enter__(self):
+        self._orig = torch.Tensor.exponential_
+        outer = self
+
+        def fake(t, *a, **k):
+            if outer.record:
+                outer._orig(t, *a, **k)
+                outer.draws.append(t.detach().clone().cpu())
+                return t
+            d = outer.draws[outer.i]
+            outer.i += 1
+            assert tuple(d.shape) == tuple(t.shape), (d.shape, t.shape)
+            return t.copy_(d.to(t.device))
+
+        torch.Tensor.exponential_ = fake
+        return self
+
+    def __exit__(self, *exc):
+        torch.Tensor.exponential_ = self._orig
+        return False
+
+
+def make_loss_case(ref, name, *, B, S, seed, use_bcdec):
+    """``SLATE.get_loss`` of the reference (slate_module.py:198-233) with dropout off (eval mode) and the gumbel noise and
+    the slot-initialisation noise frozen: pins ``dvae_mse`` / ``cross_entropy`` (SLATE) or ``mse`` (broadcast decoder).
+    The 5.6 M parameters are not stored: both sides build the module from ``torch.manual_seed(seed)`` (the init
+    families are equal draw for draw, tests/test_interface.py) and the fixture carries a checksum."""
+    K, T, D, H = 6, 3, 64, 128
+    ocr, env = rb.slate_config(num_slots=K, num_iterations=T, slot_size=D, mlp_hidden_size=H,
+                               use_bcdec=use_bcdec, obs_size=S)
+    torch.manual_seed(seed)
+    model = ref.SLATE(ocr, env)
+    model.eval()
+    frames = _frames(B, S, seed + 3)
+    obs = torch.from_numpy(frames).permute(0, 3, 1, 2).float() / 255.0
+    torch.manual_seed(seed + 4)
+    noise = torch.empty(B, K, D).normal_()
+    with torch.no_grad(), preset_exponential(record=True) as rec:  # first run: the gumbel draws get_loss makes
+        model.get_loss(obs, None)
+    torch.manual_seed(seed + 4)  # second run: the draws replayed, so the generator is consumed by the slot noise only
+    with preset_exponential(rec.draws):
+        metrics = model.get_loss(obs, None)
+    out = {"in.frames_u8": torch.from_numpy(frames), "in.noise": noise}
+    for i, d in enumerate(rec.draws):
+        out[f"in.exponential{i}"] = d
+    for k in ("loss", "dvae_mse", "cross_entropy", "mse"):
+        if k in metrics:
+            out["out." + k] = metrics[k].detach().reshape(1)
+    checksum = float(sum(p.detach().double().sum() for p in model._module.parameters()))
+    abs_sum = float(sum(p.detach().double().abs().sum() for p in model._module.parameters()))
+    meta = dict(T=T, K=K, C=64, D=D, H=H, B=B, N=S * S, S=S, eps=1e-8, seed=seed, use_bcdec=use_bcdec,
+                n_draws=len(rec.draws), param_sum=checksum, param_abs_sum=abs_sum, tau=float(model._module._tau))
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), meta=json.dumps(meta), **_np(out))
+    print(name, {k: float(v) for k, v in metrics.items() if torch.is_tensor(v) and v.numel() == 1}, "draws", len(rec.draws))
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     ref = rb.load()
@@ -203,6 +267,9 @@ def main():
     make_slate_case(ref, "bcdec_encode_32", B=3, S=32, seed=32, K=6, T=7, D=64, H=128, use_bcdec=True)
     make_training_case(ref, "slate_path_grad_16", B=2, S=16, seed=41, steps=1, use_bcdec=False)
     make_survey_kat(ref)
+    # get_loss of the adjacent training modules (dVAE, transformer decoder, broadcast decoder), noise frozen
+    make_loss_case(ref, "loss_slate_16", B=2, S=16, seed=51, use_bcdec=False)
+    make_loss_case(ref, "loss_bcdec_16", B=2, S=16, seed=52, use_bcdec=True)
 
 
 if __name__ == "__main__":

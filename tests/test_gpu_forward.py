@@ -66,6 +66,11 @@ def test_slot_attention_fp32_matches_reference(name):
     ties = so.tie_mask(a64, 1e-5)
     same = a.argmax(-1) == g["out"]["attn"].argmax(-1)
     assert bool((same | ties).all()), int((~(same | ties)).sum())
+    # how much the tie rule excuses: tokens whose fp64 top-2 margin is below 1e-5, and how many of those really differ
+    n_tok, n_ties, n_excused = same.numel(), int(ties.sum()), int((~same & ties).sum())
+    print(f"{name}: {n_tok} tokens, {n_ties} with fp64 top-2 margin < 1e-5, {n_excused} argmax differences excused")
+    assert n_ties <= max(2, n_tok // 2000) or meta["K"] == 1, (n_ties, n_tok)  # a handful, never a loophole
+    assert n_excused <= max(1, n_tok // 5000), (n_excused, n_tok)
 
 
 @pytest.mark.parametrize("name", SA_CASES)

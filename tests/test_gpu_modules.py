@@ -160,3 +160,31 @@ def test_streamed_encoder_matches_direct_calls(iter_clusters, kv):
     assert rel_err(outs[0], g["out"]["slots"]) < tol and rel_err(outs[3], g["out"]["slots"]) < tol
     if kv == "bf16":
         assert F.last_kernel() == "tcgen05"
+
+
+@pytest.mark.parametrize("name", ["loss_slate_16", "loss_bcdec_16"])
+def test_get_loss_matches_reference_on_gpu(name):
+    """``get_loss`` on the GPU (fused slot-attention kernels inside, dVAE / decoders through torch) against the frozen
+    reference numbers: ``dvae_mse`` / ``cross_entropy`` / ``loss`` for SLATE, ``mse`` for the broadcast decoder
+    (slate_module.py:198-233), gumbel and slot noise of the reference run, dropout off."""
+    from oracle.make_golden import preset_exponential
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    meta, g = load_case(name)
+    torch.manual_seed(meta["seed"])
+    model = ocrl_b200.SLATE(*slate_config(num_slots=meta["K"], num_iterations=meta["T"], slot_size=meta["D"],
+                                          mlp_hidden_size=meta["H"], obs_size=meta["S"], use_bcdec=meta["use_bcdec"]))
+    psum = float(sum(p.detach().double().sum() for p in model._module.parameters()))
+    assert abs(psum - meta["param_sum"]) < 1e-6 * meta["param_abs_sum"]
+    model.to("cuda")
+    model.eval()
+    _inject_noise(model._module._slotattn, g["in"]["noise"].cuda())
+    obs = (g["in"]["frames_u8"].permute(0, 3, 1, 2).float() / 255.0).cuda()
+    with preset_exponential([g["in"][f"exponential{i}"] for i in range(meta["n_draws"])]):
+        m = model.get_loss(obs, None)
+    for k, want in g["out"].items():
+        got = m[k].detach().cpu().reshape(1)
+        assert rel_err(got, want) < 1e-4, (k, float(got), float(want))
+    m["loss"].backward()  # the loss carries the graph through the fused backward
+    assert all(torch.isfinite(p.grad).all() for p in model._module._slotattn.parameters() if p.grad is not None)

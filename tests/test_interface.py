@@ -111,3 +111,46 @@ def test_schedules():
     assert cosine_anneal(100, 1.0, 0.1, 0, 100) == 0.1
     assert linear_warmup(0, 0, 1, 0, 10) == pytest.approx(0.1)
     assert linear_warmup(10, 0, 1, 0, 10) == 1
+
+
+def test_ocrs_registry_shim():
+    """The reference's registry call sites (train_ocr.py:37, utils/tools.py:326-335) resolve to the drop-ins when
+    ocrl_b200/shim is in front on sys.path: ``getattr(ocrs, cfg.ocr.name)(cfg.ocr, cfg.env)``."""
+    import importlib
+    import sys
+
+    shim = os.path.join(ROOT, "ocrl_b200", "shim")
+    saved = {k: v for k, v in sys.modules.items() if k == "ocrs" or k.startswith("ocrs.")}
+    for k in saved:
+        del sys.modules[k]
+    sys.path.insert(0, shim)
+    try:
+        ocrs = importlib.import_module("ocrs")
+        ocr_cfg, env_cfg = slate_config()
+        assert ocr_cfg.name == "SLATE"
+        model = getattr(ocrs, ocr_cfg.name)(ocr_cfg, env_cfg)  # train_ocr.py:37
+        module = getattr(ocrs, ocr_cfg.name + "_Module")(ocr_cfg, env_cfg)  # utils/tools.py:326-330
+        assert type(model) is ocrl_b200.SLATE and type(module) is ocrl_b200.SLATE_Module
+        assert model.num_slots == 6 and model.rep_dim == 192 and isinstance(model._module, ocrl_b200.SLATE_Module)
+        with pytest.raises(AttributeError):
+            getattr(ocrs, "NoSuchOCR")
+        from oracle import reference_bridge as rb
+
+        if rb.available():  # with the reference further down the path its sub-packages stay reachable through the shim
+            for k in [k for k in sys.modules if k == "ocrs" or k.startswith("ocrs.")]:
+                del sys.modules[k]
+            for name in ("h5py", "omegaconf"):
+                sys.modules.setdefault(name, type(sys)(name))
+            sys.path.insert(1, rb.REFERENCE_ROOT)
+            try:
+                ocrs = importlib.import_module("ocrs")
+                assert ocrs.SLATE is ocrl_b200.SLATE
+                ref_sa = importlib.import_module("ocrs.common.slot_attn")
+                assert ref_sa.__file__.startswith(rb.REFERENCE_ROOT)
+            finally:
+                sys.path.remove(rb.REFERENCE_ROOT)
+    finally:
+        sys.path.remove(shim)
+        for k in [k for k in sys.modules if k == "ocrs" or k.startswith("ocrs.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)

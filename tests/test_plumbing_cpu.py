@@ -99,3 +99,24 @@ def test_get_samples_shapes(cpu_kernels):
     with torch.no_grad():
         out = model.get_samples(torch.rand(2, 3, 16, 16))
     assert out["samples"].dtype.name == "uint8" and out["samples"].shape == (2, 16, 16 * (2 + 6), 3)
+
+
+@pytest.mark.parametrize("name", ["loss_slate_16", "loss_bcdec_16"])
+def test_get_loss_matches_reference(cpu_kernels, name):
+    """``get_loss`` (slate_module.py:198-233) with the gumbel and slot noise of the frozen reference run: dVAE,
+    transformer decoder / broadcast decoder and the loss arithmetic of ocrl_b200.adjacent against the reference's numbers."""
+    from oracle.make_golden import preset_exponential
+
+    meta, g = load_case(name)
+    torch.manual_seed(meta["seed"])
+    model = ocrl_b200.SLATE(*slate_config(num_slots=meta["K"], num_iterations=meta["T"], slot_size=meta["D"],
+                                          mlp_hidden_size=meta["H"], obs_size=meta["S"], use_bcdec=meta["use_bcdec"]))
+    psum = float(sum(p.detach().double().sum() for p in model._module.parameters()))
+    assert abs(psum - meta["param_sum"]) < 1e-6 * meta["param_abs_sum"]  # same seeded parameters as the reference run
+    model.eval()
+    _inject_noise(model._module._slotattn, g["in"]["noise"])
+    obs = g["in"]["frames_u8"].permute(0, 3, 1, 2).float() / 255.0
+    with preset_exponential([g["in"][f"exponential{i}"] for i in range(meta["n_draws"])]):
+        m = model.get_loss(obs, None)
+    for k, want in g["out"].items():
+        assert rel_err(m[k].detach().reshape(1), want) < 1e-5, (k, float(m[k]), float(want))
