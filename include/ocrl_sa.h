@@ -136,6 +136,15 @@ int ocrl_kv_proj_bwd(const ocrl_sa_dims* dims, const float* x, const ocrl_token_
                      const float* dk, const float* dv, float* dx, float* d_ln_w, float* d_ln_b,
                      float* dwk, float* dwv, void* ws, void* stream);
 
+/* Token stage, backward, straight from the rank-(2 T K) coefficients of ocrl_sa_iter_bwd: call ocrl_sa_iter_bwd with
+ * dk = dv = NULL and pass its workspace here (plus the forward's `saved`); dk, dv [B,N,D] are never materialised
+ * (dxh_n = sum_r coef_nr M_r with M = [s W_k^T q ; W_v^T dU/S], dW from coef^T xh).  Same outputs as ocrl_kv_proj_bwd.
+ *   ws: scratch of ocrl_kv_proj_bwd_lowrank_workspace(dims) bytes.  C_in = 64, 2 T K <= 224. */
+size_t ocrl_kv_proj_bwd_lowrank_workspace(const ocrl_sa_dims* dims);
+int ocrl_kv_proj_bwd_lowrank(const ocrl_sa_dims* dims, const float* x, const ocrl_token_weights* w, const void* saved,
+                             const void* iter_bwd_workspace, float* dx, float* d_ln_w, float* d_ln_b,
+                             float* dwk, float* dwv, void* ws, void* stream);
+
 /* The fused T-iteration loop, forward.  Replaces slot_attn.py:64-102.
  *   k,v [B,N,D]; slots0 [B,K,D]; slots_out [B,K,D]; attn_vis_out [B,N,K] or NULL;
  *   saved: NULL (inference) or `saved` bytes from ocrl_sa_query_workspace;
@@ -177,7 +186,8 @@ const char* ocrl_sa_last_kernel(void);
 /* The fused backward of the loop; attention logits are recomputed from k and the saved
  * per-iteration slots rather than stored (autograd of slot_attn.py:64-102).
  *   d_slots [B,K,D]; d_attn_vis [B,N,K] or NULL;
- *   writes dk, dv [B,N,D] fp32, d_slots0 [B,K,D] and every member of dw. */
+ *   writes dk, dv [B,N,D] fp32 (both may be NULL: the per-token coefficients stay in `workspace` for
+ *   ocrl_kv_proj_bwd_lowrank), d_slots0 [B,K,D] and every member of dw. */
 int ocrl_sa_iter_bwd(const ocrl_sa_dims* dims, const void* k, const void* v, const void* saved,
                      const ocrl_sa_weights* w, const float* d_slots, const float* d_attn_vis,
                      float* dk, float* dv, float* d_slots0, const ocrl_sa_weight_grads* dw,
@@ -213,6 +223,11 @@ int ocrl_conv5x5_c64_tc(const void* in_padded, const void* packed_w, const float
                         int W, int relu, void* stream);
 int ocrl_conv_first_relu_bf16p(const float* obs, const float* weight, const float* bias, void* out_padded, int B, int C,
                                int H, int W, int CO, void* stream);
+/* The same layer fed with the frames as the datasets / environments hold them: uint8 HWC [B,H,W,C]
+ * (utils/datasets.py:17).  The ingest `obs / 255.0` (fp32) happens while the rows are staged: bit-identical to
+ * ocrl_conv_first_relu_bf16p on the converted float CHW tensor, a quarter of the input bytes. */
+int ocrl_conv_first_relu_u8p(const unsigned char* frames_hwc, const float* weight, const float* bias, void* out_padded,
+                             int B, int C, int H, int W, int CO, void* stream);
 
 #ifdef __cplusplus
 }

@@ -21,8 +21,9 @@ X_TOKENS_F32, X_NCHW_F32, X_TOKENS_BF16, X_PADDED_BF16 = 0, 1, 2, 3
 EXPORTS = [
     "ocrl_version", "ocrl_built_arch", "ocrl_last_error", "ocrl_launch_count", "ocrl_sa_query_workspace",
     "ocrl_kv_proj_fwd_workspace", "ocrl_kv_proj_fwd", "ocrl_kv_proj_bwd_workspace", "ocrl_kv_proj_bwd",
+    "ocrl_kv_proj_bwd_lowrank_workspace", "ocrl_kv_proj_bwd_lowrank",
     "ocrl_sa_iter_fwd", "ocrl_sa_iter_fwd_ex", "ocrl_sa_last_kernel", "ocrl_sa_iter_bwd",
-    "ocrl_conv_bias_relu_bf16", "ocrl_frames_to_nhwc_bf16", "ocrl_conv_first_relu_bf16",
+    "ocrl_conv_bias_relu_bf16", "ocrl_frames_to_nhwc_bf16", "ocrl_conv_first_relu_bf16", "ocrl_conv_first_relu_u8p",
     "ocrl_conv_padded_bytes", "ocrl_conv5x5_pack_weights", "ocrl_conv5x5_c64_tc", "ocrl_conv_first_relu_bf16p",
 ]
 
@@ -91,6 +92,11 @@ def lib() -> ctypes.CDLL:
         L.ocrl_kv_proj_bwd_workspace.restype = c_size_t
         L.ocrl_kv_proj_bwd.argtypes = [POINTER(SaDims), c_void_p, POINTER(TokenWeights), c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+        L.ocrl_kv_proj_bwd_lowrank_workspace.argtypes = [POINTER(SaDims)]
+        L.ocrl_kv_proj_bwd_lowrank_workspace.restype = c_size_t
+        L.ocrl_kv_proj_bwd_lowrank.argtypes = [POINTER(SaDims), c_void_p, POINTER(TokenWeights), c_void_p, c_void_p,
+                                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+        L.ocrl_kv_proj_bwd_lowrank.restype = c_int
         L.ocrl_sa_iter_fwd.argtypes = [POINTER(SaDims), c_void_p, c_void_p, c_void_p, POINTER(SaWeights), c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p]
         L.ocrl_sa_iter_fwd_ex.argtypes = [POINTER(SaDims), c_void_p, c_void_p, c_void_p, POINTER(SaWeights), c_void_p,
@@ -106,6 +112,8 @@ def lib() -> ctypes.CDLL:
         L.ocrl_conv_first_relu_bf16.restype = c_int
         L.ocrl_conv_first_relu_bf16p.argtypes = L.ocrl_conv_first_relu_bf16.argtypes
         L.ocrl_conv_first_relu_bf16p.restype = c_int
+        L.ocrl_conv_first_relu_u8p.argtypes = L.ocrl_conv_first_relu_bf16.argtypes
+        L.ocrl_conv_first_relu_u8p.restype = c_int
         L.ocrl_conv_padded_bytes.argtypes = [c_int, c_int, c_int]
         L.ocrl_conv_padded_bytes.restype = c_size_t
         L.ocrl_conv5x5_pack_weights.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p]

@@ -32,6 +32,10 @@ int kv_proj_bwd_launch(const ocrl_sa_dims* d, const float* x, const ocrl_token_w
                        const float* dv, float* dx, float* d_ln_w, float* d_ln_b, float* dwk, float* dwv, void* ws,
                        cudaStream_t stream);
 size_t kv_proj_bwd_workspace(const ocrl_sa_dims* d);
+int kv_proj_bwd_lowrank_launch(const ocrl_sa_dims* d, const float* x, const ocrl_token_weights* w, const float* saved,
+                               const void* iter_bwd_ws, float* dx, float* d_ln_w, float* d_ln_b, float* dwk, float* dwv,
+                               void* ws, cudaStream_t stream);
+size_t kv_proj_bwd_lowrank_workspace(const ocrl_sa_dims* d);
 size_t kv_proj_tc_workspace(const ocrl_sa_dims* d);
 size_t sa_iter_tc_workspace(const ocrl_sa_dims* d);
 int kv_proj_tc_launch(const ocrl_sa_dims* d, const void* x, const float* pos, const ocrl_token_weights* w, float* y_out,
@@ -171,6 +175,30 @@ int ocrl_kv_proj_bwd(const ocrl_sa_dims* d, const float* x, const ocrl_token_wei
   return kv_proj_bwd_launch(d, x, w, dk, dv, dx, d_ln_w, d_ln_b, dwk, dwv, ws, (cudaStream_t)stream);
 }
 
+size_t ocrl_kv_proj_bwd_lowrank_workspace(const ocrl_sa_dims* d) {
+  if (check_dims(d)) return 0;
+  return kv_proj_bwd_lowrank_workspace(d);
+}
+
+int ocrl_kv_proj_bwd_lowrank(const ocrl_sa_dims* d, const float* x, const ocrl_token_weights* w, const void* saved,
+                             const void* iter_bwd_workspace, float* dx, float* d_ln_w, float* d_ln_b, float* dwk,
+                             float* dwv, void* ws, void* stream) {
+  int rc = check_dims(d);
+  if (rc) return rc;
+  if ((rc = check_arch())) return rc;
+  if (!x || !w || !saved || !iter_bwd_workspace || !dx || !d_ln_w || !d_ln_b || !dwk || !dwv || !ws) {
+    set_error("kv_proj_bwd_lowrank: null pointer");
+    return OCRL_E_ALIGN;
+  }
+  if (!aligned16(x) || !aligned16(dx) || !aligned16(ws) || !aligned16(iter_bwd_workspace)) {
+    set_error("kv_proj_bwd_lowrank: pointers must be 16-byte aligned");
+    return OCRL_E_ALIGN;
+  }
+  if (d->B == 0) return OCRL_OK;
+  return kv_proj_bwd_lowrank_launch(d, x, w, reinterpret_cast<const float*>(saved), iter_bwd_workspace, dx, d_ln_w,
+                                    d_ln_b, dwk, dwv, ws, (cudaStream_t)stream);
+}
+
 const char* ocrl_sa_last_kernel(void) { return sa_iter_last_kernel(); }
 
 int ocrl_sa_iter_fwd(const ocrl_sa_dims* d, const void* k, const void* v, const float* slots0,
@@ -211,8 +239,8 @@ int ocrl_sa_iter_bwd(const ocrl_sa_dims* d, const void* k, const void* v, const 
   int rc = check_dims(d);
   if (rc) return rc;
   if ((rc = check_arch())) return rc;
-  if (!k || !v || !saved || !w || !d_slots || !dk || !dv || !d_slots0 || !dw) {
-    set_error("sa_iter_bwd: null pointer");
+  if (!k || !v || !saved || !w || !d_slots || ((dk == nullptr) != (dv == nullptr)) || !d_slots0 || !dw || !workspace) {
+    set_error("sa_iter_bwd: null pointer (dk and dv may be NULL together)");
     return OCRL_E_ALIGN;
   }
   if (!aligned16(k) || !aligned16(v) || !aligned16(dk) || !aligned16(dv) || !aligned16(workspace)) {

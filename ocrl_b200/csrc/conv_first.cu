@@ -24,8 +24,11 @@ constexpr int NW = 8;        // warps per CTA
 constexpr int RB = 4;        // output rows per staging step (RB + 4 input rows are staged)
 constexpr int XP = 8;        // left margin (elements) of a staged row: x = -2 sits at XP - 2, 16-byte aligned rows
 
-template <int C>
-__global__ void __launch_bounds__(NW * 32, 2) conv_first_kernel(const float* __restrict__ obs, const float* __restrict__ w,
+// U8: the frames are uint8 HWC [B,H,W,C] as the HDF5 datasets / environments deliver them (utils/datasets.py:17); the
+// kernel applies the reference's own ingest `obs / 255.0` (fp32 division) while staging, so the result is bit-identical
+// to feeding the float CHW tensor and the frames cross PCIe / NVLink at a quarter of the bytes.
+template <int C, bool U8>
+__global__ void __launch_bounds__(NW * 32, 2) conv_first_kernel(const void* __restrict__ obs_any, const float* __restrict__ w,
                                                                 const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
                                                                 int B, int H, int W, int padded) {
   static_assert(C * KS * KS <= KT * 16, "taps must fit the padded K");
@@ -36,6 +39,8 @@ __global__ void __launch_bounds__(NW * 32, 2) conv_first_kernel(const float* __r
   __nv_bfloat16* rows = reinterpret_cast<__nv_bfloat16*>(bfrag + KT * (CO / 8) * 32);  // [C][NR][RP]
   __nv_bfloat16* stage = rows + C * NR * RP;                                 // [NW][16][CO + 8] output staging
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g8 = lane >> 2, t4 = lane & 3;
+  const float* obs = reinterpret_cast<const float*>(obs_any);
+  const unsigned char* obs8 = reinterpret_cast<const unsigned char*>(obs_any);
 
   // ---- B fragments of the weights, once per CTA: B[k][n] = W[n][c][dy][dx], k = (c*5 + dy)*5 + dx, zero for k >= C*25
   for (int i = tid; i < KT * (CO / 8) * 32; i += NW * 32) {
@@ -95,12 +100,28 @@ __global__ void __launch_bounds__(NW * 32, 2) conv_first_kernel(const float* __r
     const int b = blk / yblocks, y0 = (blk % yblocks) * RB;
     __syncthreads();  // the previous block's readers are done with `rows`
     // ---- stage C planes x NR input rows (zero outside the image), fp32 -> bf16, 16-byte global loads
-    for (int i = tid; i < C * NR * W4; i += NW * 32) {
-      const int x4 = i % W4, p = i / W4;
-      const int c = p / NR, yy = y0 + p % NR - 2;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (yy >= 0 && yy < H) v = __ldg(reinterpret_cast<const float4*>(obs + ((size_t)(b * C + c) * H + yy) * W) + x4);
-      *reinterpret_cast<uint2*>(rows + p * RP + XP + 4 * x4) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    if (!U8) {
+      for (int i = tid; i < C * NR * W4; i += NW * 32) {
+        const int x4 = i % W4, p = i / W4;
+        const int c = p / NR, yy = y0 + p % NR - 2;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (yy >= 0 && yy < H) v = __ldg(reinterpret_cast<const float4*>(obs + ((size_t)(b * C + c) * H + yy) * W) + x4);
+        *reinterpret_cast<uint2*>(rows + p * RP + XP + 4 * x4) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+      }
+    } else {
+      // a frame row is W*C contiguous bytes (W a multiple of 16: whole 32-bit words); byte e of the row belongs to
+      // pixel e / C, plane e % C
+      const int words = W * C / 4;
+      for (int i = tid; i < NR * words; i += NW * 32) {
+        const int wd = i % words, r = i / words, yy = y0 + r - 2;
+        uint32_t v = 0u;
+        if (yy >= 0 && yy < H) v = __ldg(reinterpret_cast<const uint32_t*>(obs8 + ((size_t)b * H + yy) * W * C) + wd);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int e = 4 * wd + q, x = e / C, c = e % C;
+          rows[(c * NR + r) * RP + XP + x] = __float2bfloat16_rn(__fdiv_rn((float)((v >> (8 * q)) & 0xffu), 255.0f));
+        }
+      }
     }
     __syncthreads();
     for (int tile = warp; tile < RB * tiles_x; tile += NW) {
@@ -157,8 +178,8 @@ __global__ void __launch_bounds__(NW * 32, 2) conv_first_kernel(const float* __r
 
 using namespace ocrl;
 
-static int conv_first_launch(const float* obs, const float* weight, const float* bias, void* out, int B, int C, int H, int W,
-                             int CO, int padded, void* stream) {
+static int conv_first_launch(const void* obs, const float* weight, const float* bias, void* out, int B, int C, int H, int W,
+                             int CO, int padded, void* stream, bool u8 = false) {
   if (!obs || !weight || !bias || !out || (reinterpret_cast<uintptr_t>(out) & 15u)) {
     set_error("conv_first: null or unaligned pointer");
     return OCRL_E_ALIGN;
@@ -172,7 +193,7 @@ static int conv_first_launch(const float* obs, const float* weight, const float*
   constexpr int NR = conv1::RB + conv1::KS - 1;
   const size_t smem = sizeof(uint2) * conv1::KT * (conv1::CO / 8) * 32 +
                       sizeof(__nv_bfloat16) * ((size_t)C * NR * RP + conv1::NW * 16 * (conv1::CO + 8));
-  auto kern = conv1::conv_first_kernel<3>;
+  auto kern = u8 ? conv1::conv_first_kernel<3, true> : conv1::conv_first_kernel<3, false>;
   if (smem > 48 * 1024) OCRL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nblocks = B * ((H + conv1::RB - 1) / conv1::RB);
   const int grid = nblocks < 148 * 2 ? nblocks : 148 * 2;  // one wave at 2 CTAs (16 warps) per SM; the weight fragments are built once per CTA
@@ -190,4 +211,8 @@ extern "C" int ocrl_conv_first_relu_bf16(const float* obs, const float* weight, 
 extern "C" int ocrl_conv_first_relu_bf16p(const float* obs, const float* weight, const float* bias, void* out_padded, int B,
                                           int C, int H, int W, int CO, void* stream) {
   return conv_first_launch(obs, weight, bias, out_padded, B, C, H, W, CO, 1, stream);
+}
+extern "C" int ocrl_conv_first_relu_u8p(const unsigned char* frames_hwc, const float* weight, const float* bias,
+                                        void* out_padded, int B, int C, int H, int W, int CO, void* stream) {
+  return conv_first_launch(frames_hwc, weight, bias, out_padded, B, C, H, W, CO, 1, stream, true);
 }

@@ -52,8 +52,16 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int nc
                                        float* o_lmw, float* o_lmb, int D, int H) {
   const WGradLayout WG(D, H);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int c = 0; c < ncopies; ++c) s += partial[(size_t)c * total + i];
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // four loads in flight; the order of the sum is still fixed
+    int c = 0;
+    for (; c + 3 < ncopies; c += 4) {
+      s0 += partial[(size_t)c * total + i];
+      s1 += partial[(size_t)(c + 1) * total + i];
+      s2 += partial[(size_t)(c + 2) * total + i];
+      s3 += partial[(size_t)(c + 3) * total + i];
+    }
+    for (; c < ncopies; ++c) s0 += partial[(size_t)c * total + i];
+    const float s = (s0 + s1) + (s2 + s3);
     float* dst;
     int off;
     if (i < WG.w_ih()) { dst = o_wq; off = WG.wq(); }
@@ -108,6 +116,13 @@ static BwdWorkspace bwd_ws_layout(const ocrl_sa_dims* d) {
 
 size_t sa_iter_bwd_workspace(const ocrl_sa_dims* d) { return bwd_ws_layout(d).total; }
 
+// where the coefficients and dU / S live inside the workspace (read by the low-rank projection backward)
+void sa_iter_bwd_ws_offsets(const ocrl_sa_dims* d, size_t* coef_off, size_t* gm_off) {
+  const BwdWorkspace L = bwd_ws_layout(d);
+  *coef_off = L.coef_off;
+  *gm_off = L.gm_off;
+}
+
 int sa_iter_bwd_launch(const ocrl_sa_dims* d, const void* k, const void* v, const float* saved,
                        const ocrl_sa_weights* w, const float* d_slots, const float* d_attn, float* dk, float* dv,
                        float* d_slots0, const ocrl_sa_weight_grads* dw, void* ws, cudaStream_t stream) {
@@ -129,6 +144,7 @@ int sa_iter_bwd_launch(const ocrl_sa_dims* d, const void* k, const void* v, cons
   if (rc) return rc;
   const long long tokens = (long long)d->B * d->N;
   const int blocks = (int)((tokens + 7) / 8 < 148 * 8 ? (tokens + 7) / 8 : 148 * 8);
+  if (dk != nullptr && dv != nullptr)  // (NULL: the caller takes the coefficients themselves, ocrl_kv_proj_bwd_lowrank)
   switch (d->D) {
     case 64: expand_coef_kernel<64><<<blocks, 256, 0, stream>>>(a.coef, saved, a.gm, dk, dv, d->B, d->N, d->K, d->H_mlp, d->T); ocrl::count_launch(); break;
     case 128: expand_coef_kernel<128><<<blocks, 256, 0, stream>>>(a.coef, saved, a.gm, dk, dv, d->B, d->N, d->K, d->H_mlp, d->T); ocrl::count_launch(); break;

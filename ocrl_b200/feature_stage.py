@@ -27,6 +27,16 @@ class SlotAttnCNNEncoder(nn.Module):
         return self._encoder(obs)
 
 
+def is_u8_frames(obs) -> bool:
+    """uint8 HWC frames [B,H,W,3] as the datasets / environments hold them (utils/datasets.py:17)."""
+    return obs.dtype == torch.uint8 and obs.dim() == 4 and obs.shape[-1] == 3
+
+
+def frames_to_obs(frames):
+    """The reference's ingest (utils/datasets.py:17): uint8 HWC -> float CHW in [0, 1]."""
+    return frames.permute(0, 3, 1, 2).float() / 255.0
+
+
 class PaddedMap:
     """A bf16 feature map in the padded channels-last layout of ocrl_conv5x5_c64_tc (include/ocrl_sa.h):
     ``data`` is the flat position array [(2 + B (H + 2)) (W + 4), 64]."""
@@ -102,10 +112,13 @@ class FusedBf16Encoder:
         return self._packed
 
     def _own_path_ok(self, obs):
-        B, C, H, W = obs.shape
+        if is_u8_frames(obs):
+            B, H, W, C = obs.shape
+        else:
+            B, C, H, W = obs.shape
         hidden = [self._enc._encoder[i].m for i in range(3)] + [self._enc._encoder[3]]
         return (self._convs == "ocrl" and C == 3 and W in (32, 64, 128) and (H * W) % 128 == 0
-                and obs.dtype == torch.float32 and obs.is_contiguous()
+                and (obs.dtype == torch.float32 or is_u8_frames(obs)) and obs.is_contiguous()
                 and all(tuple(c.weight.shape[2:]) == (5, 5) and c.weight.shape[0] == 64 for c in hidden)
                 and all(c.weight.shape[1] == 64 for c in hidden[1:]))
 
@@ -117,14 +130,18 @@ class FusedBf16Encoder:
         from . import abi
 
         L = abi.lib()
-        B, C, H, W = obs.shape
+        u8 = is_u8_frames(obs)
+        if u8:
+            B, H, W, C = obs.shape
+        else:
+            B, C, H, W = obs.shape
         nbytes = L.ocrl_conv_padded_bytes(B, H, W)
         bufs = [torch.empty(nbytes // 128, 64, device=obs.device, dtype=torch.bfloat16) for _ in range(2)]
         pk = self._packed_weights()
         st = abi.stream_ptr()
-        abi.check(L.ocrl_conv_first_relu_bf16p(abi.ptr(obs), abi.ptr(self._w0_f32), abi.ptr(self._b[0]),
-                                               ctypes.c_void_p(bufs[0].data_ptr()), B, C, H, W, 64, st),
-                  "ocrl_conv_first_relu_bf16p")
+        first = L.ocrl_conv_first_relu_u8p if u8 else L.ocrl_conv_first_relu_bf16p  # uint8 HWC frames: `/ 255` on the way in
+        abi.check(first(abi.ptr(obs), abi.ptr(self._w0_f32), abi.ptr(self._b[0]),
+                        ctypes.c_void_p(bufs[0].data_ptr()), B, C, H, W, 64, st), "ocrl_conv_first_relu")
         src = 0
         for i in range(3):  # layers 2, 3 (bias + ReLU) and 4 (bias rides on the position table, no ReLU)
             last = i == 2
@@ -149,6 +166,8 @@ class FusedBf16Encoder:
         self._refresh()
         if self._own_path_ok(obs):
             return self._own_path(obs)
+        if is_u8_frames(obs):
+            obs = frames_to_obs(obs)
         B, C, H, W = obs.shape
         cin = self._w[0].shape[1]
         use_cudnn_epilogue = os.environ.get("OCRL_CONV_EPILOGUE", "cudnn") == "cudnn"

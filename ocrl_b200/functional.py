@@ -28,6 +28,9 @@ SA_PARAM_ORDER = [
 
 _KV_DTYPES = {"fp32": (abi.DT_F32, torch.float32), "bf16": (abi.DT_BF16, torch.bfloat16)}
 
+# The projection backward from the low-rank coefficients (ocrl_kv_proj_bwd_lowrank); False: dk, dv + ocrl_kv_proj_bwd
+LOWRANK_BWD = True
+
 # When set to a list, every C-ABI launch appends (name, start_event, end_event) recorded on the
 # launching stream; bench.py uses it to time the kernels live inside the step.
 KERNEL_EVENTS = None
@@ -265,8 +268,11 @@ class SlotAttentionFunction(torch.autograd.Function):
         if B == 0:  # an empty shard (uneven dp.shard): the kernels do not run, every gradient is exactly zero
             return (torch.zeros_like(inputs), torch.zeros(0, K, D, device=dev), None, None, None,
                     *[torch.zeros_like(p[n]) for n in SA_PARAM_ORDER])
-        dk = torch.empty(B, N, D, device=dev, dtype=torch.float32)
-        dv = torch.empty(B, N, D, device=dev, dtype=torch.float32)
+        # the projection backward works straight from the rank-(2 T K) coefficients of the iteration backward
+        # (dk, dv [B,N,D] fp32 are never written); LOWRANK_BWD = False keeps the two-step form for cross-checks
+        lowrank = LOWRANK_BWD and C == 64 and 2 * T * K <= 224
+        dk = None if lowrank else torch.empty(B, N, D, device=dev, dtype=torch.float32)
+        dv = None if lowrank else torch.empty(B, N, D, device=dev, dtype=torch.float32)
         d_slots0 = torch.empty(B, K, D, device=dev, dtype=torch.float32)
         g = {n: torch.empty_like(p[n]) for n in SA_PARAM_ORDER}
         dw = abi.sa_weight_grads(
@@ -284,10 +290,20 @@ class SlotAttentionFunction(torch.autograd.Function):
                                          abi.ptr(d_slots0), ctypes.byref(dw), abi.ptr(ws), abi.stream_ptr()),
                       "ocrl_sa_iter_bwd")
         # norm_inputs + project_k / project_v
-        ws2 = torch.empty(max(L.ocrl_kv_proj_bwd_workspace(ctypes.byref(dims)), 16), device=dev, dtype=torch.uint8)
         dx = torch.empty_like(inputs)
         tw = abi.token_weights(in_ln_w=p["norm_inputs.weight"], in_ln_b=p["norm_inputs.bias"],
                                wk=p["project_k.weight"], wv=p["project_v.weight"])
+        if lowrank:
+            ws2 = torch.empty(max(L.ocrl_kv_proj_bwd_lowrank_workspace(ctypes.byref(dims)), 16), device=dev,
+                              dtype=torch.uint8)
+            with _timed("kv_proj_bwd"):
+                abi.check(L.ocrl_kv_proj_bwd_lowrank(ctypes.byref(dims), abi.ptr(inputs), ctypes.byref(tw),
+                                                     abi.ptr(saved), abi.ptr(ws), abi.ptr(dx),
+                                                     abi.ptr(g["norm_inputs.weight"]), abi.ptr(g["norm_inputs.bias"]),
+                                                     abi.ptr(g["project_k.weight"]), abi.ptr(g["project_v.weight"]),
+                                                     abi.ptr(ws2), abi.stream_ptr()), "ocrl_kv_proj_bwd_lowrank")
+            return (dx, d_slots0, None, None, None, *[g[n] for n in SA_PARAM_ORDER])
+        ws2 = torch.empty(max(L.ocrl_kv_proj_bwd_workspace(ctypes.byref(dims)), 16), device=dev, dtype=torch.uint8)
         with _timed("kv_proj_bwd"):
             abi.check(L.ocrl_kv_proj_bwd(ctypes.byref(dims), abi.ptr(inputs), ctypes.byref(tw), abi.ptr(dk),
                                          abi.ptr(dv), abi.ptr(dx), abi.ptr(g["norm_inputs.weight"]),

@@ -17,7 +17,8 @@ from torch import nn
 
 from .adjacent import (BosToken, BroadCastDecoder, LearnedPositionalEncoding, OneHotDictionary,
                        TransformerDecoder, cosine_anneal, dVAE, gumbel_softmax)
-from .feature_stage import FusedBf16Encoder, PositionalEmbedding, SlotAttnCNNEncoder
+from .feature_stage import (FusedBf16Encoder, PositionalEmbedding, SlotAttnCNNEncoder, frames_to_obs,
+                            is_u8_frames)
 from .networks import linear
 from .slot_attn import SlotAttentionEncoder
 
@@ -152,6 +153,10 @@ class SLATE_Module(nn.Module):
         return cached[1]
 
     def _slot_attention(self, obs):
+        u8 = is_u8_frames(obs)  # uint8 HWC frames (utils/datasets.py:17): only the all-hand-written bf16 path ingests them
+        if u8 and (self._hot_needs_grad(obs) or self._conv_mode() != "bf16"
+                   or os.environ.get("OCRL_CONV_FUSED", "1") == "0"):
+            obs = frames_to_obs(obs)
         if not self._hot_needs_grad(obs):
             # inference: position add + (transpose) + token MLP + projections fused into one kernel
             with torch.no_grad():
@@ -202,12 +207,15 @@ class SLATE_Module(nn.Module):
         return self._dvae.decode(z_gen)
 
     def _attn_maps(self, attns, obs, num_slots):
-        return attns.transpose(-1, -2).reshape(obs.shape[0], num_slots, 1, obs.shape[2], obs.shape[3])
+        h, w = (obs.shape[1], obs.shape[2]) if is_u8_frames(obs) else (obs.shape[2], obs.shape[3])
+        return attns.transpose(-1, -2).reshape(obs.shape[0], num_slots, 1, h, w)
 
     def forward(self, obs, with_attns=False, with_masks=False):
         assert not (with_attns and with_masks)  # one of attns and masks can be returned
         if self._use_cnn_feat:
             return img_to_slot(torch.cat([self._enc_pos(self._enc(obs)), obs], dim=1))
+        if is_u8_frames(obs) and (self._use_cnn_feat or with_attns):
+            obs = frames_to_obs(obs)  # these outputs contain the float frames themselves
         if with_attns or with_masks:
             slots, attns = self._get_slots(obs, with_attns=True)
             attns = self._attn_maps(attns, obs, slots.shape[1])

@@ -78,3 +78,31 @@ def test_hand_written_feature_stage_matches_oracle_cnn(size, B):
     # and the library path of the same object agrees
     lib_map = FusedBf16Encoder(enc, convs="cudnn")(obs)
     assert rel_err(fm.to_nchw().float().cpu(), lib_map.float().cpu()) < 2e-2
+
+
+@pytest.mark.parametrize("size,B", [(64, 5), (32, 2), (128, 1)])
+def test_uint8_hwc_frames_are_ingested_bit_exactly(size, B):
+    """uint8 HWC frames (utils/datasets.py:17) through ocrl_conv_first_relu_u8p: the `/ 255.0` of the reference's ingest
+    happens inside the first convolution, bit-identical to feeding the converted float CHW tensor -- feature map, slots
+    and masks (SLATE.__call__ takes the frames as they are in the bf16 mode)."""
+    import ocrl_b200
+    from ocrl_b200 import synth
+    from ocrl_b200.config import slate_config
+    from ocrl_b200.feature_stage import FusedBf16Encoder, frames_to_obs
+
+    torch.manual_seed(5)
+    model = ocrl_b200.SLATE(*slate_config(obs_size=size, kv_dtype="bf16"))
+    model.to("cuda")
+    model.eval()
+    frames = torch.from_numpy(synth.random_objs_frames(B, size, seed=3)).cuda()  # [B,H,W,3] uint8
+    assert frames.dtype == torch.uint8 and frames.shape == (B, size, size, 3)
+    fast = FusedBf16Encoder(model._module._enc, convs="ocrl")
+    a = fast(frames)
+    b = fast(frames_to_obs(frames).contiguous())
+    assert torch.equal(a.data, b.data)
+    with torch.no_grad():
+        torch.manual_seed(9)
+        s8, m8 = model(frames, with_masks=True)
+        torch.manual_seed(9)
+        sf, mf = model(frames_to_obs(frames).contiguous(), with_masks=True)
+    assert torch.equal(s8, sf) and torch.equal(m8, mf) and m8.shape == (B, 6, 1, size, size)
