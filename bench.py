@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--no-train", action="store_true", help="skip the short SLATE training-step measurement")
     ap.add_argument("--pool", type=int, default=512, help="distinct frames in the synthetic pool")
     ap.add_argument("--sustain", type=float, default=1.2, help="seconds of the extra sustained run (0: skip)")
+    ap.add_argument("--sweep", action="store_true",
+                    help="BASELINE.json config 5: the iteration kernel over N x K x T (one JSON line per shape, this GPU)")
     return ap.parse_args()
 
 
@@ -291,8 +293,9 @@ def measure(a, mode, steps, warmup, dev, dist, rank, world, pool_host, pool_dev,
         # value: frames already resident in HBM, slots left in HBM.  e2e: every step copies its frames from pinned host
         # memory and its slots back to pinned host memory, copies overlapping the replays.
         nbuf = int(os.environ.get("OCRL_BENCH_BUFFERS", 3))
-        icl = os.environ.get("OCRL_BENCH_ITER_CLUSTERS")  # experiment knob; the bench line is the default (None)
-        streamed = ocrl_b200.StreamedEncoder(model, batch_dev(0), buffers=nbuf, iter_clusters=int(icl) if icl else None)
+        icl = os.environ.get("OCRL_BENCH_ITER_CLUSTERS")  # experiment knob (0: launcher's choice); the bench line is the API default
+        streamed = ocrl_b200.StreamedEncoder(model, batch_dev(0), buffers=nbuf,
+                                             iter_clusters="auto" if icl is None else (int(icl) or None))
         outs_host = [torch.empty_like(out_host).pin_memory() for _ in range(nbuf)]
         outs_dev = [torch.empty(a.batch, a.slots, a.slot_size, device=dev) for _ in range(nbuf)]
 
@@ -455,6 +458,49 @@ def roofline_of(a, mode, events):
                             "algorithmic_bytes_per_image": tok_bytes_img}}
 
 
+def run_sweep(a, dev, out):
+    """BASELINE.json config 5: the fused iteration kernel alone over N in {4096, 16384} x K in {6, 8, 11, 16} x
+    T in {3, 5, 7}, bf16 k/v, D = H = 192: CUDA-event time of back-to-back launches on inputs larger than the L2,
+    algorithmic bytes per image of SURVEY 8(d), which kernel the dispatcher chose.  The path shards by image with no
+    collective, so N GPUs run N copies of each line (weak scaling, see the N-GPU bench lines)."""
+    from ocrl_b200 import abi, functional as F
+    from oracle import slot_oracle as so
+
+    peak = HBM_FALLBACK_GBS
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak = float(json.load(f)["hbm_gbs"])
+    except Exception:
+        pass
+    D = a.slot_size
+    for N in (4096, 16384):
+        B = 64 if N == 4096 else 16
+        x = torch.randn(B, N, 64, device=dev)
+        for K in (6, 8, 11, 16):
+            p = {k: v.to(dev) for k, v in so.random_sa_params(K, 64, D, D, seed=3).items()}
+            k, v, _ = F.kv_project(x, p, kv="bf16")
+            s0 = torch.randn(B, K, D, device=dev)
+            for T in (3, 5, 7):
+                prep = F.PreparedWeights()
+                for _ in range(3):
+                    F.iterate(k, v, s0, p, T, prepared=prep)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                reps = 10
+                e0.record()
+                for _ in range(reps):
+                    F.iterate(k, v, s0, p, T, prepared=prep)
+                e1.record()
+                torch.cuda.synchronize()
+                us = e0.elapsed_time(e1) / reps * 1e3
+                bytes_img = 2 * N * D * 2 + N * K * 4 + 2 * K * D * 4
+                gbs = B * bytes_img / us / 1e3
+                print(json.dumps({"sweep": "iteration kernel", "N": N, "K": K, "T": T, "D": D, "B": B, "kernel": F.last_kernel(),
+                                  "us": round(us, 1), "images_per_s": round(B / us * 1e6), "GBps": round(gbs, 1),
+                                  "frac_of_hbm": round(gbs / peak, 4), "streamed_GBps": round(T * B * 2 * N * D * 2 / us / 1e3, 1),
+                                  "algorithmic_bytes_per_image": bytes_img}), file=out, flush=True)
+
+
 def _claim_stdout():
     """The contract is ONE JSON line on stdout.  Native libraries (NCCL prints its version banner with C stdio)
     write to file descriptor 1 too, so fd 1 is pointed at stderr and the JSON line goes to a private duplicate."""
@@ -485,6 +531,13 @@ def main():
 
     from ocrl_b200 import synth
 
+    if a.sweep:
+        if rank == 0:
+            run_sweep(a, dev, out)
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     # each rank owns its own shard of the frame pool (no data-path collective: images are independent)
     pool_u8 = torch.from_numpy(synth.random_objs_frames(a.pool, a.size, seed=1000 + rank))
     pool_host = synth.to_obs(pool_u8).contiguous().pin_memory()  # float32 CHW in [0,1], as the reference API takes

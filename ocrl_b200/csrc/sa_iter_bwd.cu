@@ -1,4 +1,4 @@
-// Host entry of the fused iteration backward + the small expansion / reduction kernels
+// Host entry of the fused iteration backward + the small expansion kernel (weight gradients: sa_iter_wgrad.cu)
 // (the cluster kernel is instantiated in sa_iter_bwd_{f32,bf16}.cu)
 #include "sa_iter_bwd.cuh"
 
@@ -45,46 +45,13 @@ __global__ void __launch_bounds__(256) expand_coef_kernel(const float* __restric
   }
 }
 
-// out[i] = sum_c partial[c][i]  (deterministic reduction of the per-cluster weight gradients)
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, int ncopies, int total, float* o_wq,
-                                       float* o_wih, float* o_whh, float* o_bih, float* o_bhh, float* o_w1,
-                                       float* o_b1, float* o_w2, float* o_b2, float* o_lsw, float* o_lsb,
-                                       float* o_lmw, float* o_lmb, int D, int H) {
-  const WGradLayout WG(D, H);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // four loads in flight; the order of the sum is still fixed
-    int c = 0;
-    for (; c + 3 < ncopies; c += 4) {
-      s0 += partial[(size_t)c * total + i];
-      s1 += partial[(size_t)(c + 1) * total + i];
-      s2 += partial[(size_t)(c + 2) * total + i];
-      s3 += partial[(size_t)(c + 3) * total + i];
-    }
-    for (; c < ncopies; ++c) s0 += partial[(size_t)c * total + i];
-    const float s = (s0 + s1) + (s2 + s3);
-    float* dst;
-    int off;
-    if (i < WG.w_ih()) { dst = o_wq; off = WG.wq(); }
-    else if (i < WG.w_hh()) { dst = o_wih; off = WG.w_ih(); }
-    else if (i < WG.b_ih()) { dst = o_whh; off = WG.w_hh(); }
-    else if (i < WG.b_hh()) { dst = o_bih; off = WG.b_ih(); }
-    else if (i < WG.w1()) { dst = o_bhh; off = WG.b_hh(); }
-    else if (i < WG.b1()) { dst = o_w1; off = WG.w1(); }
-    else if (i < WG.w2()) { dst = o_b1; off = WG.b1(); }
-    else if (i < WG.b2()) { dst = o_w2; off = WG.w2(); }
-    else if (i < WG.ln_s_w()) { dst = o_b2; off = WG.b2(); }
-    else if (i < WG.ln_s_b()) { dst = o_lsw; off = WG.ln_s_w(); }
-    else if (i < WG.ln_m_w()) { dst = o_lsb; off = WG.ln_s_b(); }
-    else if (i < WG.ln_m_b()) { dst = o_lmw; off = WG.ln_m_w(); }
-    else { dst = o_lmb; off = WG.ln_m_b(); }
-    dst[i - off] = s;
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 int sa_iter_pick_cluster(const ocrl_sa_dims* d);
+size_t sa_iter_wgrad_part_floats(const ocrl_sa_dims* d);
+int sa_iter_wgrad_launch(const ocrl_sa_dims* d, const float* flog, const float* saved, float* part,
+                         const ocrl_sa_weight_grads* dw, cudaStream_t stream);
 
 static int bwd_num_clusters(const ocrl_sa_dims* d, int CL) {
   int dev = 0, sms = 148;
@@ -99,18 +66,18 @@ static int bwd_num_clusters(const ocrl_sa_dims* d, int CL) {
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct BwdWorkspace {
-  size_t coef_off, gm_off, wgrad_off, total;
+  size_t coef_off, gm_off, flog_off, part_off, total;
 };
 static BwdWorkspace bwd_ws_layout(const ocrl_sa_dims* d) {
-  const int max_clusters = bwd_num_clusters(d, sa_iter_pick_cluster(d));
   BwdWorkspace w;
   w.coef_off = 0;
   size_t coef = sizeof(float) * (size_t)d->B * d->N * d->T * 2 * d->K;
   w.gm_off = align_up(coef, 256);
   size_t gm = sizeof(float) * (size_t)d->B * d->T * d->K * d->D;
-  w.wgrad_off = align_up(w.gm_off + gm, 256);
-  size_t wg = sizeof(float) * (size_t)max_clusters * WGradLayout(d->D, d->H_mlp).total();
-  w.total = align_up(w.wgrad_off + wg, 256);
+  w.flog_off = align_up(w.gm_off + gm, 256);
+  size_t fl = sizeof(float) * (size_t)d->B * d->T * FLog(d->K, d->D, d->H_mlp).stride();
+  w.part_off = align_up(w.flog_off + fl, 256);
+  w.total = align_up(w.part_off + sizeof(float) * sa_iter_wgrad_part_floats(d), 256);
   return w;
 }
 
@@ -132,14 +99,12 @@ int sa_iter_bwd_launch(const ocrl_sa_dims* d, const void* k, const void* v, cons
   a.k = k; a.v = v; a.saved = saved; a.w = *w; a.d_slots = d_slots; a.d_attn = d_attn;
   a.coef = reinterpret_cast<float*>(base + L.coef_off);
   a.gm = reinterpret_cast<float*>(base + L.gm_off);
-  a.wgrad = reinterpret_cast<float*>(base + L.wgrad_off);
+  a.flog = reinterpret_cast<float*>(base + L.flog_off);
   a.d_slots0 = d_slots0;
   a.B = d->B; a.N = d->N; a.D = d->D; a.H = d->H_mlp; a.K = d->K; a.T = d->T;
   a.eps = d->eps; a.ln_eps = d->ln_eps;
   a.CL = sa_iter_pick_cluster(d);
   a.NCL = bwd_num_clusters(d, a.CL);
-  const WGradLayout WG(d->D, d->H_mlp);
-  OCRL_CHECK_CUDA(cudaMemsetAsync(a.wgrad, 0, sizeof(float) * (size_t)a.NCL * WG.total(), stream));
   int rc = (d->kv_dtype == OCRL_DT_F32) ? sa_iter_bwd_dispatch<float>(a, stream) : sa_iter_bwd_dispatch<__nv_bfloat16>(a, stream);
   if (rc) return rc;
   const long long tokens = (long long)d->B * d->N;
@@ -151,12 +116,7 @@ int sa_iter_bwd_launch(const ocrl_sa_dims* d, const void* k, const void* v, cons
     default: expand_coef_kernel<192><<<blocks, 256, 0, stream>>>(a.coef, saved, a.gm, dk, dv, d->B, d->N, d->K, d->H_mlp, d->T); ocrl::count_launch(); break;
   }
   OCRL_CHECK_CUDA(cudaGetLastError());
-  reduce_partials_kernel<<<148, 256, 0, stream>>>(a.wgrad, a.NCL, WG.total(), dw->wq, dw->w_ih, dw->w_hh, dw->b_ih,
-                                                  dw->b_hh, dw->w1, dw->b1, dw->w2, dw->b2, dw->ln_slots_w,
-                                                  dw->ln_slots_b, dw->ln_mlp_w, dw->ln_mlp_b, d->D, d->H_mlp);
-  ocrl::count_launch();
-  OCRL_CHECK_CUDA(cudaGetLastError());
-  return OCRL_OK;
+  return sa_iter_wgrad_launch(d, a.flog, saved, reinterpret_cast<float*>(base + L.part_off), dw, stream);
 }
 
 }  // namespace ocrl

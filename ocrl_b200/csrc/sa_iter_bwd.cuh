@@ -35,6 +35,22 @@ struct WGradLayout {  // flat per-cluster partial weight-gradient buffer (floats
   __host__ __device__ int total() const { return ln_m_b() + D; }
 };
 
+// Per (image, iteration) record of the factors of the weight gradients.  Every weight gradient of the loop is a sum of
+// K-row outer products per image and iteration (dW2 = dsn^T y, dW1 = dpre^T mhat, dW_ih = dgate_i^T u, dW_hh = dgate_h^T h,
+// dWq = dq^T shat), so the cluster kernel only records the row / column factors it has in shared memory anyway and a
+// split-K product over all B T K rows forms the gradients once at the end (sa_iter_wgrad.cu) -- instead of a
+// read-modify-write of 1.3 MB of partial gradients through the L2 per image and iteration.  u, h and the MLP
+// pre-activation come from the forward's saved state.
+struct FLog {
+  int K, L;  // L = max(D, H): row pitch
+  __host__ __device__ FLog(int k, int d, int h) : K(k), L(d > h ? d : h) {}
+  enum { DSN = 0, DPRE = 1, DR = 2, DZ = 3, DN = 4, DNR = 5, DQ = 6, MHAT = 7, SHAT = 8, NFACT = 9 };
+  enum { LN_M_W = 0, LN_M_B = 1, LN_S_W = 2, LN_S_B = 3, NVEC = 4 };
+  __host__ __device__ size_t fact(int f) const { return (size_t)f * K * L; }
+  __host__ __device__ size_t vec(int v) const { return (size_t)NFACT * K * L + (size_t)v * L; }
+  __host__ __device__ size_t stride() const { return (size_t)NFACT * K * L + (size_t)NVEC * L; }
+};
+
 struct IterBwdArgs {
   const void* k;
   const void* v;
@@ -45,7 +61,7 @@ struct IterBwdArgs {
   float* coef;          // [B][N][T][2K]
   float* gm;            // [B][T][K][D]   dU_t / S_t
   float* d_slots0;
-  float* wgrad;         // [NCL][WGradLayout::total()], zeroed by the host
+  float* flog;          // [B][T][FLog::stride()] factors of the weight gradients
   int B, N, D, H, K, T, CL, NCL;
   float eps, ln_eps;
 };
@@ -175,8 +191,7 @@ __global__ void __launch_bounds__(BwdCfg<KV, D, KP>::NT, 1) sa_iter_bwd_kernel(c
   const int DS = D / CL, HS = H / CL;
   const int LMAX = D > H ? D : H;
   const SavedLayout SL(K, D, H);
-  const WGradLayout WG(D, H);
-  float* wg = a.wgrad + (size_t)cid * WG.total();
+  const FLog FL(K, D, H);
 
   // ---- shared memory carve-up (must match bwd_smem_bytes) ---------------------------------------
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -271,6 +286,7 @@ __global__ void __launch_bounds__(BwdCfg<KV, D, KP>::NT, 1) sa_iter_bwd_kernel(c
     for (int t = T - 1; t >= 0; --t) {
       const bool last = (t == T - 1);
       const float* sv = a.saved + ((size_t)img * T + t) * SL.stride();
+      float* fl = a.flog + ((size_t)img * T + t) * FL.stride();  // this CTA records its feature slice of every factor
       // ---- load the saved forward state of iteration t (replicated) ----------------------------
       for (int e = tid; e < KP * D; e += NT) {
         const bool ok = e < K * D;
@@ -305,20 +321,20 @@ __global__ void __launch_bounds__(BwdCfg<KV, D, KP>::NT, 1) sa_iter_bwd_kernel(c
       __syncthreads();
       for (int e = tid; e < K * H; e += NT) pre_s[e] = fmaxf(pre_s[e], 0.f);  // y
       __syncthreads();
-      outer_acc<NW>(wg + WG.w2(), H, rank * DS, DS, dsn + rank * DS, D, pre_s, H, H, K, warp, lane);
-      for (int o = tid; o < DS; o += NT) {
-        float s = 0.f;
-        for (int j = 0; j < K; ++j) s += dsn[j * D + rank * DS + o];
-        wg[WG.b2() + rank * DS + o] += s;
+      for (int e = tid; e < K * DS; e += NT) {  // dW2 = dsn^T relu(pre), db2 = column sums of dsn
+        const int j = e / DS, o = e % DS;
+        fl[FL.fact(FLog::DSN) + j * FL.L + rank * DS + o] = dsn[j * D + rank * DS + o];
       }
       // ---- B2: MLP hidden layer.  partial d mhat[k][:] = sum_{j in slice(H)} dpre[k][j] W1[j][:] -
       cols_dot<KP, NW, NT>(a.w.w1, D, rank * HS, HS, dpre, HS, part, D, D, K, red, false, tid);
       rs_push(part, D, DS, rsB);
-      outer_acc<NW>(wg + WG.w1(), D, rank * HS, HS, dpre, HS, mhat, D, D, K, warp, lane);
-      for (int o = tid; o < HS; o += NT) {
-        float s = 0.f;
-        for (int j = 0; j < K; ++j) s += dpre[j * HS + o];
-        wg[WG.b1() + rank * HS + o] += s;
+      for (int e = tid; e < K * HS; e += NT) {  // dW1 = dpre^T mhat, db1 = column sums of dpre
+        const int j = e / HS, o = e % HS;
+        fl[FL.fact(FLog::DPRE) + j * FL.L + rank * HS + o] = dpre[j * HS + o];
+      }
+      for (int e = tid; e < K * DS; e += NT) {
+        const int j = e / DS, o = e % DS;
+        fl[FL.fact(FLog::MHAT) + j * FL.L + rank * DS + o] = mhat[j * D + rank * DS + o];
       }
       cluster.sync();  // E2a
       for (int e = tid; e < K * DS; e += NT) {
@@ -335,8 +351,8 @@ __global__ void __launch_bounds__(BwdCfg<KV, D, KP>::NT, 1) sa_iter_bwd_kernel(c
           gw = fmaf(dyv, (hp_s[j * D + d] - stat_m[2 * j]) * stat_m[2 * j + 1], gw);
           gb += dyv;
         }
-        wg[WG.ln_m_w() + d] += gw;
-        wg[WG.ln_m_b() + d] += gb;
+        fl[FL.vec(FLog::LN_M_W) + d] = gw;
+        fl[FL.vec(FLog::LN_M_B) + d] = gb;
       }
       ln_bwd_rows(hp_s, fullA, stat_m, a.w.ln_mlp_w, dhp, K, D, warp, lane, NW);
       __syncthreads();
@@ -367,20 +383,13 @@ __global__ void __launch_bounds__(BwdCfg<KV, D, KP>::NT, 1) sa_iter_bwd_kernel(c
       }
       rs_push(part, D, DS, rsA);
       rs_push(part2, D, DS, rsB);
-      for (int gsel = 0; gsel < 3; ++gsel) {
-        outer_acc<NW>(wg + WG.w_ih(), D, gsel * D + rank * DS, DS, dgate + (gsel)*KP * DS, DS, u_s, D, D, K, warp, lane);
-        outer_acc<NW>(wg + WG.w_hh(), D, gsel * D + rank * DS, DS, dgate + (3 + gsel) * KP * DS, DS, h_s, D, D, K, warp,
-                      lane);
-      }
-      for (int e = tid; e < 3 * DS; e += NT) {
-        const int gsel = e / DS, o = e % DS;
-        float si = 0.f, sh = 0.f;
-        for (int j = 0; j < K; ++j) {
-          si += dgate[(gsel * KP + j) * DS + o];
-          sh += dgate[((3 + gsel) * KP + j) * DS + o];
-        }
-        wg[WG.b_ih() + gsel * D + rank * DS + o] += si;
-        wg[WG.b_hh() + gsel * D + rank * DS + o] += sh;
+      for (int e = tid; e < K * DS; e += NT) {  // dW_ih = [dr dz dn]^T u, dW_hh = [dr dz dn r]^T h, biases = column sums
+        const int j = e / DS, o = e % DS;
+        const size_t at = (size_t)j * FL.L + rank * DS + o;
+        fl[FL.fact(FLog::DR) + at] = dgate[(0 * KP + j) * DS + o];
+        fl[FL.fact(FLog::DZ) + at] = dgate[(1 * KP + j) * DS + o];
+        fl[FL.fact(FLog::DN) + at] = dgate[(2 * KP + j) * DS + o];
+        fl[FL.fact(FLog::DNR) + at] = dgate[(5 * KP + j) * DS + o];
       }
       cluster.sync();  // E3a
       for (int e = tid; e < K * DS; e += NT) {
@@ -559,7 +568,11 @@ __global__ void __launch_bounds__(BwdCfg<KV, D, KP>::NT, 1) sa_iter_bwd_kernel(c
       // ---- B6: query projection backward -----------------------------------------------------------
       cols_dot<KP, NW, NT>(a.w.wq, D, rank * DS, DS, dq_sl, DS, part, D, D, K, red, false, tid);
       rs_push(part, D, DS, rsB);
-      outer_acc<NW>(wg + WG.wq(), D, rank * DS, DS, dq_sl, DS, shat, D, D, K, warp, lane);
+      for (int e = tid; e < K * DS; e += NT) {  // dWq = dq^T shat
+        const int j = e / DS, o = e % DS;
+        fl[FL.fact(FLog::DQ) + j * FL.L + rank * DS + o] = dq_sl[j * DS + o];
+        fl[FL.fact(FLog::SHAT) + j * FL.L + rank * DS + o] = shat[j * D + rank * DS + o];
+      }
       cluster.sync();  // E5a
       for (int e = tid; e < K * DS; e += NT) {
         const int j = e / DS, o = e % DS;
@@ -575,8 +588,8 @@ __global__ void __launch_bounds__(BwdCfg<KV, D, KP>::NT, 1) sa_iter_bwd_kernel(c
           gw = fmaf(dyv, (h_s[j * D + d] - stat_s[2 * j]) * stat_s[2 * j + 1], gw);
           gb += dyv;
         }
-        wg[WG.ln_s_w() + d] += gw;
-        wg[WG.ln_s_b() + d] += gb;
+        fl[FL.vec(FLog::LN_S_W) + d] = gw;
+        fl[FL.vec(FLog::LN_S_B) + d] = gb;
       }
       ln_bwd_rows(h_s, fullA, stat_s, a.w.ln_slots_w, part, K, D, warp, lane, NW);
       __syncthreads();

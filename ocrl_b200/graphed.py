@@ -88,14 +88,19 @@ class StreamedEncoder:
 
     iter_clusters: clusters of the iteration kernel per replay.  The kernel is latency-bound, so with several replays
     in flight fewer, fuller clusters cost fewer SM-seconds and leave SMs to the neighbours' convolutions: at batch 64
-    eight clusters (8 images each, no tail) give 177.5 k images/s against 169.0 k with the launcher's thirteen, while
-    one replay alone gets 11 % slower and the kernel's own launch goes from 134 to 189 us (profiles/r1/ab_clusters_v9.txt).
-    None (default): the launcher's choice, lowest latency per replay; an integer caps at that count."""
+    six clusters (ten or eleven images each) give 165 k images/s (174 k sustained over a second) against 157 k (163 k)
+    with the launcher's thirteen, while one replay alone gets slower (profiles/r2/stream_cluster_sweep.txt).
+    "auto" (default): one cluster per ten images from batch 48 up when the replays run concurrently, else the launcher's
+    choice; None: always the launcher's choice (lowest latency per replay); an integer caps at that count.  Results do
+    not depend on it (tested)."""
 
     def __init__(self, ocr, example_obs: torch.Tensor, with_masks: bool = False, concurrent_replays: bool = True,
-                 buffers: int = 3, iter_clusters: int | None = None):
+                 buffers: int = 3, iter_clusters: int | str | None = "auto"):
         dev = example_obs.device
         self._nb = buffers
+        if iter_clusters == "auto":
+            batch = example_obs.shape[0]
+            iter_clusters = max(1, batch // 10) if (concurrent_replays and buffers > 1 and batch >= 48) else None
         self.iter_clusters = iter_clusters
         self._enc = [GraphedEncoder(ocr, example_obs, with_masks, iter_clusters=iter_clusters) for _ in range(buffers)]
         # with concurrent_replays the buffers replay on their own streams, so the latency-bound iteration kernel of

@@ -129,7 +129,7 @@ def test_bf16_mode_with_tensor_core_convs(monkeypatch, conv):
 
 
 @pytest.mark.parametrize("kv", ["fp32", "bf16"])
-@pytest.mark.parametrize("iter_clusters", [None, 2, 8])
+@pytest.mark.parametrize("iter_clusters", [None, 2, 8, "auto"])
 def test_streamed_encoder_matches_direct_calls(iter_clusters, kv):
     """StreamedEncoder (double-buffered H2D / graph replay / D2H) returns, batch by batch, what the model returns for
     the same frames and the same slot-initialisation noise -- in the exact-parity mode and in the bf16 mode the
