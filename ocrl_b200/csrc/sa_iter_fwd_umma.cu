@@ -33,6 +33,7 @@ struct Cfg {
   // NL image lanes per cluster; KB rows in the slot-indexed buffers; NKS / NVS ring slots for k / v half tiles;
   // NWB buffers for the softmax weights of a 128-token pair
   static constexpr int D = D_, H = H_, CL = CL_, NL = NL_, KB = KB_, NKS = NKS_, NVS = NVS_, NWB = NWB_;
+  static constexpr int KS = KB > 8 ? 16 : 8;  // slot columns of the tensor-core operands and accumulators (K <= KS)
   // NUS update streams: the eight update warps are split into NUS groups that run the slot updates of different ops
   // concurrently (op n -> stream n % NUS); an update is a chain of exchange rounds, bound by latency, not by work
   static constexpr int NUS = NUS_, UW = 8 / NUS, UT = 32 * UW;
@@ -42,7 +43,7 @@ struct Cfg {
   static constexpr int LX = D > H ? D : H;
   static constexpr int CH_BYTES = HT * 128, HT_BYTES = NCH * CH_BYTES;  // one 64-wide feature chunk / one half tile
   static constexpr int WH_BYTES = 2048, WP_BYTES = 2 * WH_BYTES;        // w tile of a half ([8][16 slots][8] bf16) / a pair
-  static constexpr int OPD_BYTES = D * 16, OPX_BYTES = LX * 16;         // activation operands [features/8][8 slots][8] bf16
+  static constexpr int OPD_BYTES = D * 2 * KS, OPX_BYTES = LX * 2 * KS;  // activation operands [features/8][KS slots][8] bf16
   static constexpr int DS = D / CL, HS = H / CL;
   // weight blocks in tensor memory (row = lane): X = W_ih (3 DS rows) | W1' (HS) | W2 (DS);  Y = W_hh (3 DS) | Wq' (DS)
   static constexpr int RX = 3 * DS + HS + DS, RY = 3 * DS + DS;
@@ -64,8 +65,8 @@ struct Cfg {
   static constexpr int OFF_WT = OFF_VRING + NVS * HT_BYTES;
   static constexpr int OFF_BIAS = OFF_WT + NWB * WP_BYTES;  // (the LayerNorm affine parameters are folded into W1', Wq')
   // fp32 constants: b_ih[3DS] b_hh[3DS] b1'[HS] b2[DS] c1[HS] cq[DS] bq'[DS] + LayerNorm stats mean[8] rstd[8]
-  static constexpr int NCONST = 9 * DS + 2 * HS + 16 * NUS;
-  static constexpr int XBUF_BYTES = KB * D * 4 + 32 * CL;          // R1 receive buffer (fp32 partial sums), single
+  static constexpr int NCONST = 9 * DS + 2 * HS + 32 * NUS;
+  static constexpr int XBUF_BYTES = KB * D * 4 + 4 * KS * CL;      // R1 receive buffer (fp32 partial sums), single
   static constexpr int OFF_XBUF = (OFF_BIAS + NCONST * 4 + 15) & ~15;
   static constexpr int OFF_ACT = (OFF_XBUF + NUS * XBUF_BYTES + 127) & ~127;  // bf16 all-gather targets (operands), by round parity
   static constexpr int OFF_UST = OFF_ACT + NUS * 2 * OPX_BYTES;    // U staging (pass -> update hand-off), one per stream
@@ -73,10 +74,10 @@ struct Cfg {
   static constexpr int OFF_LANE = (OFF_UST + NUS * UST_BYTES + 127) & ~127;  // per lane: q operand, slots operand, own slice (fp32)
   static constexpr int LANE_BYTES = (2 * OPD_BYTES + KB * DS * 4 + 127) & ~127;
   static constexpr int OFF_P = (OFF_LANE + NL * LANE_BYTES + 15) & ~15;   // product outputs, fp32 [2][128 rows][8 slots]
-  static constexpr int OFF_SRED = OFF_P + NUS * 2 * 128 * 32;      // [4][8] token sums of the softmax warps, per stream
+  static constexpr int OFF_SRED = OFF_P + NUS * 2 * 128 * 4 * KS;  // [4][KS] token sums of the softmax warps, per stream
   // k_full k_empty [NKS] v_full v_empty [NVS] lg_full lg_empty w_full w_empty u_full u_accfree [2 each]
   // per stream: xbar[2] u_ready u_free ubar[2];  q_ready[NL]
-  static constexpr int OFF_BAR = OFF_SRED + NUS * 128;
+  static constexpr int OFF_BAR = OFF_SRED + NUS * 16 * KS;
   static constexpr int NBAR = 2 * NKS + 2 * NVS + 12 + 6 * NUS + NL;
   static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
   static constexpr int SMEM_BYTES = OFF_TMEM + 16;
@@ -89,7 +90,7 @@ template <int D, int H, int CL, int NL, int KB, int NKS, int NVS, int NWB, int N
 __global__ void __launch_bounds__(512, 1)
 sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v) {
   using C = Cfg<D, H, CL, NL, KB, NKS, NVS, NWB, NUS, DEFER>;
-  constexpr int DS = C::DS, HS = C::HS, UP = C::UP, HT = C::HT, NCH = C::NCH, UW = C::UW, UT = C::UT;
+  constexpr int DS = C::DS, HS = C::HS, UP = C::UP, HT = C::HT, NCH = C::NCH, UW = C::UW, UT = C::UT, KS = C::KS;
   constexpr float LOG2E = 1.4426950408889634f;
 
   extern __shared__ __align__(1024) unsigned char sm[];  // swizzled TMA tiles need 1024-byte alignment
@@ -119,19 +120,19 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
   float* s_bqf = s_bias + 8 * DS + 2 * HS;   // Wq . beta_slots
   // update stream of this warp (warps 8..15; the pass warps address the per-stream hand-off buffers by op)
   const int us = (warp >= 8) ? (warp - 8) / UW : 0;
-  float* s_mean = s_bias + 9 * DS + 2 * HS + 16 * us;  // LayerNorm statistics of the round in flight
-  float* s_rstd = s_mean + 8;
+  float* s_mean = s_bias + 9 * DS + 2 * HS + 32 * us;  // LayerNorm statistics of the round in flight
+  float* s_rstd = s_mean + 16;
   unsigned char* xbuf = sm + C::OFF_XBUF + us * C::XBUF_BYTES;
   auto act = [&](uint32_t r) { return sm + C::OFF_ACT + (2 * us + (r & 1)) * C::OPX_BYTES; };  // operand [LX/8][8 slots][8] bf16
-  float* P_GI = reinterpret_cast<float*>(sm + C::OFF_P) + us * 2 * 128 * 8;  // [128 rows of block X][8 slots]
-  float* P_GH = P_GI + 128 * 8;                                              // [128 rows of block Y][8 slots]
+  float* P_GI = reinterpret_cast<float*>(sm + C::OFF_P) + us * 2 * 128 * KS;  // [128 rows of block X][KS slots]
+  float* P_GH = P_GI + 128 * KS;                                              // [128 rows of block Y][KS slots]
   auto ustage_of = [&](int s) { return reinterpret_cast<float*>(sm + C::OFF_UST + s * C::UST_BYTES); };
-  auto sred_of = [&](int s) { return reinterpret_cast<float*>(sm + C::OFF_SRED + s * 128); };
+  auto sred_of = [&](int s) { return reinterpret_cast<float*>(sm + C::OFF_SRED + s * 16 * KS); };
   auto qop = [&](int l) { return sm + C::OFF_LANE + l * C::LANE_BYTES; };
   auto slh_hi = [&](int l) { return sm + C::OFF_LANE + l * C::LANE_BYTES + C::OPD_BYTES; };  // the lane's slots, operand layout
   auto own_of = [&](int l) { return reinterpret_cast<float*>(sm + C::OFF_LANE + l * C::LANE_BYTES + 2 * C::OPD_BYTES); };
   // byte offset of (slot, feature f) inside an operand buffer
-  auto opnd_off = [](int slot, int f) { return (f >> 3) * 128 + slot * 16 + (f & 7) * 2; };
+  auto opnd_off = [](int slot, int f) { return (f >> 3) * (16 * KS) + slot * 16 + (f & 7) * 2; };
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
   uint64_t* k_full = bars;
   uint64_t* k_empty = k_full + NKS;
@@ -259,7 +260,7 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
   // ------------------------------------------------------------------ one-time setup
   // The slots of lane 0's first image are fetched now and written to shared memory at the end of the setup: their global
   // round trip hides under the weight load instead of standing in front of the first query
-  constexpr int PRE2 = (8 * (D / 2) + 255) / 256, PRE1 = (8 * DS + 255) / 256;
+  constexpr int PRE2 = (KS * (D / 2) + 255) / 256, PRE1 = (KS * DS + 255) / 256;
   float2 pre2[PRE2];
   float pre1[PRE1];
   if (tid >= 256 && nops[0] > 0) {
@@ -385,16 +386,16 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
       // Drain of an op's U accumulator into the staging buffer of the update engine.  It is DEFERRED: the softmax of the
       // next op's first pair runs first, so the U issuer always has softmax weights waiting when the previous op's
       // products retire and the tensor pipe does not idle across op boundaries.
-      auto drain = [&](int n, const float (&S)[8]) {
-        float ua[8], ub[8];
+      auto drain = [&](int n, const float (&S)[KS]) {
+        float ua[KS], ub[KS];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { ua[i] = 0.f; ub[i] = 0.f; }
+        for (int i = 0; i < KS; ++i) { ua[i] = 0.f; ub[i] = 0.f; }
         if (NP > 0) {
           mbar_wait(&u_full[n & 1], (n >> 1) & 1);
           tc::fence_after();
           const uint32_t ucol = tlane + C::COL_U + C::U_STRIDE * (n & 1);
-          tc::tmem_ld8(ucol, ua);
-          if (C::HAS_B) tc::tmem_ld8(ucol + C::U_B, ub);
+          tc::tmem_ldn(ucol, ua);
+          if (C::HAS_B) tc::tmem_ldn(ucol + C::U_B, ub);
           tc::fence_before();
           __syncwarp();
           if (lane == 0) tc::arrive(&u_accfree[n & 1]);
@@ -408,31 +409,31 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
           const int da = (C::MA == 128) ? warp * 32 + lane : warp * 16 + r16;
           const bool oka = (C::MA == 128) || lane < 16;
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
+          for (int i = 0; i < KS; ++i)
             if (i < KB && oka) ustage[i * UP + da] = ua[i];
           if (C::HAS_B && lane < 16) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < KS; ++i)
               if (i < KB) ustage[i * UP + 128 + warp * 16 + r16] = ub[i];
           }
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (lane == i) sred[warp * 8 + i] = S[i];
+          for (int i = 0; i < KS; ++i)
+            if (lane == i) sred[warp * KS + i] = S[i];
         }
         if (tid == 0 && n < 40) PP_TRACE(8 + n * 8 + 1);
         __syncwarp();
         if (lane == 0) mbar_arrive(u_ready_of(sx));
       };
-      float Sprev[8];
+      float Sprev[KS];
       int n_prev = -1;
       for (int n = 0; n < total_ops; ++n) {
         int l, c;
         op_of(n, l, c);
         const int t = c % T, img = image_of(l, c / T);
         const bool last = (t == T - 1);
-        float Sl[8];
+        float Sl[KS];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) Sl[i] = 0.f;
+        for (int i = 0; i < KS; ++i) Sl[i] = 0.f;
         for (int p = 0; p < NP; ++p, ++gp) {
           const uint32_t lb = gp & 1, wb = gp % NWB;
           const bool tt = tracer && tid == 0 && n == TRACE_OP && p < 4;
@@ -441,8 +442,8 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
           if (tt) a.trace[340 + p * 12 + 1] = clock64();
           if (tid == 0 && p == 0 && n < 40) PP_TRACE(8 + n * 8);
           tc::fence_after();
-          float x[8];
-          tc::tmem_ld8(tlane + C::COL_LG + C::LG_STRIDE * lb, x);
+          float x[KS];
+          tc::tmem_ldn(tlane + C::COL_LG + C::LG_STRIDE * lb, x);
           tc::fence_before();
           __syncwarp();
           if (lane == 0) tc::arrive(&lg_empty[lb]);
@@ -452,28 +453,28 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
           const bool tok_ok = (ht < TP) && (tok < N);
           float mx = -INFINITY;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < KS; ++i) {
             x[i] = (i < K) ? x[i] : -INFINITY;
             mx = fmaxf(mx, x[i]);
           }
           float sum = 0.f;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < KS; ++i) {
             x[i] = ex2f(x[i] - mx);  // q carries log2(e)
             sum += x[i];
           }
           const float inv = __fdividef(1.f, sum);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) x[i] *= inv;
+          for (int i = 0; i < KS; ++i) x[i] *= inv;
           if (last && a.attn_out != nullptr && tok_ok) {
             float* ao = a.attn_out + ((size_t)img * N + tok) * K;
             if ((K & 1) == 0) {
 #pragma unroll
-              for (int i = 0; i < 8; i += 2)
+              for (int i = 0; i < KS; i += 2)
                 if (i < K) __stcs(reinterpret_cast<float2*>(ao + i), make_float2(x[i], x[i + 1]));
             } else {
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
+              for (int i = 0; i < KS; ++i)
                 if (i < K) __stcs(ao + i, x[i]);
             }
           }
@@ -483,7 +484,7 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
           if (tt) a.trace[340 + p * 12 + 4] = clock64();
           unsigned char* wrow = wtiles + wb * C::WP_BYTES + half * C::WH_BYTES + (tih >> 3) * 256 + (tih & 7) * 2;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < KS; ++i) {
             const float wv = (tok_ok && i < K) ? x[i] + a.eps : 0.f;
             const __nv_bfloat16 wq = __float2bfloat16_rn(wv);
             *reinterpret_cast<__nv_bfloat16*>(wrow + i * 16) = wq;
@@ -499,7 +500,7 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
           }
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) Sl[i] = warp_sum(Sl[i]);
+        for (int i = 0; i < KS; ++i) Sl[i] = warp_sum(Sl[i]);
         if (n_prev >= 0) {  // (only when this op had no pair)
           drain(n_prev, Sprev);
           n_prev = -1;
@@ -509,7 +510,7 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
         if (n + 1 < total_ops) op_of(n + 1, l_next, c_next);
         if (C::DEFER && l_next >= 0 && l_next != l && NP > 0) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) Sprev[i] = Sl[i];
+          for (int i = 0; i < KS; ++i) Sprev[i] = Sl[i];
           n_prev = n;
         } else {
           drain(n, Sl);
@@ -523,7 +524,7 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
       // (The U products have an issuer warp of their own: an mbarrier wait costs ~100 cycles even when it is already
       // complete, and a single issuer spent as long in its six waits per 128-token pair as in the MMAs.)
       const bool leader = tc::elect_one();
-      constexpr uint32_t ID_LG = tc::idesc_bf16(64, 8);
+      constexpr uint32_t ID_LG = tc::idesc_bf16(64, KS);
       uint32_t gp = 0;  // pairs whose logit products have been issued
       int jk = 0;       // half tiles consumed from the k ring
       for (int n = 0; n < total_ops; ++n) {
@@ -554,7 +555,7 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
               for (int ks = 0; ks < 4; ++ks)
                 if (leader)
                   tc::mma_bf16(dcol, tc::smem_desc(ka + ch * C::CH_BYTES + ks * 32, 16, 1024, tc::SW_128),
-                               tc::smem_desc(qa + (ch * 4 + ks) * 256, 128, 128, tc::SW_NONE), ID_LG, (ch | ks) != 0);
+                               tc::smem_desc(qa + (ch * 4 + ks) * (32 * KS), 16 * KS, 128, tc::SW_NONE), ID_LG, (ch | ks) != 0);
             if (leader) tc::commit(&k_empty[s]);
             __syncwarp();
             ++jk;
@@ -678,7 +679,7 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
       }
     };
     // Products: D[128 weight rows x 16] = W block (tensor memory, `wcol`) x operand (K-major [k/8][8 slots][8] bf16,
-    // the second 8-row group aliased onto the first: SBO = 0), `ksteps` of 16 features.  Warp 0 of the engine issues
+    // with 8 slot columns the second 8-row group is aliased onto the first: SBO = 0), `ksteps` of 16 features.  Warp 0 of the engine issues
     // (uniform control flow, one elected lane) and commits to ubar[which]; every thread of the engine waits for the
     // commits of a barrier in order (`uph` counts them; a barrier is never more than one phase ahead of its waiters:
     // W_hh h, which stays in flight across other products, has a barrier of its own); warps 0-3 / 4-7 then move
@@ -692,7 +693,7 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
         const uint32_t oa = smem_u32(opnd);
         if (tc::elect_one()) {
           for (int ks = 0; ks < ksteps; ++ks)
-            tc::mma_bf16_ts(tmem + dcol, tmem + wcol + 8 * ks, tc::smem_desc(oa + ks * 256, 128, 0, tc::SW_NONE), ID_UPD, ks != 0);
+            tc::mma_bf16_ts(tmem + dcol, tmem + wcol + 8 * ks, tc::smem_desc(oa + ks * (32 * KS), 16 * KS, KS == 16 ? 128 : 0, tc::SW_NONE), ID_UPD, ks != 0);
           tc::commit(&ubar[which]);
         }
         __syncwarp();
@@ -706,11 +707,11 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
     const uint32_t tq = tmem + ((uint32_t)((uwarp & 3) * 32) << 16);  // this warp's quarter of the lanes
     auto unload = [&](uint32_t dcol, float* Pr, int group) {
       if (UW == 4 || (uwarp >> 2) == group) {  // four warps cover the 128 lanes; eight split the two accumulators
-        float v8[8];
-        tc::tmem_ld8(tq + dcol, v8);
-        float4* o = reinterpret_cast<float4*>(Pr + ((uwarp & 3) * 32 + lane) * 8);
-        o[0] = make_float4(v8[0], v8[1], v8[2], v8[3]);
-        o[1] = make_float4(v8[4], v8[5], v8[6], v8[7]);
+        float vs[KS];
+        tc::tmem_ldn(tq + dcol, vs);
+        float4* o = reinterpret_cast<float4*>(Pr + ((uwarp & 3) * 32 + lane) * KS);
+#pragma unroll
+        for (int i = 0; i < KS / 4; ++i) o[i] = make_float4(vs[4 * i], vs[4 * i + 1], vs[4 * i + 2], vs[4 * i + 3]);
         tc::fence_before();
       }
     };
@@ -741,7 +742,7 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
         float val = 0.f;
         if (i < K * DS) {
           const int slot = i / DS, dl = i % DS;
-          const float acc = P_GH[(3 * DS + dl) * 8 + slot];
+          const float acc = P_GH[(3 * DS + dl) * KS + slot];
           const float qv = s_rstd[slot] * (acc - s_mean[slot] * s_cq[dl]) + s_bqf[dl];
           if (a.saved != nullptr) saved_at(q_img, q_t)[SL.off_q() + slot * D + rank * DS + dl] = qv;
           val = qv * LOG2E;
@@ -777,7 +778,7 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
       const bool tr_on = tracer && utid == 0 && n < 40;
 #define PP_T(i) do { if (tr_on) a.trace[8 + n * 8 + (i)] = clock64(); } while (0)
       // ============================================================ R1: reduce-scatter of sum w v, all-reduce of sum w
-      arm(round, (uint32_t)(K * D * 4 + 32 * CL));
+      arm(round, (uint32_t)(K * D * 4 + 4 * KS * CL));
       // gh = W_hh h only needs the slots that entered the iteration: it runs under the pass and the R1 round trip.
       // The lane's previous update may have run on the other stream: its last act was the lane's query for this op
       // (phase c of q_ready[l]).  A parity wait cannot tell how far the barrier is -- this stream may come here one phase
@@ -801,10 +802,11 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
           const uint32_t off = (uint32_t)(((rank * KB + slot) * DS + dl) * 4);
           st_async_v4(mapa_u32(lbuf + off, dest), val, mapa_u32(lbar, dest));
         }
-        if (utid < 8 * CL) {
-          const int slot = utid & 7, dest = utid >> 3;
-          const float s = sred[slot] + sred[8 + slot] + sred[16 + slot] + sred[24 + slot];
-          const uint32_t off = (uint32_t)(KB * D * 4 + (rank * 8 + slot) * 4);
+        static_assert(KS * CL <= UT, "one thread per (slot, destination) of the token sums");
+        if (utid < KS * CL) {
+          const int slot = utid % KS, dest = utid / KS;
+          const float s = sred[slot] + sred[KS + slot] + sred[2 * KS + slot] + sred[3 * KS + slot];
+          const uint32_t off = (uint32_t)(KB * D * 4 + (rank * KS + slot) * 4);
           st_async_b32(mapa_u32(lbuf + off, dest), __float_as_uint(s), mapa_u32(lbar, dest));
         }
       }
@@ -827,7 +829,7 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
 #pragma unroll
             for (int src = 0; src < CL; ++src) {
               u += rs[(src * KB + slot) * DS + dl];
-              sw += ss[src * 8 + slot];
+              sw += ss[src * KS + slot];
             }
             val = u / sw;
             if (a.saved != nullptr) {
@@ -857,11 +859,11 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
         float hp = 0.f;
         if (i < K * DS) {
           const int slot = i / DS, dl = i % DS;
-          const float gir = P_GI[(dl) * 8 + slot] + s_bih[dl], ghr = P_GH[(dl) * 8 + slot] + s_bhh[dl];
-          const float giz = P_GI[(DS + dl) * 8 + slot] + s_bih[DS + dl];
-          const float ghz = P_GH[(DS + dl) * 8 + slot] + s_bhh[DS + dl];
-          const float gin = P_GI[(2 * DS + dl) * 8 + slot] + s_bih[2 * DS + dl];
-          const float ghn = P_GH[(2 * DS + dl) * 8 + slot] + s_bhh[2 * DS + dl];
+          const float gir = P_GI[(dl) * KS + slot] + s_bih[dl], ghr = P_GH[(dl) * KS + slot] + s_bhh[dl];
+          const float giz = P_GI[(DS + dl) * KS + slot] + s_bih[DS + dl];
+          const float ghz = P_GH[(DS + dl) * KS + slot] + s_bhh[DS + dl];
+          const float gin = P_GI[(2 * DS + dl) * KS + slot] + s_bih[2 * DS + dl];
+          const float ghn = P_GH[(2 * DS + dl) * KS + slot] + s_bhh[2 * DS + dl];
           const float r = sigmoidf_(gir + ghr), z = sigmoidf_(giz + ghz);
           const float nn = tanhf(gin + r * ghn);
           hp = (1.f - z) * nn + z * own[i];
@@ -894,7 +896,7 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
         float hid = 0.f;
         if (i < K * HS) {
           const int slot = i / HS, hl = i % HS;
-          const float acc = P_GI[(3 * DS + hl) * 8 + slot];
+          const float acc = P_GI[(3 * DS + hl) * KS + slot];
           const float pre = s_rstd[slot] * (acc - s_mean[slot] * s_c1[hl]) + s_b1f[hl];
           if (a.saved != nullptr) saved_at(img, t)[SL.off_pre() + slot * H + rank * HS + hl] = pre;
           hid = fmaxf(pre, 0.f);
@@ -916,7 +918,7 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
         float sn = 0.f;
         if (i < K * DS) {
           const int slot = i / DS, dl = i % DS;
-          sn = own[i] + (s_b2[dl] + P_GI[(3 * DS + HS + dl) * 8 + slot]);
+          sn = own[i] + (s_b2[dl] + P_GI[(3 * DS + HS + dl) * KS + slot]);
           own[i] = sn;
           if (last) a.slots_out[((size_t)img * K + slot) * D + rank * DS + dl] = sn;
         }
@@ -1075,26 +1077,35 @@ extern "C" void ocrl_dev_iter_variant(int v) { g_dev_variant = v; }  // developm
 
 // Returns OCRL_E_SHAPE (without launching) for shapes this kernel does not cover.
 int sa_iter_fwd_umma_dispatch(const IterFwdArgs& a, cudaStream_t s) {
-  if (a.K > 8) {
-    set_error("sa_iter_fwd(tcgen05): K <= 8");
+  if (a.K > 16) {
+    set_error("sa_iter_fwd(tcgen05): K <= 16");
     return OCRL_E_SHAPE;
   }
   if (a.D == 192 && a.H == 192) {
-    // three lanes hide the slot update completely (B = 64: 122 against 133 us with two); two keep the k/v of the images
-    // in flight inside the L2 (compulsory DRAM traffic only)
+    // three lanes hide the slot update completely; two keep the k/v of the images in flight inside the L2 (compulsory
+    // DRAM traffic only).  Measured at B = 64 (us, three lanes / two lanes): one update stream, 4 v slots 124 / 133; two
+    // streams, 3 v slots 118 / 140; two streams + deferred drain 125 / 162
     if (a.K <= 6) {
-      // measured at B = 64 (us, three lanes / two lanes): one update stream, 4 v slots 124 / 133; two streams, 3 v slots
-      // 118 / 140; two streams + deferred drain 125 / 162
       if (a.lanes == 2) return umma::launch_umma<192, 192, 8, 2, 6, 3, 4, 2, 1, 0>(a, s);
       if (g_dev_variant == 1) return umma::launch_umma<192, 192, 8, 3, 6, 3, 3, 2, 2, 1>(a, s);
       return umma::launch_umma<192, 192, 8, 3, 6, 3, 3, 2, 2, 0>(a, s);
     }
-    if (a.lanes == 2) return umma::launch_umma<192, 192, 8, 2, 8, 3, 3, 2, 2>(a, s);
-    return umma::launch_umma<192, 192, 8, 3, 8, 3, 3, 2, 2>(a, s);
+    if (a.K <= 8) {
+      if (a.lanes == 2) return umma::launch_umma<192, 192, 8, 2, 8, 3, 3, 2, 2>(a, s);
+      return umma::launch_umma<192, 192, 8, 3, 8, 3, 3, 2, 2>(a, s);
+    }
+    // 9 .. 16 slots: 16 slot columns in every operand and accumulator; the slot-sized buffers double, which leaves the
+    // ring five half-tile slots (two k, three v) and one update stream
+    if (a.K <= 12) return umma::launch_umma<192, 192, 8, 3, 12, 2, 3, 2, 1>(a, s);
+    return umma::launch_umma<192, 192, 8, 3, 16, 2, 3, 2, 1>(a, s);
   }
   if (a.D == 64 && a.H == 128) {  // the "Slot-Attention (small)" configuration
-    if (a.B >= 48 && a.lanes != 3) return umma::launch_umma<64, 128, 4, 2, 8, 6, 6, 2, 1>(a, s);
-    return umma::launch_umma<64, 128, 8, 3, 8, 6, 6, 2, 1>(a, s);
+    if (a.K <= 8) {
+      if (a.B >= 48 && a.lanes != 3) return umma::launch_umma<64, 128, 4, 2, 8, 6, 6, 2, 1>(a, s);
+      return umma::launch_umma<64, 128, 8, 3, 8, 6, 6, 2, 1>(a, s);
+    }
+    if (a.B >= 48 && a.lanes != 3) return umma::launch_umma<64, 128, 4, 2, 16, 6, 6, 2, 1>(a, s);
+    return umma::launch_umma<64, 128, 8, 3, 16, 6, 6, 2, 1>(a, s);
   }
   set_error("sa_iter_fwd(tcgen05): D=%d H=%d not instantiated", a.D, a.H);
   return OCRL_E_SHAPE;

@@ -4,7 +4,7 @@ oracle.  Variants are selected per call through ocrl_sa_launch_opts (no environm
 
 The kernels are fed exactly bf16-representable k, v, so the comparison measures only the kernels' own arithmetic
 (bf16 q / weights / slot-update activations on tensor cores, fp32 accumulate): 2e-2 relative, the north-star bf16
-tolerance.  Shapes cover ragged token counts, batches that do not fill the clusters' image lanes evenly, K = 1..8
+tolerance.  Shapes cover ragged token counts, batches that do not fill the clusters' image lanes evenly, K = 1..16
 and T = 1..7."""
 import pytest
 import torch
@@ -202,3 +202,28 @@ def test_full_size_slot_and_token_permutation_properties():
     s_tp, a_tp, _ = F.iterate(k[:, tp].contiguous(), v[:, tp].contiguous(), s0, p, 3)
     assert rel_err(s_tp.cpu(), s.cpu()) < 2e-3, rel_err(s_tp.cpu(), s.cpu())
     assert rel_err(a_tp.cpu(), a[:, tp].cpu()) < 2e-3
+
+
+@pytest.mark.parametrize("lanes", [0, 2])
+@pytest.mark.parametrize("B,N,K,T,D,H", [(3, 1000, 11, 3, 192, 192), (2, 4096, 16, 2, 192, 192), (7, 272, 9, 5, 192, 192),
+                                         (64, 4096, 16, 3, 192, 192), (5, 1000, 11, 5, 64, 128), (3, 100, 16, 7, 64, 128)])
+def test_nine_to_sixteen_slots_on_the_tcgen05_kernel(B, N, K, T, D, H, lanes):
+    """BASELINE.json config 5 (num_slots 6 -> 16): K = 9 .. 16 run the tcgen05 kernel with 16 slot columns in every
+    tensor-core operand and accumulator (they used to fall back to the per-image FFMA kernel)."""
+    from ocrl_b200 import functional as F
+
+    p = so.random_sa_params(K, 64, D, H, seed=13)
+    gen = torch.Generator().manual_seed(B * 11 + N + K)
+    x = torch.randn(B, N, 64, generator=gen)
+    s0 = torch.randn(B, K, D, generator=gen)
+    k_ref, v_ref = so.kv_project(x, p)
+    kb, vb = k_ref.bfloat16(), v_ref.bfloat16()
+    sel = list(range(B)) if B <= 3 else [0, B // 2, B - 1]
+    s_ref, a_ref = so.iterate(kb[sel].float(), vb[sel].float(), s0[sel], p, T, 1e-8)
+    with F.launch_options(variant="tcgen05", lanes=lanes, strict=True):
+        s, a = _run(kb, vb, s0, p, T)
+    assert F.last_kernel() == "tcgen05"
+    assert torch.isfinite(s).all() and torch.isfinite(a).all()
+    assert rel_err(s[sel], s_ref) < BF16_TOL, rel_err(s[sel], s_ref)
+    assert rel_err(a[sel], a_ref) < BF16_TOL, rel_err(a[sel], a_ref)
+    assert torch.allclose(a.sum(-1), torch.ones(B, N), atol=1e-4)
