@@ -1082,16 +1082,27 @@ int sa_iter_fwd_umma_dispatch(const IterFwdArgs& a, cudaStream_t s) {
     return OCRL_E_SHAPE;
   }
   if (a.D == 192 && a.H == 192) {
+    // Lanes per cluster when the caller does not say: the count that needs fewer rounds of images per lane on the ~15
+    // clusters of eight CTAs a B200 holds; on a tie two lanes (more clusters busy: B = 16 images of 16 384 tokens run
+    // 119 us on eight clusters against 163 us on six)
+    int lanes = a.lanes;
+    if (lanes != 2 && lanes != 3) {
+      auto rounds = [&](int nl) {
+        const int ncl = min(15, (a.B + nl - 1) / nl);
+        return (a.B + nl * ncl - 1) / (nl * ncl);
+      };
+      lanes = rounds(3) < rounds(2) ? 3 : 2;
+    }
     // three lanes hide the slot update completely; two keep the k/v of the images in flight inside the L2 (compulsory
     // DRAM traffic only).  Measured at B = 64 (us, three lanes / two lanes): one update stream, 4 v slots 124 / 133; two
     // streams, 3 v slots 118 / 140; two streams + deferred drain 125 / 162
     if (a.K <= 6) {
-      if (a.lanes == 2) return umma::launch_umma<192, 192, 8, 2, 6, 3, 4, 2, 1, 0>(a, s);
+      if (lanes == 2) return umma::launch_umma<192, 192, 8, 2, 6, 3, 4, 2, 1, 0>(a, s);
       if (g_dev_variant == 1) return umma::launch_umma<192, 192, 8, 3, 6, 3, 3, 2, 2, 1>(a, s);
       return umma::launch_umma<192, 192, 8, 3, 6, 3, 3, 2, 2, 0>(a, s);
     }
     if (a.K <= 8) {
-      if (a.lanes == 2) return umma::launch_umma<192, 192, 8, 2, 8, 3, 3, 2, 2>(a, s);
+      if (lanes == 2) return umma::launch_umma<192, 192, 8, 2, 8, 3, 3, 2, 2>(a, s);
       return umma::launch_umma<192, 192, 8, 3, 8, 3, 3, 2, 2>(a, s);
     }
     // 9 .. 16 slots: 16 slot columns in every operand and accumulator; the slot-sized buffers double, which leaves the

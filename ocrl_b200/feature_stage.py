@@ -164,6 +164,8 @@ class FusedBf16Encoder:
         from . import abi
 
         self._refresh()
+        if not obs.is_contiguous():  # e.g. a permuted view of HWC frames: the kernels read dense NCHW / HWC frames
+            obs = obs.contiguous()
         if self._own_path_ok(obs):
             return self._own_path(obs)
         if is_u8_frames(obs):
