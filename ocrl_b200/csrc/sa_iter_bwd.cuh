@@ -197,29 +197,31 @@ __global__ void __launch_bounds__(BwdCfg<KV, D, KP>::NT, 1) sa_iter_bwd_kernel(c
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* sp = smem_raw;
   const size_t ring_bytes = (size_t)NW * STAGES * 2 * Cfg::GROUP_BYTES;
-  const size_t red_bytes = (size_t)NW * KP * D * sizeof(float);  // >= NW*KP*64 floats for cols_dot too
+  const size_t red_bytes = (size_t)NW * KP * 64 * sizeof(float);  // cross-warp reductions go 64 columns at a time
   KV* ring = reinterpret_cast<KV*>(sp);
   float* red = reinterpret_cast<float*>(sp);  // aliases the ring outside the token pass
   sp += (ring_bytes > red_bytes ? ring_bytes : red_bytes);
   auto take = [&](size_t nfloats) { float* p = reinterpret_cast<float*>(sp); sp += sizeof(float) * nfloats; return p; };
+  // Slot-sized buffers (KP x D floats each; 12 of them -- with 16 slot rows at D = 192 that is 147 KB).  Buffers whose
+  // lifetimes do not overlap share storage: the MLP pre-activation (B1 only) with the all-gathered dU (written from
+  // E3a on), the queries (loaded right before the token pass) with the second GRU partial (dead after its push in B4),
+  // dU / S (token pass only) with the all-gather target of d mhat / d shat (idle between B3 and E5a).
   float* h_s = take(KP * D);
-  float* q_s = take(KP * D);
   float* u_s = take(KP * D);
   float* z_s = take(KP * D);
   float* hp_s = take(KP * D);
-  float* pre_s = take(KP * H);     // becomes y = relu(pre) in place after the mask is taken
-  float* shat = take(KP * D);      // LN_s(h)
-  float* mhat = take(KP * D);      // LN_m(h')
+  float* pre_s = take(KP * LMAX);  // MLP pre-activation [KP][H] ...
+  float* du_full = pre_s;          // ... then the all-gathered dU [KP][D]
   float* dsn = take(KP * D);       // d slots_next (input gradient of this iteration), replicated
   float* dhp = take(KP * D);       // d h'
   float* part = take(KP * LMAX);   // local partial sums before an exchange
   float* part2 = take(KP * D);
+  float* q_s = part2;              // the iteration's queries during the token pass
   float* rsA = take(KP * LMAX);    // reduce-scatter receive buffers [CL][KP][slice]
   float* rsB = take(KP * D);
   float* fullA = take(KP * D);     // all-gather receive: d mhat, later d shat
-  float* du_full = take(KP * D);
+  float* gm_s = fullA;             // dU / S during the token pass
   float* dhg_full = take(KP * D);
-  float* gm_s = take(KP * D);      // dU / S
   float* dgate = take(6 * KP * DS);  // [dgi_r, dgi_z, dgi_n, dgh_r, dgh_z, dgh_n][KP][DS]
   float* dpre = take(KP * HS);
   float* dq_sl = take(KP * DS);
@@ -291,7 +293,6 @@ __global__ void __launch_bounds__(BwdCfg<KV, D, KP>::NT, 1) sa_iter_bwd_kernel(c
       for (int e = tid; e < KP * D; e += NT) {
         const bool ok = e < K * D;
         h_s[e] = ok ? sv[SL.off_h() + e] : 0.f;
-        q_s[e] = ok ? sv[SL.off_q() + e] : 0.f;
         u_s[e] = ok ? sv[SL.off_u() + e] : 0.f;
         z_s[e] = ok ? sv[SL.off_z() + e] : 0.f;
         hp_s[e] = ok ? sv[SL.off_hp() + e] : 0.f;
@@ -301,12 +302,6 @@ __global__ void __launch_bounds__(BwdCfg<KV, D, KP>::NT, 1) sa_iter_bwd_kernel(c
       __syncthreads();
       ln_stats(h_s, stat_s, K, D, a.ln_eps, warp, lane, NW);
       ln_stats(hp_s, stat_m, K, D, a.ln_eps, warp, lane, NW);
-      __syncthreads();
-      for (int e = tid; e < K * D; e += NT) {
-        const int j = e / D, d = e % D;
-        shat[e] = (h_s[e] - stat_s[2 * j]) * stat_s[2 * j + 1] * __ldg(a.w.ln_slots_w + d) + __ldg(a.w.ln_slots_b + d);
-        mhat[e] = (hp_s[e] - stat_m[2 * j]) * stat_m[2 * j + 1] * __ldg(a.w.ln_mlp_w + d) + __ldg(a.w.ln_mlp_b + d);
-      }
       __syncthreads();
 
       // ---- B1: MLP output layer.  partial dy[k][:] = sum_{d in slice} dsn[k][d] W2[d][:] ----------
@@ -319,7 +314,6 @@ __global__ void __launch_bounds__(BwdCfg<KV, D, KP>::NT, 1) sa_iter_bwd_kernel(c
         dpre[j * HS + o] = (pre_s[j * H + rank * HS + o] > 0.f) ? dy : 0.f;
       }
       __syncthreads();
-      for (int e = tid; e < K * H; e += NT) pre_s[e] = fmaxf(pre_s[e], 0.f);  // y
       __syncthreads();
       for (int e = tid; e < K * DS; e += NT) {  // dW2 = dsn^T relu(pre), db2 = column sums of dsn
         const int j = e / DS, o = e % DS;
@@ -334,7 +328,9 @@ __global__ void __launch_bounds__(BwdCfg<KV, D, KP>::NT, 1) sa_iter_bwd_kernel(c
       }
       for (int e = tid; e < K * DS; e += NT) {
         const int j = e / DS, o = e % DS;
-        fl[FL.fact(FLog::MHAT) + j * FL.L + rank * DS + o] = mhat[j * D + rank * DS + o];
+        const int d = rank * DS + o;  // LN_m(h'), the input of the MLP
+        fl[FL.fact(FLog::MHAT) + j * FL.L + d] =
+            (hp_s[j * D + d] - stat_m[2 * j]) * stat_m[2 * j + 1] * __ldg(a.w.ln_mlp_w + d) + __ldg(a.w.ln_mlp_b + d);
       }
       cluster.sync();  // E2a
       for (int e = tid; e < K * DS; e += NT) {
@@ -402,6 +398,7 @@ __global__ void __launch_bounds__(BwdCfg<KV, D, KP>::NT, 1) sa_iter_bwd_kernel(c
       for (int e = tid; e < KP * D; e += NT) {
         const int j = e / D;
         gm_s[e] = (j < K) ? du_full[e] / S_s[j] : 0.f;
+        q_s[e] = (e < K * D) ? sv[SL.off_q() + e] : 0.f;
       }
       __syncthreads();
       for (int j = warp; j < K; j += NW) {
@@ -542,22 +539,23 @@ __global__ void __launch_bounds__(BwdCfg<KV, D, KP>::NT, 1) sa_iter_bwd_kernel(c
           }
         }
       }
-      // ---- CTA reduction of dq, reduce-scatter across the cluster ---------------------------------
+      // ---- CTA reduction of dq (64 columns at a time), reduce-scatter across the cluster -------------
       __syncthreads();
 #pragma unroll
-      for (int j = 0; j < KP; ++j)
+      for (int c = 0; c < NC; ++c) {
 #pragma unroll
-        for (int c = 0; c < NC; ++c)
-          *reinterpret_cast<float2*>(red + ((size_t)warp * KP + j) * D + 64 * c + 2 * lane) =
-              make_float2(dq[j][2 * c], dq[j][2 * c + 1]);
-      __syncthreads();
-      for (int e = tid; e < K * D; e += NT) {
-        const int j = e / D, d = e % D;
-        float s = 0.f;
+        for (int j = 0; j < KP; ++j)
+          *reinterpret_cast<float2*>(red + ((size_t)warp * KP + j) * 64 + 2 * lane) = make_float2(dq[j][2 * c], dq[j][2 * c + 1]);
+        __syncthreads();
+        for (int e = tid; e < K * 64; e += NT) {
+          const int j = e / 64, d = 64 * c + e % 64;
+          float s = 0.f;
 #pragma unroll
-        for (int w8 = 0; w8 < NW; ++w8) s += red[((size_t)w8 * KP + j) * D + d];
-        const int r = d / DS, o = d % DS;
-        cluster.map_shared_rank(rsA, r)[(rank * KP + j) * DS + o] = s;
+          for (int w8 = 0; w8 < NW; ++w8) s += red[((size_t)w8 * KP + j) * 64 + e % 64];
+          const int r = d / DS, o = d % DS;
+          cluster.map_shared_rank(rsA, r)[(rank * KP + j) * DS + o] = s;
+        }
+        __syncthreads();
       }
       cluster.sync();  // E4
       for (int e = tid; e < K * DS; e += NT) {
@@ -571,7 +569,9 @@ __global__ void __launch_bounds__(BwdCfg<KV, D, KP>::NT, 1) sa_iter_bwd_kernel(c
       for (int e = tid; e < K * DS; e += NT) {  // dWq = dq^T shat
         const int j = e / DS, o = e % DS;
         fl[FL.fact(FLog::DQ) + j * FL.L + rank * DS + o] = dq_sl[j * DS + o];
-        fl[FL.fact(FLog::SHAT) + j * FL.L + rank * DS + o] = shat[j * D + rank * DS + o];
+        const int d = rank * DS + o;  // LN_s(h), the input of the query projection
+        fl[FL.fact(FLog::SHAT) + j * FL.L + d] =
+            (h_s[j * D + d] - stat_s[2 * j]) * stat_s[2 * j + 1] * __ldg(a.w.ln_slots_w + d) + __ldg(a.w.ln_slots_b + d);
       }
       cluster.sync();  // E5a
       for (int e = tid; e < K * DS; e += NT) {
@@ -608,22 +608,31 @@ template <typename KV, int D, int KP>
 static size_t bwd_smem_bytes(int H, int CL) {
   using Cfg = BwdCfg<KV, D, KP>;
   const size_t ring_bytes = (size_t)Cfg::NW * Cfg::STAGES * 2 * Cfg::GROUP_BYTES;
-  const size_t red_bytes = (size_t)Cfg::NW * KP * D * sizeof(float);
+  const size_t red_bytes = (size_t)Cfg::NW * KP * 64 * sizeof(float);
   const int LMAX = D > H ? D : H;
   const int DS = D / CL, HS = H / CL;
-  size_t f = (size_t)KP * D * 15 + (size_t)KP * H + 2 * (size_t)KP * LMAX + 6 * (size_t)KP * DS + (size_t)KP * HS +
+  size_t f = (size_t)KP * D * 10 + 3 * (size_t)KP * LMAX + 6 * (size_t)KP * DS + (size_t)KP * HS +
              (size_t)KP * DS + 4 * (size_t)KP + 2 * (size_t)KP + Cfg::NW * 96;
   return (ring_bytes > red_bytes ? ring_bytes : red_bytes) + sizeof(float) * f + sizeof(uint64_t) * Cfg::NW * Cfg::STAGES +
          128;
 }
 
 template <typename KV, int D, int KP>
-static int launch_bwd(const IterBwdArgs& a, cudaStream_t stream) {
+static int launch_bwd(const IterBwdArgs& a_in, cudaStream_t stream) {
   using Cfg = BwdCfg<KV, D, KP>;
   auto kern = sa_iter_bwd_kernel<KV, D, KP>;
-  const size_t smem = bwd_smem_bytes<KV, D, KP>(a.H, a.CL);
+  IterBwdArgs a = a_in;
+  size_t smem = bwd_smem_bytes<KV, D, KP>(a.H, a.CL);
+  // many slot rows: the per-CTA slices of the gate gradients shrink with the cluster size -- take a larger cluster than
+  // the token count alone would ask for until the state fits (K = 16, D = 192 needs clusters of four)
+  while (smem > 227 * 1024 && a.CL < 8 && D % (2 * a.CL) == 0 && a.H % (2 * a.CL) == 0) {
+    const int total_ctas = a.NCL * a.CL;
+    a.CL *= 2;
+    a.NCL = max(1, min(a.B, max(total_ctas, 148) / a.CL));
+    smem = bwd_smem_bytes<KV, D, KP>(a.H, a.CL);
+  }
   if (smem > 227 * 1024) {
-    set_error("sa_iter_bwd: shared memory %zu B exceeds 227 KB (D=%d K=%d H=%d); backward supports K*D up to ~2300", smem,
+    set_error("sa_iter_bwd: shared memory %zu B exceeds 227 KB (D=%d K=%d H=%d); backward: slot-sized state does not fit", smem,
               D, a.K, a.H);
     return OCRL_E_SHAPE;
   }
