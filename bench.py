@@ -211,7 +211,8 @@ class Clocks:
 
 
 # ------------------------------------------------------------------------------------------------
-def measure(a, mode, steps, warmup, dev, dist, rank, world, pool_host, pool_dev, want_events=True, sustain_s=0.0):
+def measure(a, mode, steps, warmup, dev, dist, rank, world, pool_host, pool_dev, want_events=True, sustain_s=0.0,
+            pool_u8_host=None):
     """One precision mode: eager loop (kernel events -> roofline), CUDA-graph resident loop (value) and
     CUDA-graph end-to-end loop from pinned host frames (e2e)."""
     import ocrl_b200
@@ -319,6 +320,38 @@ def measure(a, mode, steps, warmup, dev, dist, rank, world, pool_host, pool_dev,
     ms_res, _ = timed(step_resident, steps, warmup, join=e2e_join)
     ms_single = timed(step_single, steps, warmup)[0] if step_single is not None else None
     ms_e2e, _ = timed(step_e2e, steps, max(3, warmup), join=e2e_join)
+    ms_u8 = None
+    if graphed is not None and mode == "bf16" and pool_u8_host is not None:
+        # the same host-to-host loop fed with the frames as the datasets / environments hold them (uint8 HWC,
+        # utils/datasets.py:17): the `/ 255` ingest runs inside the first convolution, a quarter of the H2D bytes
+        try:
+            streamed_u8 = ocrl_b200.StreamedEncoder(model, pool_u8_host[:a.batch].to(dev), buffers=nbuf)
+
+            def step_u8(i):
+                streamed_u8.submit(pool_u8_host[(i % nb) * a.batch:(i % nb + 1) * a.batch], outs_host[i % nbuf])
+
+            ms_u8, _ = timed(step_u8, steps, max(3, warmup), join=streamed_u8.join)
+        except Exception as exc:
+            sys.stderr.write(f"bench.py: uint8 frame path not measured ({exc})\n")
+    rollout = None
+    if graphed is not None and mode == "bf16" and want_events:
+        # BASELINE.json config 4 (PPO rollout, sb3s/ocr_extractor.py:45): pooling(ocr(obs)) at the rollout batch (4
+        # environments) and the PPO minibatch (32), one CUDA-graph replay per call, one call at a time (latency)
+        try:
+            from types import SimpleNamespace as NS
+
+            pcfg = NS(d_model=128, nhead=8, num_layers=1, pos_emb="None", norm_first=False, use_mlp1=False, use_mlp2=False,
+                      cw_embedding=False, push_embedding=False)
+            pool = ocrl_b200.Transformer_Module(model.rep_dim, model.num_slots, pcfg).to(dev).eval()
+            rollout = {}
+            for rb in (4, 32):
+                enc = ocrl_b200.GraphedEncoder(ocrl_b200.RolloutExtractor(model, pool), pool_dev[:rb])
+                ms_r = timed(lambda i: enc(pool_dev[(i % 8) * rb:(i % 8 + 1) * rb]), 200, 20)[0]
+                rollout[f"batch_{rb}"] = {"us_per_call": ms_r / 200 * 1e3, "images_per_s": rb * 200 / ms_r * 1e3 * world}
+            rollout["path"] = ("GraphedEncoder(RolloutExtractor(SLATE, Transformer_Module)): frames -> slots -> pooled "
+                               "features [B,128], every kernel hand-written, one graph replay per call")
+        except Exception as exc:
+            sys.stderr.write(f"bench.py: rollout path not measured ({exc})\n")
     sustained = None
     if sustain_s > 0:  # the same resident loop for >= sustain_s seconds, with its own clock samples (rank 0)
         n_sus = max(steps, int(sustain_s * 1e3 / max(ms_res / steps, 1e-3)) + 1)
@@ -334,7 +367,8 @@ def measure(a, mode, steps, warmup, dev, dist, rank, world, pool_host, pool_dev,
     res = {"value": images / ms_res * 1e3, "ms_per_step": ms_res / steps, "eager_value": images / ms_eager * 1e3,
            "e2e_value": images / ms_e2e * 1e3, "e2e_ms_per_step": ms_e2e / steps, "graph": graphed is not None,
            "single_stream_value": (images / ms_single * 1e3) if ms_single else None,
-           "events": events or [], "own_per_step": own_per_step, "sustained": sustained}
+           "events": events or [], "own_per_step": own_per_step, "sustained": sustained,
+           "e2e_u8_value": (images / ms_u8 * 1e3) if ms_u8 else None, "rollout": rollout}
     return res
 
 
@@ -547,7 +581,8 @@ def main():
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
-    main_res = measure(a, a.mode, a.steps, a.warmup, dev, dist, rank, world, pool_host, pool_dev, sustain_s=a.sustain)
+    main_res = measure(a, a.mode, a.steps, a.warmup, dev, dist, rank, world, pool_host, pool_dev, sustain_s=a.sustain,
+                       pool_u8_host=pool_u8.contiguous().pin_memory())
     clk = clocks.stop() if rank == 0 else None
     other = None
     if not a.no_other_mode:
@@ -593,6 +628,11 @@ def main():
                 "own_kernels_per_step": main_res["own_per_step"], "eager_value": main_res["eager_value"],
                 "single_stream_value": main_res["single_stream_value"],
                 "sustained": main_res["sustained"],
+                "rollout": main_res.get("rollout"),
+                "e2e_u8": ({"value": main_res["e2e_u8_value"], "unit": UNIT, "h2d_bytes_per_step": a.batch * a.size * a.size * 3,
+                            "d2h_bytes_per_step": a.batch * a.slots * a.slot_size * 4,
+                            "note": "host to host from pinned uint8 HWC frames (the reference's dataset format); `/ 255` inside the first convolution"}
+                           if main_res.get("e2e_u8_value") else None),
                 "roofline": roofline_of(a, a.mode, main_res["events"])}
         if other is not None:
             om, r = other

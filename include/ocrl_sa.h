@@ -229,6 +229,24 @@ int ocrl_conv_first_relu_bf16p(const float* obs, const float* weight, const floa
 int ocrl_conv_first_relu_u8p(const unsigned char* frames_hwc, const float* weight, const float* bias, void* out_padded,
                              int B, int C, int H, int W, int CO, void* stream);
 
+/* PPO consumer: the slot pooling of poolings/common/transformer.py:9-33 (configs/pooling/transformer.yaml: d_model 128,
+ * 8 heads, ONE post-norm nn.TransformerEncoderLayer with ReLU and dim_feedforward 2048, no positional encoding), forward
+ * only, dropout inactive -- what sb3s/ocr_extractor.py:45 runs on the slots during rollouts:
+ *   out[B, d_model] = TransformerEncoderLayer(cat([cls, Linear(slots)]))[cls]
+ * slots [B,S,Din] fp32 (S <= 16, Din % 32 == 0); weights are the module's own parameters (PyTorch layouts). */
+typedef struct ocrl_pool_weights {
+  const float* lin_w; const float* lin_b;             /* _linear [d_model, Din], [d_model] */
+  const float* cls;                                    /* _cls_token._cls_token [d_model] */
+  const float* in_proj_w; const float* in_proj_b;     /* self_attn.in_proj_weight [3 d_model, d_model], bias [3 d_model] */
+  const float* out_proj_w; const float* out_proj_b;   /* self_attn.out_proj [d_model, d_model], [d_model] */
+  const float* lin1_w; const float* lin1_b;           /* linear1 [dff, d_model], [dff] */
+  const float* lin2_w; const float* lin2_b;           /* linear2 [d_model, dff], [d_model] */
+  const float* norm1_w; const float* norm1_b;         /* norm1 [d_model] */
+  const float* norm2_w; const float* norm2_b;         /* norm2 [d_model] */
+} ocrl_pool_weights;
+int ocrl_pool_transformer_fwd(const float* slots, const ocrl_pool_weights* w, float* out, int B, int S, int Din,
+                              int d_model, int nhead, int dff, float ln_eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,6 +6,7 @@ from .feature_stage import PositionalEmbedding, SlotAttnCNNEncoder  # noqa: F401
 from .slate_module import SLATE_Module  # noqa: F401
 from .slate import SLATE, Base  # noqa: F401
 from .graphed import GraphedEncoder, StreamedEncoder  # noqa: F401
+from .pooling import RolloutExtractor, Transformer_Module  # noqa: F401
 
 __all__ = ["SLATE", "SLATE_Module", "Base", "SlotAttention", "SlotAttentionEncoder", "SlotAttnCNNEncoder",
-           "PositionalEmbedding", "GraphedEncoder", "StreamedEncoder"]
+           "PositionalEmbedding", "GraphedEncoder", "StreamedEncoder", "Transformer_Module", "RolloutExtractor"]

@@ -25,6 +25,7 @@ EXPORTS = [
     "ocrl_sa_iter_fwd", "ocrl_sa_iter_fwd_ex", "ocrl_sa_last_kernel", "ocrl_sa_iter_bwd",
     "ocrl_conv_bias_relu_bf16", "ocrl_frames_to_nhwc_bf16", "ocrl_conv_first_relu_bf16", "ocrl_conv_first_relu_u8p",
     "ocrl_conv_padded_bytes", "ocrl_conv5x5_pack_weights", "ocrl_conv5x5_c64_tc", "ocrl_conv_first_relu_bf16p",
+    "ocrl_pool_transformer_fwd",
 ]
 
 # ocrl_sa_launch_opts.variant
@@ -58,6 +59,15 @@ def launch_opts(variant="auto", max_clusters=0, lanes=0, strict=False, trace=Fal
         variant = SA_VARIANTS[variant]
     return LaunchOpts(int(variant), int(max_clusters or 0), int(lanes or 0), int(bool(strict)), int(bool(trace)),
                       int(bool(prepared)))
+
+
+_POOL_W = ["lin_w", "lin_b", "cls", "in_proj_w", "in_proj_b", "out_proj_w", "out_proj_b", "lin1_w", "lin1_b",
+           "lin2_w", "lin2_b", "norm1_w", "norm1_b", "norm2_w", "norm2_b"]
+
+
+class PoolWeights(Structure):
+    """ocrl_pool_weights (include/ocrl_sa.h)."""
+    _fields_ = [(n, c_void_p) for n in _POOL_W]
 
 
 class SaWeightGrads(Structure):
@@ -120,6 +130,9 @@ def lib() -> ctypes.CDLL:
         L.ocrl_conv5x5_pack_weights.restype = c_int
         L.ocrl_conv5x5_c64_tc.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
         L.ocrl_conv5x5_c64_tc.restype = c_int
+        L.ocrl_pool_transformer_fwd.argtypes = [c_void_p, POINTER(PoolWeights), c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                                c_int, c_float, c_void_p]
+        L.ocrl_pool_transformer_fwd.restype = c_int
         for name in ("ocrl_sa_query_workspace", "ocrl_kv_proj_fwd", "ocrl_kv_proj_bwd", "ocrl_sa_iter_fwd",
                      "ocrl_sa_iter_fwd_ex", "ocrl_sa_iter_bwd", "ocrl_conv_bias_relu_bf16", "ocrl_frames_to_nhwc_bf16"):
             getattr(L, name).restype = c_int

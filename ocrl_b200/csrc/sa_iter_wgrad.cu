@@ -34,8 +34,11 @@ struct Args {
 };
 
 __global__ void __launch_bounds__(NT) wgrad_gemm_kernel(const Args a) {
+  // rows of a chunk = NB whole (image, iteration) records x K slot rows; their offsets inside a record are the same for
+  // every chunk, so the index arithmetic is done once per block
   __shared__ float as[KC][ROWS];
   __shared__ float bs[KC][COLS];
+  __shared__ int offa[KC], offb[KC];
   const int tid = threadIdx.x;
   int p = 0;
 #pragma unroll
@@ -47,30 +50,36 @@ __global__ void __launch_bounds__(NT) wgrad_gemm_kernel(const Args a) {
   const int r0 = (tile / ctiles) * ROWS, c0 = (tile % ctiles) * COLS;
   const FLog FL(a.K, a.D, a.H);
   const SavedLayout SL(a.K, a.D, a.H);
-  const int M = a.B * a.T * a.K;
-  const int per = (M + WG_SPLITS - 1) / WG_SPLITS;
-  const int m_begin = blockIdx.y * per, m_end = min(M, m_begin + per);
+  const int K = a.K, NB = KC / K, rows = NB * K;  // records and rows per chunk
+  const int BT = a.B * a.T;
+  const int per = (BT + WG_SPLITS - 1) / WG_SPLITS;
+  const int bt_begin = blockIdx.y * per, bt_end = min(BT, bt_begin + per);
+  const size_t a_stride = FL.stride(), b_stride = (P.b_fact >= 0) ? FL.stride() : (size_t)SL.stride();
+  const float* a_base = a.flog + FL.fact(P.a_fact) + r0;
+  const float* b_base = (P.b_fact >= 0 ? a.flog + FL.fact(P.b_fact) : a.saved + P.b_off) + c0;
+  if (tid < rows) {
+    const int blk = tid / K, j = tid % K;
+    offa[tid] = (int)(blk * a_stride + (size_t)j * FL.L);
+    offb[tid] = (int)(blk * b_stride + (size_t)j * (P.b_fact >= 0 ? FL.L : P.b_pitch));
+  }
+  __syncthreads();
   const int c = tid % COLS, rq = tid / COLS;  // rows r0 + 4 rq .. + 3
+  const int la_kk = tid / ROWS, la_rr = tid % ROWS;  // this thread's A elements: rows la_kk, la_kk + 16
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int m0 = m_begin; m0 < m_end; m0 += KC) {
-    for (int e = tid; e < KC * ROWS; e += NT) {
-      const int kk = e / ROWS, rr = e % ROWS, m = m0 + kk;
-      float v = 0.f;
-      if (m < m_end && r0 + rr < P.rows)
-        v = __ldg(a.flog + (size_t)(m / a.K) * FL.stride() + FL.fact(P.a_fact) + (size_t)(m % a.K) * FL.L + r0 + rr);
-      as[kk][rr] = v;
+  for (int bt0 = bt_begin; bt0 < bt_end; bt0 += NB) {
+    const int live = min(NB, bt_end - bt0) * K;  // rows of this chunk that exist
+    const float* ap = a_base + (size_t)bt0 * a_stride;
+    const float* bp = b_base + (size_t)bt0 * b_stride;
+#pragma unroll
+    for (int h = 0; h < KC * ROWS / NT; ++h) {
+      const int kk = la_kk + h * (NT / ROWS);
+      as[kk][la_rr] = (kk < live && r0 + la_rr < P.rows) ? __ldg(ap + offa[kk] + la_rr) : 0.f;
     }
-    for (int e = tid; e < KC * COLS; e += NT) {
-      const int kk = e / COLS, cc = e % COLS, m = m0 + kk;
-      float v = 0.f;
-      if (m < m_end && c0 + cc < P.cols) {
-        if (P.b_fact >= 0)
-          v = __ldg(a.flog + (size_t)(m / a.K) * FL.stride() + FL.fact(P.b_fact) + (size_t)(m % a.K) * FL.L + c0 + cc);
-        else
-          v = __ldg(a.saved + (size_t)(m / a.K) * SL.stride() + P.b_off + (size_t)(m % a.K) * P.b_pitch + c0 + cc);
-        if (P.b_relu) v = fmaxf(v, 0.f);
-      }
-      bs[kk][cc] = v;
+#pragma unroll
+    for (int h = 0; h < KC * COLS / NT; ++h) {
+      const int kk = rq + h * (NT / COLS);
+      float v = (kk < live && c0 + c < P.cols) ? __ldg(bp + offb[kk] + c) : 0.f;
+      bs[kk][c] = P.b_relu ? fmaxf(v, 0.f) : v;
     }
     __syncthreads();
 #pragma unroll 8

@@ -247,6 +247,39 @@ def make_loss_case(ref, name, *, B, S, seed, use_bcdec):
     print(name, {k: float(v) for k, v in metrics.items() if torch.is_tensor(v) and v.numel() == 1}, "draws", len(rec.draws))
 
 
+def pool_params(module, seed, d_model):
+    """The seeded, perturbed parameters of a pooling Transformer (reference's or the drop-in: same construction order,
+    hence the same draws): biases / LayerNorm weights perturbed, CLS token non-zero."""
+    _perturb(module, seed + 1)
+    with torch.no_grad():
+        module._cls_token._cls_token.add_(0.3 * torch.randn(d_model, generator=torch.Generator().manual_seed(seed + 2)))
+
+
+def make_pool_case(name, *, B, S, Din, d_model, nhead, seed):
+    """The PPO consumer's slot pooling (poolings/common/transformer.py:9-33, one post-norm layer as in
+    configs/pooling/transformer.yaml) on seeded slots; eval mode (dropout inactive).  The 0.6 M parameters are not
+    stored: both sides build the module from ``torch.manual_seed(seed)`` + ``pool_params`` and the fixture carries a
+    checksum."""
+    import importlib
+
+    mod = importlib.import_module("poolings.common.transformer")
+    torch.manual_seed(seed)
+    t = mod.Transformer(Din, d_model, nhead, 1, None, False)
+    t.eval()
+    pool_params(t, seed, d_model)
+    g = torch.Generator().manual_seed(seed + 3)
+    slots = 1.5 * torch.randn(B, S, Din, generator=g)
+    with torch.no_grad():
+        out = t(slots)
+    data = {"in.slots": slots, "out.pooled": out}
+    meta = dict(B=B, S=S, Din=Din, d_model=d_model, nhead=nhead, eps=1e-5, seed=seed,
+                param_sum=float(sum(p.detach().double().sum() for p in t.parameters())),
+                param_abs_sum=float(sum(p.detach().double().abs().sum() for p in t.parameters())),
+                state_keys=list(t.state_dict().keys()))
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), meta=json.dumps(meta), **_np(data))
+    print(name, "out.sum", float(out.sum()), tuple(out.shape))
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     ref = rb.load()
@@ -270,6 +303,8 @@ def main():
     # get_loss of the adjacent training modules (dVAE, transformer decoder, broadcast decoder), noise frozen
     make_loss_case(ref, "loss_slate_16", B=2, S=16, seed=51, use_bcdec=False)
     make_loss_case(ref, "loss_bcdec_16", B=2, S=16, seed=52, use_bcdec=True)
+    # PPO consumer: slot pooling transformer (rollout path)
+    make_pool_case("pool_transformer", B=5, S=6, Din=192, d_model=128, nhead=8, seed=61)
 
 
 if __name__ == "__main__":

@@ -188,3 +188,58 @@ def test_get_loss_matches_reference_on_gpu(name):
         assert rel_err(got, want) < 1e-4, (k, float(got), float(want))
     m["loss"].backward()  # the loss carries the graph through the fused backward
     assert all(torch.isfinite(p.grad).all() for p in model._module._slotattn.parameters() if p.grad is not None)
+
+
+@pytest.mark.parametrize("B,S", [(5, 6), (1, 1), (32, 16), (4, 7)])
+def test_pooling_transformer_kernel_matches_reference(B, S):
+    """The fused rollout forward of the PPO consumer's slot pooling (ocrl_pool_transformer_fwd) against the frozen
+    reference output (B = 5, S = 6) and, on other batch / slot counts, against the oracle: 1e-4."""
+    from oracle import pool_oracle as po
+    from tests.test_oracle_golden import _pool_module
+
+    meta, g = load_case("pool_transformer")
+    t = _pool_module(meta).cuda()
+    p = {k: v.detach().cpu() for k, v in t.state_dict().items()}
+    if (B, S) == (meta["B"], meta["S"]):
+        slots, want = g["in"]["slots"], g["out"]["pooled"]
+    else:
+        slots = torch.randn(B, S, meta["Din"], generator=torch.Generator().manual_seed(B * 100 + S))
+        want = po.transformer_pool(slots, p, meta["nhead"])
+    with torch.no_grad():
+        got = t(slots.cuda())  # no autograd graph, eval mode -> the fused kernel
+        torch_path = t._trans(torch.cat([t._cls_token().repeat(B, 1, 1), t._linear(slots.cuda())], dim=1).permute(1, 0, 2))[0]
+    assert got.shape == (B, meta["d_model"])
+    assert rel_err(got.cpu(), want) < 1e-4, rel_err(got.cpu(), want)
+    assert rel_err(got.cpu(), torch_path.cpu()) < 1e-4
+    # training pass (PPO minibatch update): gradients flow through the torch path of the same module
+    t.train()
+    out = t(slots.cuda().requires_grad_(True))
+    assert out.requires_grad
+
+
+def test_rollout_extractor_graph_follows_pooling_updates():
+    """pooling(ocr(obs)) captured in one CUDA graph (RolloutExtractor + GraphedEncoder): equal to the eager calls, and
+    captured again after an optimizer-style in-place update of the pooling's weights (PPO trains the pooling)."""
+    from types import SimpleNamespace as NS
+
+    meta, g = load_case("slate_encode_64")
+    model = ocrl_b200.SLATE(*slate_config(kv_dtype="bf16"))
+    _load_hot(model._module, g["p"])
+    model.to("cuda")
+    model.eval()
+    _inject_noise(model._module._slotattn, g["in"]["noise"].cuda())
+    pcfg = NS(d_model=128, nhead=8, num_layers=1, pos_emb="None", norm_first=False, use_mlp1=False, use_mlp2=False,
+              cw_embedding=False, push_embedding=False)
+    torch.manual_seed(3)
+    pool = ocrl_b200.Transformer_Module(model.rep_dim, model.num_slots, pcfg).cuda().eval()
+    obs = (g["in"]["frames_u8"].permute(0, 3, 1, 2).float() / 255.0).contiguous().cuda()
+    enc = ocrl_b200.GraphedEncoder(ocrl_b200.RolloutExtractor(model, pool), obs)
+    with torch.no_grad():
+        want = pool(model(obs))
+        got = enc(obs).clone()
+        assert got.shape == (obs.shape[0], 128) and torch.equal(got, want)
+        pool._trans._linear.weight.mul_(1.5)  # an optimizer step on the pooling
+        assert enc.stale()
+        want2 = pool(model(obs))
+        got2 = enc(obs).clone()
+    assert not torch.equal(want2, want) and torch.equal(got2, want2)

@@ -134,6 +134,18 @@ def test_ocrs_registry_shim():
         assert model.num_slots == 6 and model.rep_dim == 192 and isinstance(model._module, ocrl_b200.SLATE_Module)
         with pytest.raises(AttributeError):
             getattr(ocrs, "NoSuchOCR")
+        # sb3s/ocr_extractor.py:33-35: the pooling module by name, built from the OCR's rep_dim / num_slots
+        for k in [k for k in sys.modules if k == "poolings" or k.startswith("poolings.")]:
+            del sys.modules[k]
+        poolings = importlib.import_module("poolings")
+        from types import SimpleNamespace as NS
+
+        pcfg = NS(name="Transformer", d_model=128, nhead=8, num_layers=1, pos_emb="None", norm_first=False,
+                  use_mlp1=False, use_mlp2=False, cw_embedding=False, push_embedding=False)
+        pool = getattr(poolings, pcfg.name + "_Module")(model.rep_dim, model.num_slots, pcfg)
+        assert type(pool) is ocrl_b200.Transformer_Module and pool.rep_dim == 128
+        for k in [k for k in sys.modules if k == "poolings" or k.startswith("poolings.")]:
+            del sys.modules[k]
         from oracle import reference_bridge as rb
 
         if rb.available():  # with the reference further down the path its sub-packages stay reachable through the shim

@@ -134,3 +134,31 @@ def test_oracle_matches_live_reference():
     s, a = so.slot_attention(x, s0, p, 3)
     assert rel_err(s, rs) < 2e-6 and rel_err(a, ra) < 2e-6
     assert torch.equal(so.position_grid(64), ref.PositionalEmbedding(64, 64).linear_position_embedding)
+
+
+def _pool_module(meta):
+    """ocrl_b200's drop-in pooling transformer with the fixture's seeded parameters (same draws as the reference)."""
+    from ocrl_b200.pooling import Transformer
+    from oracle.make_golden import pool_params
+
+    torch.manual_seed(meta["seed"])
+    t = Transformer(meta["Din"], meta["d_model"], meta["nhead"], 1, None, False)
+    t.eval()
+    pool_params(t, meta["seed"], meta["d_model"])
+    psum = float(sum(p.detach().double().sum() for p in t.parameters()))
+    assert abs(psum - meta["param_sum"]) < 1e-6 * meta["param_abs_sum"]
+    assert list(t.state_dict().keys()) == meta["state_keys"]  # reference checkpoints load strictly
+    return t
+
+
+def test_pooling_oracle_and_module_match_reference():
+    """PPO consumer (poolings/common/transformer.py:9-33): the oracle restatement and the drop-in module's torch path
+    against the output frozen from the real reference module."""
+    from oracle import pool_oracle as po
+
+    meta, g = load_case("pool_transformer")
+    t = _pool_module(meta)
+    p = {k: v.detach() for k, v in t.state_dict().items()}
+    assert rel_err(po.transformer_pool(g["in"]["slots"], p, meta["nhead"]), g["out"]["pooled"]) < 2e-6
+    with torch.no_grad():
+        assert rel_err(t(g["in"]["slots"]), g["out"]["pooled"]) < 2e-6
