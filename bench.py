@@ -486,7 +486,7 @@ def roofline_of(a, mode, events):
             "frac": (achieved / peak if achieved else None), "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": a.batch * bytes_img,
             "algorithmic_bytes_per_image": bytes_img, "avg_launch_ms": it_avg, "launches_timed": len(it_ms),
-            "token_stage": {"kernel": "kv_proj_tc_kernel (tcgen05 + TMA)" if mode == "bf16" else "token_stage_kernel (fp32 FFMA)",
+            "token_stage": {"kernel": "kv_proj_tc2_kernel (tcgen05 + TMA, two row groups per CTA)" if mode == "bf16" else "token_stage_kernel (fp32 FFMA)",
                             "avg_launch_ms": tk_avg, "achieved": tok_achieved, "unit": "GB/s",
                             "frac": (tok_achieved / peak if tok_achieved else None), "traffic": tok_traffic,
                             "algorithmic_bytes_per_image": tok_bytes_img}}
@@ -565,6 +565,9 @@ def main():
 
     from ocrl_b200 import synth
 
+    if os.environ.get("OCRL_DEV_PROJ_VARIANT"):  # development knob: 1 = the single-chain token-stage kernel
+        from ocrl_b200 import abi
+        abi.lib().ocrl_dev_proj_variant(int(os.environ["OCRL_DEV_PROJ_VARIANT"]))
     if a.sweep:
         if rank == 0:
             run_sweep(a, dev, out)

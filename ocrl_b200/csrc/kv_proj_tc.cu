@@ -463,6 +463,304 @@ kv_proj_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Two row groups per CTA.  The kernel above runs ONE serial chain per SM (LayerNorm -> MMA -> tcgen05.ld -> ... ->
+// epilogue, 9.1 k cycles per 128-token tile of which the tensor pipe works 0.5 k): every step waits for the previous
+// one.  Here two independent chains share an SM: row warps 0-3 + producer warp 8 work on the CTA's even tiles, row warps
+// 4-7 + producer warp 9 on the odd ones, each with its own token stage, A tile, staging tiles, barriers and half of the
+// tensor memory (256 columns: 64 shared by the two MLP accumulators, 192 for the projection, which therefore runs as a
+// k pass and a v pass through the same columns for D > 64).  The weights in shared memory are shared.
+constexpr int PT2_NT = 320;  // 2 x 4 row warps + 2 producer / MMA warps
+
+template <int D>
+__global__ void __launch_bounds__(PT2_NT, 1)
+kv_proj_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w1,
+                   const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_wkv,
+                   const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
+                   const __grid_constant__ CUtensorMap tm_pos, const ProjTcParams p) {
+  constexpr int NKV = 2 * D;
+  constexpr int PASS_N = (D == 64) ? 128 : D;     // output features per projection pass (k | v together for D = 64)
+  constexpr int NPASS = NKV / PASS_N;             // 1 or 2
+  constexpr int CPP = PASS_N / 64;                // 64-feature chunks per pass
+  constexpr uint32_t X_BYTES = PT_TM * PT_C * 4;
+  constexpr uint32_t GRP_BYTES = X_BYTES + PT_TM * 128 + 2 * PT_TM * 128;  // token stage, A tile, two staging tiles
+  static_assert(64 + PASS_N <= 256, "a group owns 256 tensor-memory columns");
+
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* sp = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* Wkv_s = sp; sp += NKV * 128;
+  unsigned char* W1_s = sp; sp += 64 * 128;
+  unsigned char* W2_s = sp; sp += 64 * 128;
+  unsigned char* grp_s = sp; sp += 2 * GRP_BYTES;
+  float* prm = reinterpret_cast<float*>(sp); sp += 6 * PT_C * sizeof(float);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sp); sp += 20 * sizeof(uint64_t);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sp);
+  uint64_t* w_full = bars;  // shared; then per group: full, empty, a_ready, mma_done, kv_free, o_ready[2], o_free[2]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = (warp < 8) ? (warp >> 2) : (warp - 8);  // group of this warp
+  uint64_t* gb = bars + 1 + 9 * g;
+  uint64_t* full = gb;
+  uint64_t* empty = gb + 1;
+  uint64_t* a_ready = gb + 2;
+  uint64_t* mma_done = gb + 3;
+  uint64_t* kv_free = gb + 4;
+  uint64_t* o_ready = gb + 5;
+  uint64_t* o_free = gb + 7;
+  unsigned char* X_s = grp_s + g * GRP_BYTES;
+  unsigned char* A_s = X_s + X_BYTES;
+  unsigned char* O_s = A_s + PT_TM * 128;
+
+  if (tid < PT_C) {
+    prm[tid] = p.has_mlp ? __ldg(p.enc_ln_w + tid) : 1.f;
+    prm[64 + tid] = p.has_mlp ? __ldg(p.enc_ln_b + tid) : 0.f;
+    prm[128 + tid] = p.has_mlp ? __ldg(p.b1 + tid) : 0.f;
+    prm[192 + tid] = p.has_mlp ? __ldg(p.b2 + tid) : 0.f;
+    prm[256 + tid] = __ldg(p.in_ln_w + tid);
+    prm[320 + tid] = __ldg(p.in_ln_b + tid);
+  }
+  if (tid == 0) {
+    mbar_init(w_full, 1);
+    for (int q = 0; q < 2; ++q) {
+      uint64_t* b = bars + 1 + 9 * q;
+      mbar_init(b + 0, 1);
+      mbar_init(b + 1, PT_ROWT);
+      mbar_init(b + 2, PT_ROWT);
+      mbar_init(b + 3, 1);
+      mbar_init(b + 4, PT_ROWT);
+      mbar_init(b + 5, PT_ROWT); mbar_init(b + 6, PT_ROWT);
+      mbar_init(b + 7, 1); mbar_init(b + 8, 1);
+    }
+  }
+  mbar_fence_init();
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot + 256u * (uint32_t)g;
+  constexpr uint32_t COL_G = 0, COL_KV = 64;
+
+  const int cta_tiles = (p.ntiles > (int)blockIdx.x) ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int my_tiles = (cta_tiles > g) ? (cta_tiles - g + 1) / 2 : 0;       // the CTA's tiles g, g + 2, ...
+  auto tile_of = [&](int it) { return (long long)blockIdx.x + (long long)(2 * it + g) * gridDim.x; };
+
+  if (warp >= 8) {
+    if (lane == 0) {
+      // ============================ TMA producer + MMA issuer of group g =================================
+      auto load_x = [&](int it) {
+        const long long tile = tile_of(it);
+        unsigned char* dst = X_s;
+        mbar_expect_tx(full, (p.x_format == OCRL_X_TOKENS_BF16 && !p.pos_tiles) ? X_BYTES / 2 : X_BYTES);
+        if (p.x_format == OCRL_X_NCHW_F32) {
+          const long long m0 = tile * PT_TM;
+          const int b = (int)(m0 / p.N), n0 = (int)(m0 % p.N);
+          tma_load_2d(dst, &tm_x, n0, b * PT_C, full);
+        } else if (p.x_format == OCRL_X_TOKENS_BF16) {
+          if (p.pad_w > 0) {
+            const long long m0 = tile * PT_TM;
+            const int b = (int)(m0 / p.N), y0 = (int)(m0 % p.N) / p.pad_w;
+            for (int j = 0; j < PT_TM / p.pad_w; ++j)
+              tma_load_2d(dst + j * p.pad_w * 128, &tm_x, 0, (2 + b * (p.pad_h + 2) + y0 + j) * (p.pad_w + 4) + 2, full);
+          } else {
+            tma_load_2d(dst, &tm_x, 0, (int)(tile * PT_TM), full);
+          }
+          if (p.pos_tiles) tma_load_2d(dst + X_BYTES / 2, &tm_pos, 0, (int)((tile * PT_TM) % p.N), full);
+        } else {
+          tma_load_2d(dst, &tm_x, 0, (int)(tile * PT_TM), full);
+          tma_load_2d(dst + X_BYTES / 2, &tm_x, 32, (int)(tile * PT_TM), full);
+        }
+      };
+      if (g == 0) {  // weights, once per CTA
+        uint32_t wbytes = NKV * 128;
+        if (p.has_mlp) wbytes += 2 * 64 * 128;
+        mbar_expect_tx(w_full, wbytes);
+#pragma unroll
+        for (int r = 0; r < NKV / 128; ++r) tma_load_2d(Wkv_s + r * 128 * 128, &tm_wkv, 0, r * 128, w_full);
+        if (p.has_mlp) {
+          tma_load_2d(W1_s, &tm_w1, 0, 0, w_full);
+          tma_load_2d(W2_s, &tm_w2, 0, 0, w_full);
+        }
+      }
+      if (my_tiles > 0) load_x(0);
+      mbar_wait(w_full, 0);
+
+      uint32_t ar_phase = 0, kf_phase = 0;
+      int sq = 0;  // stores issued by this producer (selects the staging tile)
+      auto mma_tile = [&](const unsigned char* b_tile, int n, uint32_t col) {
+        tc_fence_after();
+        const uint64_t da = umma_desc_sw128(A_s), db = umma_desc_sw128(b_tile);
+#pragma unroll
+        for (int ks = 0; ks < PT_C / 16; ++ks) umma_bf16(tmem + col, da + 2 * ks, db + 2 * ks, umma_idesc(n), ks > 0);
+        umma_commit(mma_done);
+      };
+      for (int it = 0; it < my_tiles; ++it) {
+        if (p.has_mlp) {
+          mbar_wait(a_ready, ar_phase); ar_phase ^= 1;
+          mma_tile(W1_s, 64, COL_G);
+          mbar_wait(a_ready, ar_phase); ar_phase ^= 1;   // (the row threads have read the first accumulator by now)
+          mma_tile(W2_s, 64, COL_G);
+        }
+        const long long tile = tile_of(it);
+#pragma unroll 1
+        for (int ps = 0; ps < NPASS; ++ps) {
+          if (ps == 0) { mbar_wait(a_ready, ar_phase); ar_phase ^= 1; }
+          else { mbar_wait(kv_free, kf_phase); kf_phase ^= 1; }   // the k pass has been read out of the columns
+          mma_tile(Wkv_s + ps * PASS_N * 128, PASS_N, COL_KV);
+          if (ps == 0 && it + 1 < my_tiles) {  // the token stage is free as soon as the rows sit in registers
+            mbar_wait(empty, (uint32_t)(it & 1));
+            load_x(it + 1);
+          }
+          for (int chl = 0; chl < CPP; ++chl, ++sq) {
+            const int buf = sq & 1;
+            mbar_wait(&o_ready[buf], (uint32_t)((sq >> 1) & 1));
+            const int f0 = 64 * (ps * CPP + chl);
+            if (f0 < D) tma_store_2d(&tm_k, O_s + buf * (PT_TM * 128), f0, (int)(tile * PT_TM));
+            else tma_store_2d(&tm_v, O_s + buf * (PT_TM * 128), f0 - D, (int)(tile * PT_TM));
+            tma_store_commit();
+            if (sq >= 1) {
+              tma_store_wait_read<1>();
+              mbar_arrive(&o_free[buf ^ 1]);
+            }
+          }
+        }
+      }
+      tma_store_wait_all<0>();
+    }
+  } else {
+    // ================================ row threads of group g: one token each ================================
+    const int row = tid & 127;
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t md_phase = 0;
+    int store_seq = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+      const long long tile = tile_of(it);
+      const long long m = tile * PT_TM + row;
+      float x[PT_C];
+      mbar_wait(full, (uint32_t)(it & 1));
+      const unsigned char* xs = X_s;
+      if (p.x_format == OCRL_X_NCHW_F32) {
+#pragma unroll
+        for (int c = 0; c < PT_C; ++c) x[c] = reinterpret_cast<const float*>(xs)[c * PT_TM + row];
+      } else if (p.x_format == OCRL_X_TOKENS_BF16) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 u = *reinterpret_cast<const uint4*>(xs + row * 128 + ((c ^ (row & 7)) << 4));
+          const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            x[8 * c + 2 * i] = __uint_as_float(w4[i] << 16);
+            x[8 * c + 2 * i + 1] = __uint_as_float(w4[i] & 0xffff0000u);
+          }
+          if (p.pos_tiles) {
+            const uint4 q = *reinterpret_cast<const uint4*>(xs + X_BYTES / 2 + row * 128 + ((c ^ (row & 7)) << 4));
+            const uint32_t q4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              x[8 * c + 2 * i] += __uint_as_float(q4[i] << 16);
+              x[8 * c + 2 * i + 1] += __uint_as_float(q4[i] & 0xffff0000u);
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 v4 = *reinterpret_cast<const float4*>(xs + h * (X_BYTES / 2) + row * 128 + ((c ^ (row & 7)) << 4));
+            x[32 * h + 4 * c + 0] = v4.x; x[32 * h + 4 * c + 1] = v4.y;
+            x[32 * h + 4 * c + 2] = v4.z; x[32 * h + 4 * c + 3] = v4.w;
+          }
+      }
+      mbar_arrive(empty);
+      if (p.pos != nullptr && !p.pos_tiles) {
+        const int n = (int)((tile * PT_TM + row) % p.N);
+#pragma unroll
+        for (int c = 0; c < PT_C; ++c) x[c] += __ldg(p.pos + (size_t)c * p.N + n);
+      }
+      if (p.has_mlp) {
+        row_layer_norm(x, prm, prm + 64, p.ln_eps);
+        store_row_bf16_sw128(A_s, row, x);
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(a_ready);
+        mbar_wait(mma_done, md_phase); md_phase ^= 1;
+        tc_fence_after();
+        {
+          float acc[32];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            tmem_ld32(trow + COL_G + 32 * h, acc);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[32 * h + i] = fmaxf(acc[i] + prm[128 + 32 * h + i], 0.f);
+          }
+        }
+        store_row_bf16_sw128(A_s, row, x);
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(a_ready);
+        mbar_wait(mma_done, md_phase); md_phase ^= 1;
+        tc_fence_after();
+        {
+          float acc[32];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            tmem_ld32(trow + COL_G + 32 * h, acc);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[32 * h + i] = acc[i] + prm[192 + 32 * h + i];
+          }
+        }
+      }
+      if (p.y_out != nullptr && m < p.M) {
+#pragma unroll
+        for (int c = 0; c < PT_C / 4; ++c)
+          *reinterpret_cast<float4*>(p.y_out + m * PT_C + 4 * c) = make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+      }
+      row_layer_norm(x, prm + 256, prm + 320, p.ln_eps);
+      store_row_bf16_sw128(A_s, row, x);
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(a_ready);
+      // ---- k pass, v pass: TMEM -> bf16 -> swizzled staging tile -> TMA store (by the producer), 64 features at a time
+#pragma unroll 1
+      for (int ps = 0; ps < NPASS; ++ps) {
+        mbar_wait(mma_done, md_phase); md_phase ^= 1;
+        tc_fence_after();
+#pragma unroll 1
+        for (int chl = 0; chl < CPP; ++chl) {
+          float lo[32], hi[32];
+          tmem_ld64(trow + COL_KV + 64 * chl, lo, hi);
+          if (chl == CPP - 1 && ps + 1 < NPASS) {  // the columns may take the next pass
+            tc_fence_before();
+            mbar_arrive(kv_free);
+          }
+          const int buf = store_seq & 1;
+          unsigned char* ot = O_s + buf * (PT_TM * 128);
+          if (store_seq >= 2) mbar_wait(&o_free[buf], (uint32_t)(((store_seq >> 1) - 1) & 1));
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float* src = (c < 4) ? (lo + 8 * c) : (hi + 8 * (c - 4));
+            uint4 u;
+            u.x = pack_bf16x2(src[0], src[1]); u.y = pack_bf16x2(src[2], src[3]);
+            u.z = pack_bf16x2(src[4], src[5]); u.w = pack_bf16x2(src[6], src[7]);
+            *reinterpret_cast<uint4*>(ot + row * 128 + ((c ^ (row & 7)) << 4)) = u;
+          }
+          fence_proxy_async();
+          mbar_arrive(&o_ready[buf]);
+          ++store_seq;
+        }
+      }
+      tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 8) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(*tmem_slot) : "memory");
+  }
+}
+
 // fp32 weights -> bf16 copies in the layout the tensor maps describe ([rows][64], k rows pre-scaled by D^-1/2)
 __global__ void proj_tc_prep_kernel(const float* __restrict__ w1, const float* __restrict__ w2,
                                     const float* __restrict__ wk, const float* __restrict__ wv, __nv_bfloat16* w1b,
@@ -518,6 +816,11 @@ static bool make_map(CUtensorMap* tm, CUtensorMapDataType dt, int esz, const voi
   return fn(tm, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+
+static int g_proj_variant = 0;  // 0: two row groups per CTA, 1: the single-chain kernel (development knob, not in the header)
+}  // namespace ocrl
+extern "C" void ocrl_dev_proj_variant(int v) { ocrl::g_proj_variant = v; }
+namespace ocrl {
 
 size_t kv_proj_tc_workspace(const ocrl_sa_dims* d) {
   return sizeof(__nv_bfloat16) * ((size_t)2 * 64 * 64 + (size_t)2 * d->D * 64 + (size_t)d->N * 64) + 256 + 1024;  // + bf16 position table, trace slots
@@ -594,6 +897,23 @@ int kv_proj_tc_launch(const ocrl_sa_dims* d, const void* x, const float* pos, co
   int dev = 0, sms = 148;
   OCRL_CHECK_CUDA(cudaGetDevice(&dev));
   OCRL_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (g_proj_variant == 0) {  // two row groups per CTA (default)
+    const int grid2 = (p.ntiles + 1) / 2 < sms ? (p.ntiles + 1) / 2 : sms;
+    const size_t smem2 = 1024 + (size_t)2 * D * 128 + 2 * 64 * 128 + 2 * (PT_TM * PT_C * 4 + 3 * PT_TM * 128) + 6 * PT_C * 4 +
+                         20 * 8 + 16;
+#define OCRL_LAUNCH_PT2(DD)                                                                                      \
+  do {                                                                                                           \
+    OCRL_CHECK_CUDA(cudaFuncSetAttribute(kv_proj_tc2_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                         (int)smem2));                                                           \
+    kv_proj_tc2_kernel<DD><<<grid2, PT2_NT, smem2, stream>>>(tm_x, tm_w1, tm_w2, tm_wkv, tm_k, tm_v, tm_pos, p); ocrl::count_launch(); \
+  } while (0)
+    if (D == 64) OCRL_LAUNCH_PT2(64);
+    else if (D == 128) OCRL_LAUNCH_PT2(128);
+    else OCRL_LAUNCH_PT2(192);
+#undef OCRL_LAUNCH_PT2
+    OCRL_CHECK_CUDA(cudaGetLastError());
+    return OCRL_OK;
+  }
   const int grid = p.ntiles < sms ? p.ntiles : sms;
   const size_t smem = 1024 + (size_t)2 * D * 128 + 2 * 64 * 128 + PT_TM * 128 + 2 * PT_TM * 128 + 2 * PT_TM * PT_C * 4 +
                       6 * PT_C * 4 + 12 * 8 + 16;

@@ -166,16 +166,24 @@ class PreparedWeights:
     launch options change (ocrl_sa_launch_opts.prepared).  One per module; inference only."""
 
     def __init__(self):
-        self._key = None
-        self._ws = None
+        self._params = None
+        self._ws = {}
 
     def lookup(self, p, shape_key, nbytes, device):
-        key = (shape_key, tuple((t.data_ptr(), t._version) for t in p.values()))
-        if key == self._key and self._ws is not None and self._ws.device == device:
-            return self._ws, True
-        self._ws = torch.empty(nbytes, device=device, dtype=torch.uint8)
-        self._key = key
-        return self._ws, False
+        params = tuple((t.data_ptr(), t._version) for t in p.values())
+        if params != self._params:  # a parameter changed: every prepared copy is stale
+            self._params = params
+            self._ws = {}
+        key = (shape_key, str(device))
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws, True
+        # one workspace per shape / option set, kept while the parameters stand: CUDA graphs captured for one batch
+        # size keep reading theirs while another batch size (a rollout batch next to a training batch) prepares its own
+        if len(self._ws) >= 32:
+            self._ws.pop(next(iter(self._ws)))
+        ws = self._ws[key] = torch.empty(nbytes, device=device, dtype=torch.uint8)
+        return ws, False
 
 
 def iterate(k: Tensor, v: Tensor, slots0: Tensor, p: Dict[str, Tensor], num_iterations: int, *,

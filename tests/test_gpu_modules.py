@@ -243,3 +243,28 @@ def test_rollout_extractor_graph_follows_pooling_updates():
         want2 = pool(model(obs))
         got2 = enc(obs).clone()
     assert not torch.equal(want2, want) and torch.equal(got2, want2)
+
+
+def test_graphs_survive_calls_with_another_batch_size():
+    """A captured graph keeps reading the prepared weight copies of ITS batch size while the same module serves another
+    batch size (rollout batch next to a minibatch): the per-shape workspaces of functional.PreparedWeights must not be
+    replaced under a live graph (regression: a single-entry cache freed the workspace the graph pointed at)."""
+    meta, g = load_case("slate_encode_64")
+    model = ocrl_b200.SLATE(*slate_config(kv_dtype="bf16"))
+    _load_hot(model._module, g["p"])
+    model.to("cuda")
+    model.eval()
+    obs = (g["in"]["frames_u8"].permute(0, 3, 1, 2).float() / 255.0).contiguous().cuda()
+    big = torch.cat([obs, obs.flip(0), obs], dim=0)  # batch 6
+    _inject_noise(model._module._slotattn, torch.zeros(6, 6, 192, device="cuda"))
+    enc_big = ocrl_b200.GraphedEncoder(model, big)
+    want_big = enc_big(big).clone()
+    _inject_noise(model._module._slotattn, torch.zeros(2, 6, 192, device="cuda"))
+    with torch.no_grad():
+        for _ in range(3):
+            small = model(obs)  # another shape: its own prepared workspace
+            junk = [torch.randn(1 << 20, device="cuda") for _ in range(4)]  # churn the allocator over freed blocks
+            del junk
+    enc_small = ocrl_b200.GraphedEncoder(model, obs)
+    assert torch.equal(enc_small(obs), small)
+    assert torch.equal(enc_big(big), want_big)
