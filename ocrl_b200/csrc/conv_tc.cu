@@ -338,11 +338,14 @@ extern "C" int ocrl_conv5x5_c64_tc(const void* in_padded, const void* packed_w, 
   cudaStream_t s = (cudaStream_t)stream;
   switch (W) {
     case 32: return convtc::launch<36, 3, 4>(in_padded, packed_w, bias, out_padded, B, H, W, relu, s);
-    case 64:
-      if (g_conv_variant == 1) return convtc::launch<68, 3, 5>(in_padded, packed_w, bias, out_padded, B, H, W, relu, s);
+    case 64: {
+      // small batches (rollout: 4 frames = 141 tiles, one per CTA): a CTA's 25 weight taps are a latency chain through
+      // the ring, so units of one tile with a 12-stage ring (all but the slab's shared memory) instead of 3 tiles / 4 stages
+      const long long n_tiles = ((2LL + (long long)B * (H + 2)) * (W + 4) + 127) / 128;
+      if (g_conv_variant == 0 && n_tiles <= 2 * 148) return convtc::launch<68, 1, 12>(in_padded, packed_w, bias, out_padded, B, H, W, relu, s);
       if (g_conv_variant == 2) return convtc::launch<68, 2, 8>(in_padded, packed_w, bias, out_padded, B, H, W, relu, s);
-      if (g_conv_variant == 3) return convtc::launch<68, 2, 6>(in_padded, packed_w, bias, out_padded, B, H, W, relu, s);
       return convtc::launch<68, 3, 4>(in_padded, packed_w, bias, out_padded, B, H, W, relu, s);
+    }
     case 128: return convtc::launch<132, 1, 4>(in_padded, packed_w, bias, out_padded, B, H, W, relu, s);
     default:
       set_error("conv5x5_c64_tc: W=%d not instantiated (32, 64, 128)", W);

@@ -34,7 +34,14 @@ class GraphedEncoder:
     def _weights_key(self):
         """The captured graph reads device copies derived from the parameters (bf16 convolution weights, position table,
         exp(log sigma), the iteration kernel's prepared weights): it is valid for exactly this set of parameter versions."""
-        return tuple((p.data_ptr(), p._version) for p in self._params())
+        self._plist = self._params()
+        return tuple((p.data_ptr(), p._version) for p in self._plist)
+
+    def _version_sum(self):
+        s = 0
+        for p in self._plist:
+            s += p._version
+        return s
 
     def _capture(self):
         dev = self.static_obs.device
@@ -50,10 +57,20 @@ class GraphedEncoder:
         with opts(), torch.cuda.graph(self.graph), torch.no_grad():
             self.static_out = self._call()
         self._key = self._weights_key()
+        self._vsum = self._version_sum()
+        self._calls = 0
 
     def stale(self) -> bool:
-        """True when a parameter changed (optimizer step, load_state_dict, .to()) since the graph was captured."""
-        return self._key != self._weights_key()
+        """True when a parameter changed (optimizer step, load_state_dict, .to()) since the graph was captured.  Every
+        in-place update bumps a parameter's version, so the per-call check is the sum of the versions (a few us: at
+        the rollout batch the replay itself is ~130 us and host time is what a caller sees); the full key, which also
+        notices replaced storages, is compared every 64th call."""
+        self._calls += 1
+        if self._version_sum() != self._vsum:
+            return True
+        if self._calls % 64 == 0:
+            return self._key != tuple((p.data_ptr(), p._version) for p in self._plist)
+        return False
 
     def recapture(self):
         torch.cuda.synchronize(self.static_obs.device)

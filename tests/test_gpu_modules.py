@@ -256,10 +256,11 @@ def test_graphs_survive_calls_with_another_batch_size():
     model.eval()
     obs = (g["in"]["frames_u8"].permute(0, 3, 1, 2).float() / 255.0).contiguous().cuda()
     big = torch.cat([obs, obs.flip(0), obs], dim=0)  # batch 6
-    _inject_noise(model._module._slotattn, torch.zeros(6, 6, 192, device="cuda"))
+    noise_big, noise_small = torch.zeros(6, 6, 192, device="cuda"), torch.zeros(2, 6, 192, device="cuda")  # kept alive: the graphs read them
+    _inject_noise(model._module._slotattn, noise_big)
     enc_big = ocrl_b200.GraphedEncoder(model, big)
     want_big = enc_big(big).clone()
-    _inject_noise(model._module._slotattn, torch.zeros(2, 6, 192, device="cuda"))
+    _inject_noise(model._module._slotattn, noise_small)
     with torch.no_grad():
         for _ in range(3):
             small = model(obs)  # another shape: its own prepared workspace
