@@ -1058,7 +1058,8 @@ static int launch_umma(const IterFwdArgs& a_in, cudaStream_t stream) {
   }
   int ncl = max_clusters;
   if (a.max_clusters > 0) ncl = max(1, min(ncl, a.max_clusters));
-  const int want = (a.B + NL - 1) / NL;  // NL lanes per cluster
+  int want = (a.B + NL - 1) / NL;  // NL lanes per cluster
+  if (a.B <= ncl) want = a.B;      // clusters to spare: one image each (a lane's iterations are serial: sharing a cluster only adds latency)
   if (ncl > want) ncl = want;
   {  // fewest clusters that keep the same number of image rounds (frees SMs for concurrent work)
     const int per = (a.B + ncl - 1) / ncl;
