@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define OCRL_ABI_VERSION 5
+#define OCRL_ABI_VERSION 6
 
 enum {
   OCRL_OK = 0,
@@ -180,8 +180,27 @@ int ocrl_sa_iter_fwd_ex(const ocrl_sa_dims* dims, const void* k, const void* v, 
                         const ocrl_sa_weights* w, float* slots_out, float* attn_vis_out,
                         void* saved, void* workspace, const ocrl_sa_launch_opts* opts, void* stream);
 /* Name of the kernel the last ocrl_sa_iter_fwd / _ex call of this thread launched ("" before the first call):
- * "tcgen05", "pipe", "cluster_tc" or "ffma". */
+ * "tcgen05", "tcgen05_xhat" (factored form), "pipe", "cluster_tc" or "ffma". */
 const char* ocrl_sa_last_kernel(void);
+
+/* FACTORED form of the inference path (no `saved`, no backward).  project_k / project_v have no bias
+ * (slot_attn.py:36-37), so k = s W_k x^ and v = W_v x^ are rank-C_in functions of the normalised tokens
+ * x^ = norm_inputs(x) [B,N,C_in]:   k_n . q = x^_n . (s W_k^T q)   and   sum_n w_n v_n = W_v (sum_n w_n x^_n).
+ * The loop can therefore stream x^ (2 C_in bytes per token in bf16) instead of k and v (4 D bytes per token) and fold
+ * the two projections into the slot-update weights (W_q'' = s W_k^T W_q, W_ih'' = W_ih W_v; prepared once per
+ * parameter version like the other bf16 weight copies).  Same results as ocrl_kv_proj_fwd + ocrl_sa_iter_fwd within
+ * the bf16-mode tolerance (2e-2; measured 3e-4 on the goldens, the k/v form measures 2.4e-4).
+ *   ocrl_xhat_fwd: the token stage up to and including norm_inputs; xhat_out [B,N,C_in] bf16.  Arguments as
+ *     ocrl_kv_proj_fwd (w->wk / w->wv are not read); workspace of ocrl_kv_proj_fwd_workspace(dims) bytes, required.
+ *   ocrl_sa_iter_fwd_xhat: slot_attn.py:64-102 on x^; wk, wv = project_{k,v}.weight [D,C_in] fp32; workspace = `fwd_ws`
+ *     of ocrl_sa_query_workspace; opts as in ocrl_sa_iter_fwd_ex (variant must be AUTO or TCGEN05).
+ * Covered: C_in = 64, (D, H_mlp) = (192, 192), K <= 16, math_mode TENSOR; anything else returns OCRL_E_SHAPE (the
+ * caller then takes the k/v form). */
+int ocrl_xhat_fwd(const ocrl_sa_dims* dims, const void* x, const float* pos_table, const ocrl_token_weights* w,
+                  float* y_out, void* xhat_out, void* workspace, void* stream);
+int ocrl_sa_iter_fwd_xhat(const ocrl_sa_dims* dims, const void* xhat, const float* wk, const float* wv,
+                          const float* slots0, const ocrl_sa_weights* w, float* slots_out, float* attn_vis_out,
+                          void* workspace, const ocrl_sa_launch_opts* opts, void* stream);
 
 /* The fused backward of the loop; attention logits are recomputed from k and the saved
  * per-iteration slots rather than stored (autograd of slot_attn.py:64-102).

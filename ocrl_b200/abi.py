@@ -23,6 +23,7 @@ EXPORTS = [
     "ocrl_kv_proj_fwd_workspace", "ocrl_kv_proj_fwd", "ocrl_kv_proj_bwd_workspace", "ocrl_kv_proj_bwd",
     "ocrl_kv_proj_bwd_lowrank_workspace", "ocrl_kv_proj_bwd_lowrank",
     "ocrl_sa_iter_fwd", "ocrl_sa_iter_fwd_ex", "ocrl_sa_last_kernel", "ocrl_sa_iter_bwd",
+    "ocrl_xhat_fwd", "ocrl_sa_iter_fwd_xhat",
     "ocrl_conv_bias_relu_bf16", "ocrl_frames_to_nhwc_bf16", "ocrl_conv_first_relu_bf16", "ocrl_conv_first_relu_u8p",
     "ocrl_conv_padded_bytes", "ocrl_conv5x5_pack_weights", "ocrl_conv5x5_c64_tc", "ocrl_conv_first_relu_bf16p",
     "ocrl_pool_transformer_fwd",
@@ -112,6 +113,12 @@ def lib() -> ctypes.CDLL:
         L.ocrl_sa_iter_fwd_ex.argtypes = [POINTER(SaDims), c_void_p, c_void_p, c_void_p, POINTER(SaWeights), c_void_p,
                                           c_void_p, c_void_p, c_void_p, POINTER(LaunchOpts), c_void_p]
         L.ocrl_sa_last_kernel.restype = c_char_p
+        L.ocrl_xhat_fwd.argtypes = [POINTER(SaDims), c_void_p, c_void_p, POINTER(TokenWeights), c_void_p, c_void_p,
+                                    c_void_p, c_void_p]
+        L.ocrl_xhat_fwd.restype = c_int
+        L.ocrl_sa_iter_fwd_xhat.argtypes = [POINTER(SaDims), c_void_p, c_void_p, c_void_p, c_void_p, POINTER(SaWeights),
+                                            c_void_p, c_void_p, c_void_p, POINTER(LaunchOpts), c_void_p]
+        L.ocrl_sa_iter_fwd_xhat.restype = c_int
         L.ocrl_sa_iter_bwd.argtypes = [POINTER(SaDims), c_void_p, c_void_p, c_void_p, POINTER(SaWeights), c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p, POINTER(SaWeightGrads), c_void_p,
                                        c_void_p]

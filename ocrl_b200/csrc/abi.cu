@@ -39,7 +39,10 @@ size_t kv_proj_bwd_lowrank_workspace(const ocrl_sa_dims* d);
 size_t kv_proj_tc_workspace(const ocrl_sa_dims* d);
 size_t sa_iter_tc_workspace(const ocrl_sa_dims* d);
 int kv_proj_tc_launch(const ocrl_sa_dims* d, const void* x, const float* pos, const ocrl_token_weights* w, float* y_out,
-                      void* k_out, void* v_out, void* workspace, cudaStream_t stream);
+                      void* k_out, void* v_out, void* workspace, cudaStream_t stream, void* xhat_out = nullptr);
+int sa_iter_fwd_xhat_launch(const ocrl_sa_dims* d, const void* xhat, const float* wk, const float* wv, const float* slots0,
+                            const ocrl_sa_weights* w, float* slots_out, float* attn_out, void* workspace,
+                            const ocrl_sa_launch_opts* opts, cudaStream_t stream);
 
 // Cluster size = CTAs per image.  Needs D % CL == 0 and H % CL == 0 (each CTA owns D/CL slot
 // features in the GRU/MLP) and enough tokens per CTA to keep 8 warps busy.
@@ -151,6 +154,53 @@ int ocrl_kv_proj_fwd(const ocrl_sa_dims* d, const void* x, const float* pos_tabl
     return OCRL_E_SHAPE;
   }
   return token_stage_launch(d, x, pos_table, w, y_out, k_out, v_out, (cudaStream_t)stream);
+}
+
+int ocrl_xhat_fwd(const ocrl_sa_dims* d, const void* x, const float* pos_table, const ocrl_token_weights* w, float* y_out,
+                  void* xhat_out, void* workspace, void* stream) {
+  int rc = check_dims(d);
+  if (rc) return rc;
+  if ((rc = check_arch())) return rc;
+  if (!x || !w || !xhat_out || !workspace || !w->in_ln_w || !w->in_ln_b) {
+    set_error("xhat_fwd: null pointer (x, weights, xhat_out and the workspace are required)");
+    return OCRL_E_ALIGN;
+  }
+  if (!aligned16(x) || !aligned16(xhat_out) || (y_out && !aligned16(y_out)) ||
+      (w->mlp_w1 && (!aligned16(w->mlp_w1) || !aligned16(w->mlp_w2)))) {
+    set_error("xhat_fwd: pointers must be 16-byte aligned");
+    return OCRL_E_ALIGN;
+  }
+  if (d->math_mode != OCRL_MATH_TENSOR) {
+    set_error("xhat_fwd: the factored form is a tensor-path feature (math_mode TENSOR)");
+    return OCRL_E_SHAPE;
+  }
+  if (d->B == 0) return OCRL_OK;
+  rc = kv_proj_tc_launch(d, x, pos_table, w, y_out, nullptr, nullptr, workspace, (cudaStream_t)stream, xhat_out);
+  if (rc == OCRL_E_SHAPE) set_error("xhat_fwd: shape not covered (C_in = 64, D in {64, 128, 192})");
+  return rc;
+}
+
+int ocrl_sa_iter_fwd_xhat(const ocrl_sa_dims* d, const void* xhat, const float* wk, const float* wv, const float* slots0,
+                          const ocrl_sa_weights* w, float* slots_out, float* attn_vis_out, void* workspace,
+                          const ocrl_sa_launch_opts* opts, void* stream) {
+  int rc = check_dims(d);
+  if (rc) return rc;
+  if ((rc = check_arch())) return rc;
+  if (!xhat || !wk || !wv || !slots0 || !w || !slots_out) {
+    set_error("sa_iter_fwd_xhat: null pointer");
+    return OCRL_E_ALIGN;
+  }
+  if (!aligned16(xhat) || !aligned16(wk) || !aligned16(wv) || !aligned16(w->wq) || !aligned16(w->w_ih) ||
+      !aligned16(w->w_hh) || !aligned16(w->w1) || !aligned16(w->w2)) {
+    set_error("sa_iter_fwd_xhat: x^ and weight matrices must be 16-byte aligned");
+    return OCRL_E_ALIGN;
+  }
+  if (d->B == 0) return OCRL_OK;
+  if (opts && (opts->max_clusters < 0 || (opts->lanes != 0 && opts->lanes != 2 && opts->lanes != 3))) {
+    set_error("sa_iter_fwd_xhat: bad launch options (max_clusters %d, lanes %d)", opts->max_clusters, opts->lanes);
+    return OCRL_E_SHAPE;
+  }
+  return sa_iter_fwd_xhat_launch(d, xhat, wk, wv, slots0, w, slots_out, attn_vis_out, workspace, opts, (cudaStream_t)stream);
 }
 
 size_t ocrl_kv_proj_bwd_workspace(const ocrl_sa_dims* d) {

@@ -34,6 +34,7 @@ struct ProjTcParams {
   int has_mlp, x_format, N, D;
   int pos_tiles;                                  // 1: the position table arrives as bf16 [N][64] tiles through TMA (tm_pos)
   int pad_w, pad_h;                               // > 0: bf16 tokens come from the padded layout of conv_tc.cu (frame W x H)
+  int xhat_only;                                  // 1: stop after norm_inputs and store x^ [M][64] bf16 through tm_k (ocrl_xhat_fwd)
   long long M;
   int ntiles;
   float ln_eps;
@@ -574,11 +575,14 @@ kv_proj_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         }
       };
       if (g == 0) {  // weights, once per CTA
-        uint32_t wbytes = NKV * 128;
+        uint32_t wbytes = p.xhat_only ? 0u : NKV * 128;
         if (p.has_mlp) wbytes += 2 * 64 * 128;
-        mbar_expect_tx(w_full, wbytes);
+        if (wbytes == 0) mbar_arrive(w_full);
+        else mbar_expect_tx(w_full, wbytes);
+        if (!p.xhat_only) {
 #pragma unroll
-        for (int r = 0; r < NKV / 128; ++r) tma_load_2d(Wkv_s + r * 128 * 128, &tm_wkv, 0, r * 128, w_full);
+          for (int r = 0; r < NKV / 128; ++r) tma_load_2d(Wkv_s + r * 128 * 128, &tm_wkv, 0, r * 128, w_full);
+        }
         if (p.has_mlp) {
           tma_load_2d(W1_s, &tm_w1, 0, 0, w_full);
           tma_load_2d(W2_s, &tm_w2, 0, 0, w_full);
@@ -604,6 +608,22 @@ kv_proj_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
           mma_tile(W2_s, 64, COL_G);
         }
         const long long tile = tile_of(it);
+        if (p.xhat_only) {  // no projection: the row threads stage x^ itself, one 128 x 64 tile per token tile
+          if (it + 1 < my_tiles) {
+            mbar_wait(empty, (uint32_t)(it & 1));
+            load_x(it + 1);
+          }
+          const int buf = sq & 1;
+          mbar_wait(&o_ready[buf], (uint32_t)((sq >> 1) & 1));
+          tma_store_2d(&tm_k, O_s + buf * (PT_TM * 128), 0, (int)(tile * PT_TM));
+          tma_store_commit();
+          if (sq >= 1) {
+            tma_store_wait_read<1>();
+            mbar_arrive(&o_free[buf ^ 1]);
+          }
+          ++sq;
+          continue;
+        }
 #pragma unroll 1
         for (int ps = 0; ps < NPASS; ++ps) {
           if (ps == 0) { mbar_wait(a_ready, ar_phase); ar_phase ^= 1; }
@@ -719,6 +739,16 @@ kv_proj_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
           *reinterpret_cast<float4*>(p.y_out + m * PT_C + 4 * c) = make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
       }
       row_layer_norm(x, prm + 256, prm + 320, p.ln_eps);
+      if (p.xhat_only) {  // x^ as bf16 into a staging tile (the layout of the A tiles = the TMA store's swizzle)
+        const int buf = store_seq & 1;
+        if (store_seq >= 2) mbar_wait(&o_free[buf], (uint32_t)(((store_seq >> 1) - 1) & 1));
+        store_row_bf16_sw128(O_s + buf * (PT_TM * 128), row, x);
+        fence_proxy_async();
+        mbar_arrive(&o_ready[buf]);
+        ++store_seq;
+        tc_fence_before();
+        continue;
+      }
       store_row_bf16_sw128(A_s, row, x);
       fence_proxy_async();
       tc_fence_before();
@@ -779,7 +809,7 @@ __global__ void proj_tc_prep_kernel(const float* __restrict__ w1, const float* _
   if (i < 64 * 64) {
     if (w1 != nullptr) { w1b[i] = __float2bfloat16_rn(w1[i]); w2b[i] = __float2bfloat16_rn(w2[i]); }
   }
-  if (i < D * 64) {
+  if (wk != nullptr && i < D * 64) {
     wkvb[i] = __float2bfloat16_rn(wk[i] * kscale);
     wkvb[D * 64 + i] = __float2bfloat16_rn(wv[i]);
   }
@@ -828,8 +858,9 @@ size_t kv_proj_tc_workspace(const ocrl_sa_dims* d) {
 
 // returns OCRL_E_SHAPE when this shape has to take the FFMA kernel instead
 int kv_proj_tc_launch(const ocrl_sa_dims* d, const void* x, const float* pos, const ocrl_token_weights* w, float* y_out,
-                      void* k_out, void* v_out, void* workspace, cudaStream_t stream) {
+                      void* k_out, void* v_out, void* workspace, cudaStream_t stream, void* xhat_out) {
   const int D = d->D;
+  const bool xhat_only = (xhat_out != nullptr);
   const long long M = (long long)d->B * d->N;
   if (d->C_in != PT_C || (D != 64 && D != 128 && D != 192) || workspace == nullptr) return OCRL_E_SHAPE;
   if (d->x_format == OCRL_X_NCHW_F32 && (d->N % PT_TM) != 0) return OCRL_E_SHAPE;  // a tile must not straddle two images
@@ -872,10 +903,16 @@ int kv_proj_tc_launch(const ocrl_sa_dims* d, const void* x, const float* pos, co
   ok &= make_map(&tm_w2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w2b, 64, 64, 128, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
   ok &= make_map(&tm_wkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wkvb, 64, (uint64_t)2 * D, 128, 64, 128,
                  CU_TENSOR_MAP_SWIZZLE_128B);
-  ok &= make_map(&tm_k, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, k_out, (uint64_t)D, (uint64_t)M, (uint64_t)D * 2, 64, PT_TM,
-                 CU_TENSOR_MAP_SWIZZLE_128B);
-  ok &= make_map(&tm_v, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, v_out, (uint64_t)D, (uint64_t)M, (uint64_t)D * 2, 64, PT_TM,
-                 CU_TENSOR_MAP_SWIZZLE_128B);
+  if (xhat_only) {  // x^ [M][64] bf16
+    ok &= make_map(&tm_k, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, xhat_out, PT_C, (uint64_t)M, PT_C * 2, PT_C, PT_TM,
+                   CU_TENSOR_MAP_SWIZZLE_128B);
+    tm_v = tm_k;
+  } else {
+    ok &= make_map(&tm_k, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, k_out, (uint64_t)D, (uint64_t)M, (uint64_t)D * 2, 64, PT_TM,
+                   CU_TENSOR_MAP_SWIZZLE_128B);
+    ok &= make_map(&tm_v, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, v_out, (uint64_t)D, (uint64_t)M, (uint64_t)D * 2, 64, PT_TM,
+                   CU_TENSOR_MAP_SWIZZLE_128B);
+  }
   if (pos_tiles)
     ok &= make_map(&tm_pos, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, posb, PT_C, (uint64_t)d->N, PT_C * 2, PT_C, PT_TM,
                    CU_TENSOR_MAP_SWIZZLE_128B);
@@ -892,12 +929,13 @@ int kv_proj_tc_launch(const ocrl_sa_dims* d, const void* x, const float* pos, co
   p.pos_tiles = pos_tiles ? 1 : 0;
   p.has_mlp = has_mlp ? 1 : 0; p.x_format = padded ? OCRL_X_TOKENS_BF16 : d->x_format; p.N = d->N; p.D = D; p.M = M;
   p.pad_w = pw; p.pad_h = ph;
+  p.xhat_only = xhat_only ? 1 : 0;
   p.ntiles = (int)((M + PT_TM - 1) / PT_TM);
   p.ln_eps = d->ln_eps;
   int dev = 0, sms = 148;
   OCRL_CHECK_CUDA(cudaGetDevice(&dev));
   OCRL_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  if (g_proj_variant == 0) {  // two row groups per CTA (default)
+  if (g_proj_variant == 0 || xhat_only) {  // two row groups per CTA (default; the only kernel with the x^ mode)
     const int grid2 = (p.ntiles + 1) / 2 < sms ? (p.ntiles + 1) / 2 : sms;
     const size_t smem2 = 1024 + (size_t)2 * D * 128 + 2 * 64 * 128 + 2 * (PT_TM * PT_C * 4 + 3 * PT_TM * 128) + 6 * PT_C * 4 +
                          20 * 8 + 16;

@@ -75,4 +75,36 @@ int sa_iter_fwd_launch(const ocrl_sa_dims* d, const void* k, const void* v, cons
   return rc;
 }
 
+
+// Factored form (ocrl_sa_iter_fwd_xhat): tcgen05 kernel only, inference only.
+int sa_iter_fwd_xhat_launch(const ocrl_sa_dims* d, const void* xhat, const float* wk, const float* wv, const float* slots0,
+                            const ocrl_sa_weights* w, float* slots_out, float* attn_out, void* workspace,
+                            const ocrl_sa_launch_opts* opts, cudaStream_t stream) {
+  ocrl_sa_launch_opts o = {OCRL_SA_AUTO, 0, 0, 0, 0, 0};
+  if (opts) o = *opts;
+  g_last_kernel = "";
+  if (d->math_mode != OCRL_MATH_TENSOR || (o.variant != OCRL_SA_AUTO && o.variant != OCRL_SA_TCGEN05)) {
+    set_error("sa_iter_fwd_xhat: needs math_mode TENSOR and variant AUTO / TCGEN05");
+    return OCRL_E_SHAPE;
+  }
+  IterFwdArgs a;
+  a.k = nullptr; a.v = nullptr; a.slots0 = slots0; a.w = *w; a.slots_out = slots_out; a.attn_out = attn_out; a.saved = nullptr;
+  a.B = d->B; a.N = d->N; a.D = d->D; a.H = d->H_mlp; a.K = d->K; a.T = d->T;
+  a.eps = d->eps; a.ln_eps = d->ln_eps;
+  a.trace = nullptr;
+  a.wb16 = nullptr;
+  a.workspace = workspace;
+  a.workspace_bytes = workspace ? sa_iter_tc_workspace(d) : 0;
+  a.max_clusters = o.max_clusters;
+  a.lanes = o.lanes;
+  a.prepared = o.prepared;
+  a.xhat = xhat; a.wk = wk; a.wv = wv; a.F = d->C_in;
+  if (o.trace && workspace != nullptr)
+    a.trace = reinterpret_cast<long long*>(reinterpret_cast<unsigned char*>(workspace) + sa_iter_tc_workspace(d) - 4096);
+  a.CL = 8;
+  const int rc = sa_iter_fwd_umma_dispatch(a, stream);
+  if (rc == OCRL_OK) g_last_kernel = "tcgen05_xhat";
+  return rc;
+}
+
 }  // namespace ocrl

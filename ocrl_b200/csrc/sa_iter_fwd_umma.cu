@@ -28,7 +28,7 @@ using namespace pc;
 #define TRACE_OP 2
 #endif
 
-template <int D_, int H_, int CL_, int NL_, int KB_, int NKS_, int NVS_, int NWB_, int NUS_, int DEFER_ = 0>
+template <int D_, int H_, int CL_, int NL_, int KB_, int NKS_, int NVS_, int NWB_, int NUS_, int DEFER_ = 0, int F_ = 0>
 struct Cfg {
   // NL image lanes per cluster; KB rows in the slot-indexed buffers; NKS / NVS ring slots for k / v half tiles;
   // NWB buffers for the softmax weights of a 128-token pair
@@ -36,10 +36,25 @@ struct Cfg {
   static constexpr int KS = KB > 8 ? 16 : 8;  // slot columns of the tensor-core operands and accumulators (K <= KS)
   // NUS update streams: the eight update warps are split into NUS groups that run the slot updates of different ops
   // concurrently (op n -> stream n % NUS); an update is a chain of exchange rounds, bound by latency, not by work
-  static constexpr int NUS = NUS_, UW = 8 / NUS, UT = 32 * UW;
+  // (up to two streams share the eight update warps of a 512-thread CTA; more streams bring four warps each -- a
+  // stream needs one warp per tensor-memory lane quarter to read its accumulators)
+  static constexpr int NUS = NUS_, UWT = NUS_ <= 2 ? 8 : 4 * NUS_, UW = UWT / NUS, UT = 32 * UW;
   static constexpr bool DEFER = DEFER_ != 0;  // drain an op's U accumulator after the next op's first softmax
-  static_assert((NUS == 1 || NUS == 2) && NL <= 3, "update streams, lanes");
-  static constexpr int NT = 512, HT = 64, NCH = D / 64;
+  static_assert(NUS >= 1 && NUS <= 4 && NL <= 6, "update streams, lanes");
+  // F > 0: the FACTORED form of the pass.  k = s W_k x^ and v = W_v x^ are rank-F functions of the normalised tokens
+  // x^ [N, F] (slot_attn.py:54-61, no bias), so  k . q = x^ . (s W_k^T q)  and  sum_n w_n v_n = W_v (sum_n w_n x^_n):
+  // the kernel streams x^ (F * 2 bytes per token instead of 4 D) through ONE ring -- the same tile is the K-major
+  // operand of the logits and the MN-major operand of the weighted sum -- and the two projections are folded into the
+  // update weights (W_q'' = s W_k^T W_q diag(gamma), W_ih'' = W_ih W_v; prepared once per parameter version).
+  static constexpr int F = F_;
+  static constexpr bool XH = F_ != 0;
+  static constexpr int FW = XH ? F_ : D_;  // feature width of the streamed tiles
+  static constexpr int FS = FW / CL_;      // ... and this CTA's slice of it in the exchanges
+  static_assert(!XH || (NKS_ == NVS_ && FW % (4 * CL_) == 0), "factored pass: one ring, four features per push");
+  // The factored pass is short (the softmax warps are its critical path), so an op's accumulator is read out of tensor
+  // memory by the update stream that consumes it, not by the softmax warps
+  static constexpr bool UDRAIN = XH;
+  static constexpr int NT = 256 + 32 * UWT, HT = 64, NCH = FW / 64;
   static constexpr int LX = D > H ? D : H;
   static constexpr int CH_BYTES = HT * 128, HT_BYTES = NCH * CH_BYTES;  // one 64-wide feature chunk / one half tile
   static constexpr int WH_BYTES = 2048, WP_BYTES = 2 * WH_BYTES;        // w tile of a half ([8][16 slots][8] bf16) / a pair
@@ -48,21 +63,21 @@ struct Cfg {
   // weight blocks in tensor memory (row = lane): X = W_ih (3 DS rows) | W1' (HS) | W2 (DS);  Y = W_hh (3 DS) | Wq' (DS)
   static constexpr int RX = 3 * DS + HS + DS, RY = 3 * DS + DS;
   static constexpr int WPB = LX / 2;  // 32-bit words (bf16 pairs) per weight row in the prepared copy
-  static constexpr int UP = D + 4;
+  static constexpr int UP = FW + 4;
   static constexpr int MA = NCH >= 2 ? 128 : 64;   // U product, features [0, 128) (or all 64)
   static constexpr bool HAS_B = NCH == 3;          // second U product, features [128, 192)
-  static_assert(D % 64 == 0 && H % 64 == 0 && DS % 4 == 0 && HS % 4 == 0 && NCH <= 3 && RX <= 128 && RY <= 128, "shape");
+  static_assert(D % 64 == 0 && FW % 64 == 0 && H % 64 == 0 && DS % 4 == 0 && HS % 4 == 0 && NCH <= 3 && RX <= 128 && RY <= 128, "shape");
   // Tensor memory columns: two logit buffers, two U accumulators (features 0-127 | 128-191), the update engine's two
   // accumulators, the weight blocks (a column holds two bf16: K features take K / 2 columns).  (No need to spread a
   // product over several accumulators: back-to-back MMAs into the same columns issue at full rate, scripts/umma_time.cu.)
   static constexpr uint32_t COL_LG = 0, LG_STRIDE = 16, COL_U = 32, U_STRIDE = 32, U_B = 16, COL_GI = 96, COL_GH = 112;
   static constexpr uint32_t COL_WX = 128, COL_WY = COL_WX + LX / 2, TMEM_COLS = 512;
-  static constexpr uint32_t COL_GI2 = COL_WY + D / 2, COL_GH2 = COL_GI2 + 16;  // accumulators of the second update stream
-  static_assert(COL_GH2 + 16 <= 512, "tensor memory");
+  static constexpr uint32_t COL_GI2 = COL_WY + D / 2, COL_GH2 = COL_GI2 + 16;  // accumulators of the update streams 1, 2, ...: 32 columns each
+  static_assert(COL_GI2 + 32 * (NUS - 1) <= 512, "tensor memory");
 
   static constexpr int OFF_KRING = 0;
   static constexpr int OFF_VRING = OFF_KRING + NKS * HT_BYTES;
-  static constexpr int OFF_WT = OFF_VRING + NVS * HT_BYTES;
+  static constexpr int OFF_WT = OFF_VRING + (XH ? 0 : NVS * HT_BYTES);  // (factored pass: one ring)
   static constexpr int OFF_BIAS = OFF_WT + NWB * WP_BYTES;  // (the LayerNorm affine parameters are folded into W1', Wq')
   // fp32 constants: b_ih[3DS] b_hh[3DS] b1'[HS] b2[DS] c1[HS] cq[DS] bq'[DS] + LayerNorm stats mean[8] rstd[8]
   static constexpr int NCONST = 9 * DS + 2 * HS + 32 * NUS;
@@ -80,17 +95,24 @@ struct Cfg {
   static constexpr int OFF_BAR = OFF_SRED + NUS * 16 * KS;
   static constexpr int NBAR = 2 * NKS + 2 * NVS + 12 + 6 * NUS + NL;
   static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
-  static constexpr int SMEM_BYTES = OFF_TMEM + 16;
+  // op table (factored pass): op n -> lane | iteration << 4 | image round << 12.  Finding an op's lane / iteration /
+  // image takes integer divisions by run-time values in every role of the kernel (~2 k cycles per op in the softmax
+  // warps alone: a third of a factored pass); the table is filled once, in parallel, during the setup
+  static constexpr int OPT_MAX = XH ? 2048 : 0;
+  static constexpr int OFF_OPTAB = OFF_TMEM + 32;  // (tensor-memory base, NL <= 6 query counters)
+  static constexpr int SMEM_BYTES = OFF_OPTAB + 4 * OPT_MAX;
 };
 
 // barrier of one update stream (ids 1, 2)
 __device__ __forceinline__ void upd_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-template <int D, int H, int CL, int NL, int KB, int NKS, int NVS, int NWB, int NUS, int DEFER>
-__global__ void __launch_bounds__(512, 1)
+template <int D, int H, int CL, int NL, int KB, int NKS, int NVS, int NWB, int NUS, int DEFER, int F>
+__global__ void __launch_bounds__((NUS <= 2 ? 512 : 256 + 128 * NUS), 1)
 sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v) {
-  using C = Cfg<D, H, CL, NL, KB, NKS, NVS, NWB, NUS, DEFER>;
+  using C = Cfg<D, H, CL, NL, KB, NKS, NVS, NWB, NUS, DEFER, F>;
   constexpr int DS = C::DS, HS = C::HS, UP = C::UP, HT = C::HT, NCH = C::NCH, UW = C::UW, UT = C::UT, KS = C::KS;
+  constexpr int FW = C::FW, FS = C::FS;
+  constexpr bool XH = C::XH;
   constexpr float LOG2E = 1.4426950408889634f;
 
   extern __shared__ __align__(1024) unsigned char sm[];  // swizzled TMA tiles need 1024-byte alignment
@@ -108,7 +130,7 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
   if (tracer2) a.trace[4] = clock64();
 
   unsigned char* kring = sm + C::OFF_KRING;
-  unsigned char* vring = sm + C::OFF_VRING;
+  unsigned char* vring = XH ? kring : sm + C::OFF_VRING;  // factored pass: one ring, two readers
   unsigned char* wtiles = sm + C::OFF_WT;
   float* s_bias = reinterpret_cast<float*>(sm + C::OFF_BIAS);
   const float* s_bih = s_bias;
@@ -136,9 +158,9 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
   uint64_t* k_full = bars;
   uint64_t* k_empty = k_full + NKS;
-  uint64_t* v_full = k_empty + NKS;
-  uint64_t* v_empty = v_full + NVS;
-  uint64_t* lg_full = v_empty + NVS;   // [2] logits of a pair are in tensor memory
+  uint64_t* v_full = XH ? k_full : k_empty + NKS;
+  uint64_t* v_empty = XH ? k_empty : k_empty + NKS + NVS;
+  uint64_t* lg_full = k_empty + NKS + 2 * NVS;   // [2] logits of a pair are in tensor memory
   uint64_t* lg_empty = lg_full + 2;    // [2] the softmax warps have read them
   uint64_t* w_full = lg_empty + 2;     // [2] softmax weights of a pair are in shared memory
   uint64_t* w_empty = w_full + 2;      // [2] the U products that read them are complete
@@ -151,7 +173,7 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
   uint64_t* ubar = sbars + 6 * us + 4;  // [2] a product of the stream is complete ([1]: W_hh h, which overlaps others)
   uint64_t* q_ready = sbars + 6 * NUS;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + C::OFF_TMEM);
-  uint32_t* q_count = tmem_slot + 1;  // [NL <= 3] queries published per lane (read by the update streams)
+  uint32_t* q_count = tmem_slot + 1;  // [NL <= 6] queries published per lane (read by the update streams)
 
   // ------------------------------------------------------------------ work assignment (NL lanes per cluster)
   // Images are dealt to clusters round-robin (newest first: the projection kernel left them in L2) and a cluster
@@ -179,7 +201,7 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
     }
     row_start[NL] = prev; row_width[NL] = 1; seg_base[NL] = total_ops;
   }
-  auto op_of = [&](int n, int& l, int& c) {
+  auto op_of_div = [&](int n, int& l, int& c) {
     l = 0; c = 0;
 #pragma unroll
     for (int g = 0; g < NL; ++g) {
@@ -189,6 +211,32 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
         l = r % row_width[g];
       }
     }
+  };
+  const uint32_t* optab = reinterpret_cast<const uint32_t*>(sm + C::OFF_OPTAB);
+  const bool use_tab = (C::OPT_MAX > 0) && total_ops <= C::OPT_MAX && T < 256;
+  if (use_tab) {
+    uint32_t* tab = reinterpret_cast<uint32_t*>(sm + C::OFF_OPTAB);
+    for (int n = threadIdx.x; n < total_ops; n += C::NT) {
+      int l, c;
+      op_of_div(n, l, c);
+      tab[n] = (uint32_t)l | ((uint32_t)(c % T) << 4) | ((uint32_t)(c / T) << 12);
+    }
+    __syncthreads();
+  }
+  // op n -> lane l, op index c of the lane, iteration t = c % T, image round m = c / T
+  auto op_of4 = [&](int n, int& l, int& c, int& t, int& m) {
+    if (use_tab) {
+      const uint32_t e = optab[n];
+      l = (int)(e & 15u); t = (int)((e >> 4) & 255u); m = (int)(e >> 12);
+      c = m * T + t;
+    } else {
+      op_of_div(n, l, c);
+      t = c % T; m = c / T;
+    }
+  };
+  auto op_of = [&](int n, int& l, int& c) {
+    int t, m;
+    op_of4(n, l, c, t, m);
   };
   auto image_of = [&](int l, int m) { return B - 1 - (cid + (NL * m + l) * ncl); };
   const int ntiles = (N + HT - 1) / HT;          // 64-token half tiles of an image
@@ -211,21 +259,21 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
     OpInfo o;
     o.row_base = 0; o.cold = 0; o.pol = pol_keep;
     if (n < total_ops) {
-      int l, c;
-      op_of(n, l, c);
-      const int t = c % T;
-      o.row_base = image_of(l, c / T) * N + tile0 * HT;
+      int l, c, t, m;
+      op_of4(n, l, c, t, m);
+      o.row_base = image_of(l, m) * N + tile0 * HT;
       o.cold = (t == 0);
       o.pol = (t == T - 1) ? pol_drop : pol_keep;
     }
     return o;
   };
   const bool prod_v = (warp == 6);
+  const bool is_prod = (warp == 4) || (warp == 6 && !XH);
   const int PNS = prod_v ? NVS : NKS;
   int pj = 0, p_n = 0, p_tile = 0, p_slot = 0, p_round = 0;  // next half tile to issue, its ring slot and round
   int f_n = 0, f_tile = 0;                                   // the half tile PFD further on (L2 prefetch)
   OpInfo p_cur = op_info(0), f_cur = p_cur;
-  if ((warp == 4 || warp == 6) && TP > 0) {
+  if (is_prod && TP > 0) {
     f_n = PFD / TP;
     f_tile = PFD - f_n * TP;
     f_cur = op_info(f_n);
@@ -245,8 +293,8 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) tc::tma_load_2d_hint(dst + ch * C::CH_BYTES, tm, ch * 64, row0, full, p_cur.pol);
       if (f_n < total_ops && f_cur.cold) {
-        const size_t off = (size_t)(f_cur.row_base + f_tile * HT) * (D * 2);
-        if (off + C::HT_BYTES <= (size_t)B * N * D * 2)
+        const size_t off = (size_t)(f_cur.row_base + f_tile * HT) * (FW * 2);
+        if (off + C::HT_BYTES <= (size_t)B * N * FW * 2)
           asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(prod_v ? a.v : a.k) + off), "r"(C::HT_BYTES) : "memory");
       }
     }
@@ -263,7 +311,7 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
   constexpr int PRE2 = (KS * (D / 2) + 255) / 256, PRE1 = (KS * DS + 255) / 256;
   float2 pre2[PRE2];
   float pre1[PRE1];
-  if (tid >= 256 && nops[0] > 0) {
+  if (tid >= 256 && tid < 512 && nops[0] > 0) {
     const float* src = a.slots0 + (size_t)image_of(0, 0) * K * D;
 #pragma unroll
     for (int u = 0; u < PRE2; ++u) {
@@ -277,8 +325,9 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
     }
   }
   if (tid == 0) {
-    for (int s = 0; s < NKS; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
-    for (int s = 0; s < NVS; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
+    for (int s = 0; s < NKS; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], XH ? 2 : 1); }  // (factored: both issuers release a slot)
+    if (!XH)
+      for (int s = 0; s < NVS; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&lg_full[s], 1);
       mbar_init(&lg_empty[s], 4);
@@ -304,8 +353,8 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
   // first half tiles: their HBM latency overlaps the weight load below (behind a barrier of the pass warps that
   // publishes the mbarrier init)
   if (warp < 8) {
-    asm volatile("bar.sync 3, 256;" ::: "memory");
-    if (warp == 4 || warp == 6)
+    asm volatile("bar.sync 8, 256;" ::: "memory");
+    if (is_prod)
       while (pj < PNS && pj < total_ht) produce();
   }
   tc::fence_before();
@@ -355,7 +404,7 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
   tc::fence_before();
   __syncthreads();
   tc::fence_after();
-  if (tid >= 256 && nops[0] > 0) {  // after the zero fill of the lane buffers; the cluster barrier below publishes it
+  if (tid >= 256 && tid < 512 && nops[0] > 0) {  // after the zero fill of the lane buffers; the cluster barrier below publishes it
     unsigned char* dst = slh_hi(0);
     float* own = own_of(0);
 #pragma unroll
@@ -387,6 +436,23 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
       // next op's first pair runs first, so the U issuer always has softmax weights waiting when the previous op's
       // products retire and the tensor pipe does not idle across op boundaries.
       auto drain = [&](int n, const float (&S)[KS]) {
+        if (C::UDRAIN) {  // only the token sums; the update stream fetches the accumulator itself
+          const int sx = n % NUS;
+          float* sred = sred_of(sx);
+          if (tracer && tid == 0 && n == TRACE_OP) a.trace[364 + 11] = clock64();
+          if (n >= NUS) mbar_wait(u_free_of(sx), (uint32_t)((n / NUS - 1) & 1));
+          if (tracer && tid == 0 && n == TRACE_OP) a.trace[376 + 11] = clock64();
+          {  // lane i keeps slot i's sum (a select chain: `if (lane == i) store` compiles to a divergent jump table)
+            float sv = S[0];
+#pragma unroll
+            for (int i = 1; i < KS; ++i) sv = (lane == i) ? S[i] : sv;
+            if (lane < KS) sred[warp * KS + lane] = sv;
+          }
+          if (tid == 0 && n < 40) PP_TRACE(8 + n * 8 + 1);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(u_ready_of(sx));
+          return;
+        }
         float ua[KS], ub[KS];
 #pragma unroll
         for (int i = 0; i < KS; ++i) { ua[i] = 0.f; ub[i] = 0.f; }
@@ -416,9 +482,12 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
             for (int i = 0; i < KS; ++i)
               if (i < KB) ustage[i * UP + 128 + warp * 16 + r16] = ub[i];
           }
+          {  // lane i keeps slot i's sum (a select chain: `if (lane == i) store` compiles to a divergent jump table)
+            float sv = S[0];
 #pragma unroll
-          for (int i = 0; i < KS; ++i)
-            if (lane == i) sred[warp * KS + i] = S[i];
+            for (int i = 1; i < KS; ++i) sv = (lane == i) ? S[i] : sv;
+            if (lane < KS) sred[warp * KS + lane] = sv;
+          }
         }
         if (tid == 0 && n < 40) PP_TRACE(8 + n * 8 + 1);
         __syncwarp();
@@ -427,9 +496,9 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
       float Sprev[KS];
       int n_prev = -1;
       for (int n = 0; n < total_ops; ++n) {
-        int l, c;
-        op_of(n, l, c);
-        const int t = c % T, img = image_of(l, c / T);
+        int l, c, t, m_;
+        op_of4(n, l, c, t, m_);
+        const int img = image_of(l, m_);
         const bool last = (t == T - 1);
         float Sl[KS];
 #pragma unroll
@@ -499,8 +568,18 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
             n_prev = -1;
           }
         }
+        const bool te = tracer && tid == 0 && n == TRACE_OP;
+        if (te) a.trace[340 + 11] = clock64();
+        // (stage by stage over all slots: KS independent shuffles in flight instead of KS serial 5-step chains)
 #pragma unroll
-        for (int i = 0; i < KS; ++i) Sl[i] = warp_sum(Sl[i]);
+        for (int off = 16; off > 0; off >>= 1) {
+          float o[KS];
+#pragma unroll
+          for (int i = 0; i < KS; ++i) o[i] = __shfl_xor_sync(FULL, Sl[i], off);
+#pragma unroll
+          for (int i = 0; i < KS; ++i) Sl[i] += o[i];
+        }
+        if (te) a.trace[352 + 11] = clock64();
         if (n_prev >= 0) {  // (only when this op had no pair)
           drain(n_prev, Sprev);
           n_prev = -1;
@@ -508,7 +587,7 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
         // defer only when the next op belongs to another lane: a lane's next pass needs the query its own update produces
         int l_next = -1, c_next = 0;
         if (n + 1 < total_ops) op_of(n + 1, l_next, c_next);
-        if (C::DEFER && l_next >= 0 && l_next != l && NP > 0) {
+        if (C::DEFER && !C::UDRAIN && l_next >= 0 && l_next != l && NP > 0) {
 #pragma unroll
           for (int i = 0; i < KS; ++i) Sprev[i] = Sl[i];
           n_prev = n;
@@ -518,7 +597,8 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
       }
     } else if (warp == 4 || warp == 6) {
       // ---- TMA producers: the rest of the stream (the first ring-full was issued during the setup)
-      while (pj < total_ht) produce();
+      if (is_prod)
+        while (pj < total_ht) produce();
     } else if (warp == 5) {
       // ---- MMA issuer of the logits: the whole warp runs the control flow (uniform operands), one elected lane issues.
       // (The U products have an issuer warp of their own: an mbarrier wait costs ~100 cycles even when it is already
@@ -623,7 +703,7 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
     // (statistics from the received rows).
     const int utid = tid - 256 - us * UT, uwarp = warp - 8 - us * UW;  // thread / warp inside the stream
     auto upd_sync = [&]() { ocrl::umma::upd_sync(1 + us, UT); };
-    const uint32_t col_gi = us ? C::COL_GI2 : C::COL_GI, col_gh = us ? C::COL_GH2 : C::COL_GH;
+    const uint32_t col_gi = us ? C::COL_GI2 + 32u * (uint32_t)(us - 1) : C::COL_GI, col_gh = us ? C::COL_GH2 + 32u * (uint32_t)(us - 1) : C::COL_GH;
     float* ustage = ustage_of(us);
     float* sred = sred_of(us);
     uint64_t* u_ready = u_ready_of(us);
@@ -658,11 +738,12 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
     };
     // mean / rstd of the K rows (bf16, length D, operand layout) that just arrived: one warp per row
     auto row_stats = [&](const unsigned char* opnd) {
+      constexpr int NCD = D / 64;  // (rows of slot features; NCH counts the chunks of the streamed tiles)
       for (int row = uwarp; row < K; row += UW) {
-        float2 x[NCH];
+        float2 x[NCD];
         float s = 0.f;
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
+        for (int c = 0; c < NCD; ++c) {
           const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(opnd + opnd_off(row, 64 * c + 2 * lane));
           x[c] = make_float2(__low2float(v), __high2float(v));
           s += x[c].x + x[c].y;
@@ -670,7 +751,7 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
         const float mean = warp_sum(s) * (1.f / D);
         float q = 0.f;
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
+        for (int c = 0; c < NCD; ++c) {
           const float dx = x[c].x - mean, dy = x[c].y - mean;
           q = fmaf(dx, dx, fmaf(dy, dy, q));
         }
@@ -733,21 +814,21 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
     auto q_phase = [&](int l, int q_img, int q_t) {
       product(C::COL_WY, slh_hi(l), D / 16, col_gh, 0);
       row_stats(slh_hi(l));
-      arm(round, (uint32_t)(K * D * 2));
+      arm(round, (uint32_t)(K * FW * 2));
       product_wait(0);
       unload(col_gh, P_GH, 1);
       upd_sync();
-      for (int i0 = uwarp * 32; i0 < K * DS; i0 += UT) {
+      for (int i0 = uwarp * 32; i0 < K * FS; i0 += UT) {  // (factored: q'' = s W_k^T q, FS features per CTA)
         const int i = i0 + lane;
         float val = 0.f;
-        if (i < K * DS) {
-          const int slot = i / DS, dl = i % DS;
+        if (i < K * FS) {
+          const int slot = i / FS, dl = i % FS;
           const float acc = P_GH[(3 * DS + dl) * KS + slot];
           const float qv = s_rstd[slot] * (acc - s_mean[slot] * s_cq[dl]) + s_bqf[dl];
-          if (a.saved != nullptr) saved_at(q_img, q_t)[SL.off_q() + slot * D + rank * DS + dl] = qv;
+          if (!XH && a.saved != nullptr) saved_at(q_img, q_t)[SL.off_q() + slot * D + rank * DS + dl] = qv;
           val = qv * LOG2E;
         }
-        quad_push(round, val, i, DS, qop(l));
+        quad_push(round, val, i, FS, qop(l));
       }
       xwait(round);
       ++round;
@@ -770,15 +851,15 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
 
     for (int n = us; n < total_ops; n += NUS) {  // the stream's ops
       const int ns = n / NUS;  // ... counted per stream (barrier phases)
-      int l, c;
-      op_of(n, l, c);
-      const int t = c % T, m = c / T, img = image_of(l, m);
+      int l, c, t, m;
+      op_of4(n, l, c, t, m);
+      const int img = image_of(l, m);
       const bool last = (t == T - 1);
       float* own = own_of(l);
       const bool tr_on = tracer && utid == 0 && n < 40;
 #define PP_T(i) do { if (tr_on) a.trace[8 + n * 8 + (i)] = clock64(); } while (0)
       // ============================================================ R1: reduce-scatter of sum w v, all-reduce of sum w
-      arm(round, (uint32_t)(K * D * 4 + 4 * KS * CL));
+      arm(round, (uint32_t)(K * FW * 4 + 4 * KS * CL));
       // gh = W_hh h only needs the slots that entered the iteration: it runs under the pass and the R1 round trip.
       // The lane's previous update may have run on the other stream: its last act was the lane's query for this op
       // (phase c of q_ready[l]).  A parity wait cannot tell how far the barrier is -- this stream may come here one phase
@@ -791,15 +872,44 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
       }
       product(C::COL_WY, slh_hi(l), D / 16, col_gh, 1);
       mbar_wait(u_ready, (uint32_t)(ns & 1));
+      if (C::UDRAIN) {  // the op's accumulator: tensor memory -> the stream's staging buffer
+        if (uwarp < 4) {
+          float ua[KS], ub[KS];
+#pragma unroll
+          for (int i = 0; i < KS; ++i) { ua[i] = 0.f; ub[i] = 0.f; }
+          if (NP > 0) {
+            mbar_wait(&u_full[n & 1], (uint32_t)((n >> 1) & 1));
+            tc::fence_after();
+            const uint32_t ucol = tq + C::COL_U + C::U_STRIDE * (n & 1);
+            tc::tmem_ldn(ucol, ua);
+            if (C::HAS_B) tc::tmem_ldn(ucol + C::U_B, ub);
+            tc::fence_before();
+            __syncwarp();
+            if (lane == 0) tc::arrive(&u_accfree[n & 1]);
+          }
+          const int r16 = lane & 15;
+          const int da = (C::MA == 128) ? uwarp * 32 + lane : uwarp * 16 + r16;
+          const bool oka = (C::MA == 128) || lane < 16;
+#pragma unroll
+          for (int i = 0; i < KS; ++i)
+            if (i < KB && oka) ustage[i * UP + da] = ua[i];
+          if (C::HAS_B && lane < 16) {
+#pragma unroll
+            for (int i = 0; i < KS; ++i)
+              if (i < KB) ustage[i * UP + 128 + uwarp * 16 + r16] = ub[i];
+          }
+        }
+        upd_sync();
+      }
       PP_T(2);
       {
         const uint32_t lbuf = smem_u32(xb), lbar = smem_u32(&xbar[round & 1]);
-        constexpr int QPR = D / 4;
+        constexpr int QPR = FW / 4;
         for (int i = utid; i < K * QPR; i += UT) {
           const int slot = i / QPR, d = 4 * (i % QPR);
-          const int dest = d / DS, dl = d % DS;
+          const int dest = d / FS, dl = d % FS;
           const float4 val = *reinterpret_cast<const float4*>(ustage + slot * UP + d);
-          const uint32_t off = (uint32_t)(((rank * KB + slot) * DS + dl) * 4);
+          const uint32_t off = (uint32_t)(((rank * KB + slot) * FS + dl) * 4);
           st_async_v4(mapa_u32(lbuf + off, dest), val, mapa_u32(lbar, dest));
         }
         static_assert(KS * CL <= UT, "one thread per (slot, destination) of the token sums");
@@ -816,35 +926,35 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
       ++round;
       PP_T(3);
       // ============================================================ R2: all-gather updates = sum over CTAs / token sum
-      arm(round, (uint32_t)(K * D * 2));
+      arm(round, (uint32_t)(K * FW * 2));
       {
         const float* rs = reinterpret_cast<const float*>(xb);
         const float* ss = rs + KB * D;
-        for (int i0 = uwarp * 32; i0 < K * DS; i0 += UT) {
+        for (int i0 = uwarp * 32; i0 < K * FS; i0 += UT) {
           const int i = i0 + lane;
           float val = 0.f;
-          if (i < K * DS) {
-            const int slot = i / DS, dl = i % DS;
+          if (i < K * FS) {
+            const int slot = i / FS, dl = i % FS;
             float u = 0.f, sw = 0.f;
 #pragma unroll
             for (int src = 0; src < CL; ++src) {
-              u += rs[(src * KB + slot) * DS + dl];
+              u += rs[(src * KB + slot) * FS + dl];
               sw += ss[src * KS + slot];
             }
-            val = u / sw;
-            if (a.saved != nullptr) {
+            val = u / sw;  // factored: the weighted mean of x^ (W_v is folded into W_ih'')
+            if (!XH && a.saved != nullptr) {
               float* sv = saved_at(img, t);
               sv[SL.off_h() + slot * D + rank * DS + dl] = own[i];  // slots entering the iteration
               sv[SL.off_u() + slot * D + rank * DS + dl] = val;
               if (rank == 0 && dl == 0) sv[SL.off_s() + slot] = sw;
             }
           }
-          quad_push(round, val, i, DS, act(round));
+          quad_push(round, val, i, FS, act(round));
         }
       }
       xwait(round);
       // ---- GRU: gi = W_ih u
-      product(C::COL_WX, act(round), D / 16, col_gi, 0);
+      product(C::COL_WX, act(round), FW / 16, col_gi, 0);
       ++round;
       arm(round, (uint32_t)(K * D * 2));
       product_wait(1);  // gh
@@ -951,9 +1061,13 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
 // ([rank][block][word][128 rows]) so that the main kernel's row threads read them coalesced, plus the constants of the
 // folded LayerNorms (W LN(x) = rstd (W' x - mean c) + W beta, W' = W diag(gamma), c = row sums of the rounded W').
 // One warp per weight row.
-template <int D, int H, int CL>
-__global__ void __launch_bounds__(256) umma_prep_kernel(const ocrl_sa_weights w, uint32_t* __restrict__ words, float* __restrict__ consts) {
+// Factored pass (F > 0): the W_ih rows become W_ih'' = W_ih W_v (length F) and the W_q rows become the CTA's F / CL
+// rows of W_q'' = s W_k^T W_q (length D, LayerNorm folded as before): a folded row is sum_d coef[d] M[d][:].
+template <int D, int H, int CL, int F>
+__global__ void __launch_bounds__(256) umma_prep_kernel(const ocrl_sa_weights w, const float* __restrict__ wk, const float* __restrict__ wv,
+                                                        uint32_t* __restrict__ words, float* __restrict__ consts) {
   constexpr int DS = D / CL, HS = H / CL, LX = D > H ? D : H, WPB = LX / 2;
+  constexpr int FS = F / CL;
   constexpr int RX = 3 * DS + HS + DS, RY = 3 * DS + DS;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (gw >= CL * 2 * 128) return;
@@ -962,12 +1076,24 @@ __global__ void __launch_bounds__(256) umma_prep_kernel(const ocrl_sa_weights w,
   const float* gam = nullptr;
   const float* bet = nullptr;
   int len = 0, fold = 0;
+  // folded rows: row = cscale * sum_d coef[d * cstride] * mat[d * mstride + :]
+  const float* coef = nullptr;
+  const float* mat = nullptr;
+  int cstride = 0, mstride = 0;
+  float cscale = 1.f;
   if (blk == 0) {
-    if (r < 3 * DS) { src = w.w_ih + ((size_t)(r / DS) * D + rank * DS + r % DS) * D; len = D; }
+    if (F > 0 && r < 3 * DS) { coef = w.w_ih + ((size_t)(r / DS) * D + rank * DS + r % DS) * D; cstride = 1; mat = wv; mstride = F; len = F; }
+    else if (r < 3 * DS) { src = w.w_ih + ((size_t)(r / DS) * D + rank * DS + r % DS) * D; len = D; }
     else if (r < 3 * DS + HS) { src = w.w1 + ((size_t)rank * HS + (r - 3 * DS)) * D; len = D; fold = 1; gam = w.ln_mlp_w; bet = w.ln_mlp_b; }
     else if (r < RX) { src = w.w2 + ((size_t)rank * DS + (r - 3 * DS - HS)) * H; len = H; }
   } else {
     if (r < 3 * DS) { src = w.w_hh + ((size_t)(r / DS) * D + rank * DS + r % DS) * D; len = D; }
+    else if (F > 0) {
+      if (r < 3 * DS + FS) {
+        coef = wk + rank * FS + (r - 3 * DS); cstride = F; mat = w.wq; mstride = D; len = D; cscale = rsqrtf((float)D);
+        fold = 2; gam = w.ln_slots_w; bet = w.ln_slots_b;
+      }
+    }
     else if (r < RY) { src = w.wq + ((size_t)rank * DS + (r - 3 * DS)) * D; len = D; fold = 2; gam = w.ln_slots_w; bet = w.ln_slots_b; }
   }
   uint32_t* dst = words + ((size_t)(rank * 2 + blk) * WPB) * 128 + r;
@@ -976,7 +1102,18 @@ __global__ void __launch_bounds__(256) umma_prep_kernel(const ocrl_sa_weights w,
     const int f = 2 * (w0 + lane);
     float2 x = make_float2(0.f, 0.f);
     if (f < len) {
-      x = __ldg(reinterpret_cast<const float2*>(src + f));
+      if (coef != nullptr) {
+        float ax = 0.f, ay = 0.f;
+        for (int d = 0; d < D; ++d) {
+          const float c = __ldg(coef + (size_t)d * cstride);
+          const float2 m = __ldg(reinterpret_cast<const float2*>(mat + (size_t)d * mstride + f));
+          ax = fmaf(c, m.x, ax);
+          ay = fmaf(c, m.y, ay);
+        }
+        x = make_float2(ax * cscale, ay * cscale);
+      } else {
+        x = __ldg(reinterpret_cast<const float2*>(src + f));
+      }
       if (fold) {
         const float2 g = __ldg(reinterpret_cast<const float2*>(gam + f)), b = __ldg(reinterpret_cast<const float2*>(bet + f));
         bsum = fmaf(x.x, b.x, fmaf(x.y, b.y, bsum));
@@ -1005,10 +1142,18 @@ static size_t umma_prep_bytes() {
   return (size_t)CL * 2 * (LX / 2) * 128 * 4 + (size_t)CL * (2 * (H / CL) + 2 * (D / CL)) * 4;
 }
 
-template <int D, int H, int CL, int NL, int KB, int NKS, int NVS, int NWB, int NUS, int DEFER = 0>
+template <int D, int H, int CL, int NL, int KB, int NKS, int NVS, int NWB, int NUS, int DEFER = 0, int F = 0>
 static int launch_umma(const IterFwdArgs& a_in, cudaStream_t stream) {
-  using C = Cfg<D, H, CL, NL, KB, NKS, NVS, NWB, NUS, DEFER>;
+  using C = Cfg<D, H, CL, NL, KB, NKS, NVS, NWB, NUS, DEFER, F>;
   IterFwdArgs a = a_in;
+  if (C::XH) {
+    if (a.saved != nullptr || a.xhat == nullptr || a.wk == nullptr || a.wv == nullptr) {
+      set_error("sa_iter_fwd(tcgen05, factored): inference only (saved == NULL), needs x^, W_k, W_v");
+      return OCRL_E_SHAPE;
+    }
+    a.k = a.xhat;  // one stream of tiles: the kernel reads `k` only
+    a.v = a.xhat;
+  }
   if (a.workspace == nullptr || a.workspace_bytes < umma_prep_bytes<D, H, CL>() + 4096 + 256) {
     set_error("sa_iter_fwd(tcgen05): needs the workspace of ocrl_sa_query_workspace (bf16 weight copies)");
     return OCRL_E_SHAPE;
@@ -1018,17 +1163,17 @@ static int launch_umma(const IterFwdArgs& a_in, cudaStream_t stream) {
     a.wprep = reinterpret_cast<uint32_t*>(base);
     a.wprep_consts = reinterpret_cast<float*>(base + (size_t)CL * 2 * C::WPB * 128 * 4);
     if (!a.prepared) {
-      umma_prep_kernel<D, H, CL><<<CL * 2 * 128 / 8, 256, 0, stream>>>(a.w, const_cast<uint32_t*>(a.wprep), const_cast<float*>(a.wprep_consts));
+      umma_prep_kernel<D, H, CL, F><<<CL * 2 * 128 / 8, 256, 0, stream>>>(a.w, a.wk, a.wv, const_cast<uint32_t*>(a.wprep), const_cast<float*>(a.wprep_consts));
       ocrl::count_launch();
       OCRL_CHECK_CUDA(cudaGetLastError());
     }
   }
-  auto kern = sa_iter_fwd_umma_kernel<D, H, CL, NL, KB, NKS, NVS, NWB, NUS, DEFER>;
+  auto kern = sa_iter_fwd_umma_kernel<D, H, CL, NL, KB, NKS, NVS, NWB, NUS, DEFER, F>;
   static_assert(C::SMEM_BYTES <= 227 * 1024, "shared memory budget");
   CUtensorMap tm_k, tm_v;
   const uint64_t rows = (uint64_t)a.B * a.N;
-  if (!tc::make_map_bf16_sw128(&tm_k, a.k, D, rows, (uint64_t)D * 2, C::HT) ||
-      !tc::make_map_bf16_sw128(&tm_v, a.v, D, rows, (uint64_t)D * 2, C::HT)) {
+  if (!tc::make_map_bf16_sw128(&tm_k, a.k, C::FW, rows, (uint64_t)C::FW * 2, C::HT) ||
+      !tc::make_map_bf16_sw128(&tm_v, a.v, C::FW, rows, (uint64_t)C::FW * 2, C::HT)) {
     set_error("sa_iter_fwd(tcgen05): cuTensorMapEncodeTiled failed");
     return OCRL_E_LAUNCH;
   }
@@ -1080,6 +1225,22 @@ extern "C" void ocrl_dev_iter_variant(int v) { g_dev_variant = v; }  // developm
 int sa_iter_fwd_umma_dispatch(const IterFwdArgs& a, cudaStream_t s) {
   if (a.K > 16) {
     set_error("sa_iter_fwd(tcgen05): K <= 16");
+    return OCRL_E_SHAPE;
+  }
+  if (a.xhat != nullptr) {  // factored pass (inference)
+    if (a.D == 192 && a.H == 192 && a.F == 64) {
+      // five images in flight per cluster, three update streams (768 threads).  Measured at B = 64, N = 4096, K = 6, T = 3
+      // (graph replays, us; lanes / streams): 3 / 2: 77.0, 5 / 3: 69.5, 5 / 4: 73.4
+      if (a.K <= 6) {
+        if (g_dev_variant == 2) return umma::launch_umma<192, 192, 8, 3, 6, 8, 8, 2, 2, 0, 64>(a, s);
+        if (g_dev_variant == 3) return umma::launch_umma<192, 192, 8, 5, 6, 8, 8, 2, 4, 0, 64>(a, s);
+        return umma::launch_umma<192, 192, 8, 5, 6, 8, 8, 2, 3, 0, 64>(a, s);
+      }
+      if (a.K <= 8) return umma::launch_umma<192, 192, 8, 5, 8, 8, 8, 2, 3, 0, 64>(a, s);
+      if (a.K <= 12) return umma::launch_umma<192, 192, 8, 3, 12, 6, 6, 2, 2, 0, 64>(a, s);
+      return umma::launch_umma<192, 192, 8, 3, 16, 6, 6, 2, 2, 0, 64>(a, s);
+    }
+    set_error("sa_iter_fwd(tcgen05, factored): D=%d H=%d C_in=%d not instantiated", a.D, a.H, a.F);
     return OCRL_E_SHAPE;
   }
   if (a.D == 192 && a.H == 192) {

@@ -41,6 +41,11 @@ struct IterFwdArgs {
   int max_clusters = 0;  // ocrl_sa_launch_opts: cap on the resident clusters of the persistent kernels (0 = launcher's choice)
   int lanes = 0;         // ocrl_sa_launch_opts: images in flight per cluster (0 = default)
   int prepared = 0;      // ocrl_sa_launch_opts: the workspace already holds the prepared weights
+  // factored pass (ocrl_sa_iter_fwd_xhat): the normalised tokens x^ [B,N,F] bf16 and the projections they stand for
+  const void* xhat = nullptr;
+  const float* wk = nullptr;  // project_k.weight [D,F]
+  const float* wv = nullptr;  // project_v.weight [D,F]
+  int F = 0;
 };
 
 // out[j*ldo + out_off + row] = dot(W[row0+row, 0:L], vec[j, 0:L]) for row < nrows, j < KP.

@@ -28,6 +28,10 @@ SA_PARAM_ORDER = [
 
 _KV_DTYPES = {"fp32": (abi.DT_F32, torch.float32), "bf16": (abi.DT_BF16, torch.bfloat16)}
 
+# Inference in the bf16 / tensor-core mode streams the normalised tokens x^ instead of k, v wherever the factored kernels
+# cover the shape (ocrl_xhat_fwd + ocrl_sa_iter_fwd_xhat, include/ocrl_sa.h); False keeps the k/v form (A/B, cross-checks)
+FACTORED = True
+
 # The projection backward from the low-rank coefficients (ocrl_kv_proj_bwd_lowrank); False: dk, dv + ocrl_kv_proj_bwd
 LOWRANK_BWD = True
 
@@ -100,8 +104,10 @@ def _sa_weights(p: Dict[str, Tensor]) -> abi.SaWeights:
 
 
 def kv_project(x: Tensor, p: Dict[str, Tensor], *, kv: str = "fp32", enc: Optional[Dict[str, Tensor]] = None,
-               pos_table: Optional[Tensor] = None, want_y: bool = False, ln_eps: float = 1e-5):
+               pos_table: Optional[Tensor] = None, want_y: bool = False, ln_eps: float = 1e-5, xhat_only: bool = False):
     """Token stage: [pos add + NCHW->tokens] -> [LN+MLP of the encoder] -> norm_inputs -> k, v.
+    ``xhat_only`` (bf16 / tensor-core mode): stop after norm_inputs and return (x^ [B,N,C] bf16, None, y) -- the input
+    of the factored loop (``iterate_xhat``).
 
     x: [B,N,C] tokens, or a CNN feature map [B,C,H,W] (NCHW-contiguous fp32, or channels-last fp32 / bf16,
     whose memory already is token-major); ``pos_table`` ([C,H*W]) is added to every image's tokens.
@@ -141,8 +147,10 @@ def kv_project(x: Tensor, p: Dict[str, Tensor], *, kv: str = "fp32", enc: Option
     ws = None
     if dims.math_mode == abi.MATH_TENSOR:  # bf16 weight copies for the tcgen05 kernel
         ws = torch.empty(abi.lib().ocrl_kv_proj_fwd_workspace(ctypes.byref(dims)), device=x.device, dtype=torch.uint8)
-    k = torch.empty(B, N, D, device=x.device, dtype=dt)
-    v = torch.empty(B, N, D, device=x.device, dtype=dt)
+    if xhat_only and dims.math_mode != abi.MATH_TENSOR:
+        raise RuntimeError("kv_project(xhat_only): the factored form belongs to the bf16 / tensor-core mode")
+    k = torch.empty((B, N, C) if xhat_only else (B, N, D), device=x.device, dtype=dt)
+    v = None if xhat_only else torch.empty(B, N, D, device=x.device, dtype=dt)
     y = torch.empty(B, N, C, device=x.device, dtype=torch.float32) if want_y else None
     keep = {n: _f32c(p[n]) for n in ("norm_inputs.weight", "norm_inputs.bias", "project_k.weight", "project_v.weight")}
     tw = dict(in_ln_w=keep["norm_inputs.weight"], in_ln_b=keep["norm_inputs.bias"],
@@ -153,6 +161,11 @@ def kv_project(x: Tensor, p: Dict[str, Tensor], *, kv: str = "fp32", enc: Option
         tw.update(enc_ln_w=e["layer_norm.weight"], enc_ln_b=e["layer_norm.bias"], mlp_w1=e["mlp.0.weight"],
                   mlp_b1=e["mlp.0.bias"], mlp_w2=e["mlp.2.weight"], mlp_b2=e["mlp.2.bias"])
     w = abi.token_weights(**tw)
+    if xhat_only:
+        with _timed("xhat_fwd"):
+            abi.check(abi.lib().ocrl_xhat_fwd(ctypes.byref(dims), abi.ptr(x), abi.ptr(pos_table), ctypes.byref(w),
+                                              abi.ptr(y), abi.ptr(k), abi.ptr(ws), abi.stream_ptr()), "ocrl_xhat_fwd")
+        return k, None, y
     with _timed("kv_proj_fwd"):
         abi.check(abi.lib().ocrl_kv_proj_fwd(ctypes.byref(dims), abi.ptr(x), abi.ptr(pos_table), ctypes.byref(w),
                                              abi.ptr(y), abi.ptr(k), abi.ptr(v), abi.ptr(ws), abi.stream_ptr()),
@@ -230,12 +243,67 @@ def iterate(k: Tensor, v: Tensor, slots0: Tensor, p: Dict[str, Tensor], num_iter
     return slots, attn, saved
 
 
+def factored_covers(C: int, D: int, H: int, K: int, kv: str, opts: Optional[abi.LaunchOpts] = None) -> bool:
+    """Shapes of the factored inference kernels (ocrl_sa_iter_fwd_xhat)."""
+    if opts is not None and opts.variant not in (abi.SA_AUTO, abi.SA_TCGEN05):
+        return False
+    return (kv == "bf16" and _math_mode(abi.DT_BF16) == abi.MATH_TENSOR and C == 64 and D == 192 and H == 192
+            and K <= 16)
+
+
+def iterate_xhat(xhat: Tensor, slots0: Tensor, p: Dict[str, Tensor], num_iterations: int, *, epsilon: float = 1e-8,
+                 ln_eps: float = 1e-5, want_attn: bool = True, opts: Optional[abi.LaunchOpts] = None,
+                 prepared: Optional[PreparedWeights] = None):
+    """The fused T-iteration loop in its factored form: streams x^ = norm_inputs(x) [B,N,C] bf16 instead of k, v and
+    applies project_k / project_v through folded update weights (include/ocrl_sa.h, ocrl_sa_iter_fwd_xhat).
+    Inference only.  Returns (slots, attn_vis or None)."""
+    _require_cuda(xhat, "iterate_xhat")
+    B, N, C = xhat.shape
+    K, D = slots0.shape[1], slots0.shape[2]
+    H = p["mlp.0.weight"].shape[0]
+    dims = abi.make_dims(B, N, C, D, H, K, num_iterations, eps=epsilon, ln_eps=ln_eps, kv_dtype=abi.DT_BF16,
+                         math_mode=abi.MATH_TENSOR)
+    pw = {n: _f32c(p[n]) for n in SA_PARAM_ORDER if n in p}
+    slots0 = _f32c(slots0)
+    slots = torch.empty(B, K, D, device=xhat.device, dtype=torch.float32)
+    attn = torch.empty(B, N, K, device=xhat.device, dtype=torch.float32) if want_attn else None
+    if opts is None:
+        opts = _LAUNCH_OPTS.get()
+    fwd_ws, _, _ = abi.query_workspace(dims)
+    o = opts if opts is not None else abi.launch_opts()
+    if prepared is not None:
+        shape_key = ("xhat", B, N, K, num_iterations, D, H, C, o.max_clusters, o.lanes)
+        ws, ready = prepared.lookup(pw, shape_key, fwd_ws, xhat.device)
+    else:
+        ws, ready = torch.empty(fwd_ws, device=xhat.device, dtype=torch.uint8), False
+    opts = abi.LaunchOpts(o.variant, o.max_clusters, o.lanes, o.strict, o.trace, int(ready))
+    w = _sa_weights(pw)
+    with _timed("sa_iter_fwd"):
+        abi.check(abi.lib().ocrl_sa_iter_fwd_xhat(ctypes.byref(dims), abi.ptr(xhat), abi.ptr(pw["project_k.weight"]),
+                                                  abi.ptr(pw["project_v.weight"]), abi.ptr(slots0), ctypes.byref(w),
+                                                  abi.ptr(slots), abi.ptr(attn), abi.ptr(ws), ctypes.byref(opts),
+                                                  abi.stream_ptr()), "ocrl_sa_iter_fwd_xhat")
+    return slots, attn
+
+
 def slot_attention(inputs: Tensor, slots0: Tensor, p: Dict[str, Tensor], num_iterations: int, *,
                    epsilon: float = 1e-8, kv: str = "fp32", enc: Optional[Dict[str, Tensor]] = None,
                    pos_table: Optional[Tensor] = None, want_attn: bool = True,
                    opts: Optional[abi.LaunchOpts] = None,
-                   prepared: Optional[PreparedWeights] = None) -> Tuple[Tensor, Optional[Tensor]]:
-    """Inference-only SlotAttention.forward (no autograd graph)."""
+                   prepared: Optional[PreparedWeights] = None,
+                   factored: Optional[bool] = None) -> Tuple[Tensor, Optional[Tensor]]:
+    """Inference-only SlotAttention.forward (no autograd graph).  ``factored``: None = the module default ``FACTORED``
+    wherever the factored kernels cover the shape; False = the k/v form."""
+    if factored is None:
+        factored = FACTORED
+    if opts is None:
+        opts = _LAUNCH_OPTS.get()
+    C = p["project_k.weight"].shape[1]
+    D, H = p["project_q.weight"].shape[0], p["mlp.0.weight"].shape[0]
+    if factored and factored_covers(C, D, H, slots0.shape[1], kv, opts):
+        xhat, _, _ = kv_project(inputs, p, kv=kv, enc=enc, pos_table=pos_table, xhat_only=True)
+        return iterate_xhat(xhat, slots0, p, num_iterations, epsilon=epsilon, want_attn=want_attn, opts=opts,
+                            prepared=prepared)
     k, v, _ = kv_project(inputs, p, kv=kv, enc=enc, pos_table=pos_table)
     slots, attn, _ = iterate(k, v, slots0, p, num_iterations, epsilon=epsilon, want_attn=want_attn, opts=opts,
                              prepared=prepared)

@@ -1,4 +1,4 @@
-"""Streamed encode throughput for explicit (lanes, max_clusters) of the iteration kernel (development aid)."""
+"""Streamed encode throughput over the cluster cap of the iteration kernel and the batches in flight (development aid)."""
 import os
 import sys
 import time
@@ -17,16 +17,17 @@ model.to("cuda")
 model.eval()
 pool = synth.to_obs(torch.from_numpy(synth.random_objs_frames(8 * B, 64, seed=1))).contiguous().cuda()
 outs = [torch.empty(B, 6, 192, device="cuda") for _ in range(3)]
-for lanes, ncl in [(0, 0), (3, 6), (3, 7), (2, 0), (2, 8), (2, 10), (2, 11), (2, 13), (2, 15)]:
-    model._module._slotattn.slot_attention.launch_opts = abi.launch_opts(lanes=lanes, max_clusters=ncl) if (lanes or ncl) else None
-    enc = ocrl_b200.StreamedEncoder(model, pool[:B], iter_clusters=None)
+for buffers, ncl in [(3, "auto"), (3, None), (3, 13), (3, 10), (3, 8), (3, 5), (4, None), (4, 10), (2, None)]:
+    enc = ocrl_b200.StreamedEncoder(model, pool[:B], iter_clusters=ncl, buffers=buffers)
+    outs = [torch.empty(B, 6, 192, device="cuda") for _ in range(buffers)]
     n = 3000
     for i in range(50):
-        enc.submit(pool[(i % 8) * B:(i % 8 + 1) * B], outs[i % 3])
+        enc.submit(pool[(i % 8) * B:(i % 8 + 1) * B], outs[i % buffers])
     enc.synchronize()
     t0 = time.perf_counter()
     for i in range(n):
-        enc.submit(pool[(i % 8) * B:(i % 8 + 1) * B], outs[i % 3])
+        enc.submit(pool[(i % 8) * B:(i % 8 + 1) * B], outs[i % buffers])
     enc.synchronize()
     dt = time.perf_counter() - t0
-    print(f"lanes {lanes} max_clusters {ncl}: {B * n / dt:.0f} images/s")
+    print(f"buffers {buffers} iter_clusters {ncl} (resolved {enc.iter_clusters}): {B * n / dt:.0f} images/s", flush=True)
+    del enc

@@ -1,4 +1,4 @@
-"""Timeline of the tcgen05 iteration kernel (clock64 of CTA 0).   python scripts/trace_umma.py [B] [lanes]"""
+"""Timeline of the tcgen05 iteration kernel (clock64 of CTA 0).   python scripts/trace_umma.py [B] [lanes] [xhat]"""
 import os
 import sys
 
@@ -10,6 +10,7 @@ from oracle import slot_oracle as so  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 lanes = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+XHAT = len(sys.argv) > 3 and sys.argv[3] == "xhat"  # the factored form (ocrl_sa_iter_fwd_xhat)
 N, K, T, D = 4096, 6, 3, 192
 p = {k: v.cuda() for k, v in so.random_sa_params(K, 64, D, D, seed=3).items()}
 x = torch.randn(B, N, 64, device="cuda"); s0 = torch.randn(B, K, D, device="cuda")
@@ -18,8 +19,19 @@ dims = abi.make_dims(B, N, 64, D, D, K, T, kv_dtype=abi.DT_BF16, math_mode=abi.M
 nbytes = abi.query_workspace(dims)[0]
 ws = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
 opts = abi.launch_opts(variant="tcgen05", lanes=lanes, strict=True, trace=True)
-for _ in range(3):
-    F.iterate(k, v, s0, p, T, _workspace=ws, opts=opts)
+if XHAT:
+    import ctypes
+    xh, _, _ = F.kv_project(x, p, kv="bf16", xhat_only=True)
+    slots = torch.empty(B, K, D, device="cuda"); attn = torch.empty(B, N, K, device="cuda")
+    w = F._sa_weights(p)
+    abi.lib().ocrl_dev_iter_variant(int(os.environ.get("QV", 0)))
+    for _ in range(3):
+        abi.check(abi.lib().ocrl_sa_iter_fwd_xhat(ctypes.byref(dims), abi.ptr(xh), abi.ptr(p["project_k.weight"]),
+                                                  abi.ptr(p["project_v.weight"]), abi.ptr(s0), ctypes.byref(w), abi.ptr(slots),
+                                                  abi.ptr(attn), abi.ptr(ws), ctypes.byref(opts), abi.stream_ptr()), "xhat")
+else:
+    for _ in range(3):
+        F.iterate(k, v, s0, p, T, _workspace=ws, opts=opts)
 torch.cuda.synchronize()
 tr = ws[nbytes - 4096:].view(torch.int64).cpu().tolist()
 t0 = tr[0]
@@ -39,6 +51,7 @@ for pi in range(4):
     b = [x - base if x else -1 for x in tr[340 + pi * 12: 352 + pi * 12]]
     print(f" pair {pi}: softmax wait {b[0]} -> logits ready {b[1]} -> loaded {b[2]} -> softmax done {b[3]} -> w slot free {b[4]} -> w written {b[5]}"
           f" | issuer: logits begin {b[6]} issued {b[7]} ; U begin {b[8]} w ready {b[9]} issued {b[10]}")
+print("op 2 end (factored): pairs done %d -> token sums reduced %d -> drain begin %d -> stream's buffers free %d" % tuple(tr[340 + 12 * i + 11] - base for i in range(4)))
 print("producers (op 2 half tiles): k [wait begin, slot free] v [wait begin, slot free]")
 for j in range(8):
     b = [x - base if x else -1 for x in tr[400 + j * 4: 404 + j * 4]]

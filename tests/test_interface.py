@@ -76,7 +76,7 @@ def test_abi_exports_every_declared_symbol():
     assert declared == set(abi.EXPORTS), declared ^ set(abi.EXPORTS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.ocrl_version() == 5 and lib.ocrl_built_arch() == b"sm_100a"
+    assert lib.ocrl_version() == 6 and lib.ocrl_built_arch() == b"sm_100a"
     assert ctypes.sizeof(abi.SaDims) == 56 and ctypes.sizeof(abi.SaWeights) == 13 * 8
     assert ctypes.sizeof(abi.TokenWeights) == 10 * 8 and ctypes.sizeof(abi.LaunchOpts) == 24
 
