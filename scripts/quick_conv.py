@@ -54,14 +54,24 @@ def lib():
 
 
 flops = 2.0 * B * S * S * 64 * 64 * 25
-for v in (1, 2, 3):
+# reference of the padded layout: fp32 convolution of the same bf16 operands (+ bias, ReLU), zeros at the padding positions
+ain = a.view(-1, S + 4, 64)[2:].view(B, S + 2, S + 4, 64)[:, :S, 2:S + 2].permute(0, 3, 1, 2).float()
+ref = torch.relu(torch.nn.functional.conv2d(ain, w.to(torch.bfloat16).float(), bias, padding=2)).permute(0, 2, 3, 1)
+for v in (1, 2, 3, 4):  # 1: three tiles / four stages, 2: two tiles / eight stages, 3 / 4: paired taps (four / three stages)
     L.ocrl_dev_conv_variant(v)
     try:
+        b.fill_(7.0)
+        own()
+        torch.cuda.synchronize()
+        got = b.view(-1, S + 4, 64)[2:].view(B, S + 2, S + 4, 64)
+        inner = got[:, :S, 2:S + 2].float()
+        err = float((inner - ref).norm() / ref.norm())
+        pad_zero = float(b.float().abs().sum() - inner.abs().sum())
         tv = timeit(own)
-        print(json.dumps({"variant": v, "own_us": round(tv * 1e3, 1)}))
+        print(json.dumps({"variant": v, "own_us": round(tv * 1e3, 1), "rel_err": err, "padding_abs_sum": pad_zero}), flush=True)
     except RuntimeError as e:
         print("variant", v, "failed:", str(e)[:100])
-L.ocrl_dev_conv_variant(0)
+L.ocrl_dev_conv_variant(int(os.environ.get("QCV", 0)))
 t_own, t_lib = timeit(own), timeit(lib)
 print(json.dumps({"B": B, "size": S, "own_us": round(t_own * 1e3, 1), "cudnn_us": round(t_lib * 1e3, 1),
                   "own_tflops": round(flops / t_own / 1e9, 1), "cudnn_tflops": round(flops / t_lib / 1e9, 1),

@@ -20,7 +20,9 @@ def _to_padded(x):  # [B,64,H,W] float -> padded channels-last bf16 array
     return buf.view(-1, C)
 
 
-@pytest.mark.parametrize("B,H,W", [(1, 8, 32), (3, 32, 32), (2, 64, 64), (5, 64, 64), (1, 128, 128), (2, 6, 64)])
+# (from ~300 tiles up the launcher takes the paired-tap kernel: two filter taps per N = 128 instruction, tiles of 127 positions)
+@pytest.mark.parametrize("B,H,W", [(1, 8, 32), (3, 32, 32), (2, 64, 64), (5, 64, 64), (1, 128, 128), (2, 6, 64),
+                                   (9, 64, 64), (20, 64, 64), (40, 32, 32), (33, 24, 32)])
 @pytest.mark.parametrize("relu", [0, 1])
 def test_conv5x5_matches_torch(B, H, W, relu):
     """bf16 operands, fp32 accumulation: compare with torch's conv2d on the same bf16-rounded operands in fp32."""

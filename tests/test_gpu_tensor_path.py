@@ -92,18 +92,19 @@ def test_tensor_core_iteration_kernel_on_exact_bf16_inputs():
 
 
 def test_bf16_full_size_properties():
-    """BASELINE size in bf16 mode: finite, rows sum to one, batch-permutation equivariant bit-exactly."""
+    """BASELINE size in bf16 mode, k/v form (the factored form has its own copy of this test): finite, rows sum to one,
+    batch-permutation equivariant bit-exactly."""
     from ocrl_b200 import functional as F
 
     torch.manual_seed(0)
     p = _cuda(so.random_sa_params(6, 64, 192, 192, seed=3))
     x = torch.randn(64, 4096, 64, device="cuda")
     s0 = torch.randn(64, 6, 192, device="cuda")
-    s, a = F.slot_attention(x, s0, p, 3, kv="bf16")
+    s, a = F.slot_attention(x, s0, p, 3, kv="bf16", factored=False)
     assert torch.isfinite(s).all() and torch.isfinite(a).all()
     assert torch.allclose(a.sum(-1), torch.ones(64, 4096, device="cuda"), atol=1e-4)
     perm = torch.randperm(64, device="cuda")
-    s2, a2 = F.slot_attention(x[perm].contiguous(), s0[perm].contiguous(), p, 3, kv="bf16")
+    s2, a2 = F.slot_attention(x[perm].contiguous(), s0[perm].contiguous(), p, 3, kv="bf16", factored=False)
     assert torch.equal(s2, s[perm]) and torch.equal(a2, a[perm])
     pc = {k: v.cpu() for k, v in p.items()}
     sr, ar = so.slot_attention(x[:2].cpu(), s0[:2].cpu(), pc, 3)
