@@ -449,6 +449,15 @@ def measure_train(a, dev, pool_dev, dist, rank, world, steps=8, warmup=3):
                       % a.batch}
 
 
+def step_mb(a, N, D, esz):
+    """MB of device buffers one encode step writes and reads back (bf16 mode: two padded channels-last feature maps,
+    x^ [N,64] bf16 (factored form), attention [N,K] fp32; fp32 mode: NCHW maps, k and v)"""
+    if a.mode == "bf16":
+        maps = 2 * (2 + a.batch * (a.size + 2)) * (a.size + 4) * 64 * 2
+        return (maps + a.batch * N * (64 * 2 + a.slots * 4)) / 1e6
+    return a.batch * N * (2 * 64 * 4 + 2 * D * esz + a.slots * 4) / 1e6
+
+
 def roofline_of(a, mode, events):
     it_ms = [s.elapsed_time(e) for name, s, e in events if name == "sa_iter_fwd"]
     tk_ms = [s.elapsed_time(e) for name, s, e in events if name in ("kv_proj_fwd", "xhat_fwd")]
@@ -460,7 +469,8 @@ def roofline_of(a, mode, events):
     esz = 2 if mode == "bf16" else 4
     bytes_img = 2 * N * D * esz + N * K * 4 + 2 * K * D * 4
     streamed_img = N * 64 * 2 + N * K * 4 + 2 * K * D * 4 if factored else bytes_img
-    tok_bytes_img = N * 64 * (2 if mode == "bf16" else 4) + (N * 64 * 2 if factored else 2 * N * D * esz)
+    tok_bytes_img = N * 64 * (2 if mode == "bf16" else 4) + 2 * N * D * esz   # reference formulation: tokens in, k and v out
+    tok_streamed_img = N * 64 * 2 + N * 64 * 2 if factored else tok_bytes_img   # factored: bf16 map in, x^ out
     peak, peak_src = HBM_FALLBACK_GBS, "fallback"
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -501,7 +511,8 @@ def roofline_of(a, mode, events):
                             if mode == "bf16" else "token_stage_kernel (fp32 FFMA)",
                             "avg_launch_ms": tk_avg, "achieved": tok_achieved, "unit": "GB/s",
                             "frac": (tok_achieved / peak if tok_achieved else None), "traffic": tok_traffic,
-                            "algorithmic_bytes_per_image": tok_bytes_img}}
+                            "algorithmic_bytes_per_image": tok_bytes_img, "streamed_bytes_per_image": tok_streamed_img,
+                            "frac_streamed": (a.batch * tok_streamed_img / (tk_avg * 1e-3) / 1e9 / peak if tk_ms else None)}}
 
 
 def run_sweep(a, dev, out):
@@ -526,25 +537,44 @@ def run_sweep(a, dev, out):
             p = {k: v.to(dev) for k, v in so.random_sa_params(K, 64, D, D, seed=3).items()}
             k, v, _ = F.kv_project(x, p, kv="bf16")
             s0 = torch.randn(B, K, D, device=dev)
+            xh, _, _ = F.kv_project(x, p, kv="bf16", xhat_only=True)
             for T in (3, 5, 7):
-                prep = F.PreparedWeights()
-                for _ in range(3):
-                    F.iterate(k, v, s0, p, T, prepared=prep)
-                torch.cuda.synchronize()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                reps = 10
-                e0.record()
-                for _ in range(reps):
-                    F.iterate(k, v, s0, p, T, prepared=prep)
-                e1.record()
-                torch.cuda.synchronize()
-                us = e0.elapsed_time(e1) / reps * 1e3
                 bytes_img = 2 * N * D * 2 + N * K * 4 + 2 * K * D * 4
-                gbs = B * bytes_img / us / 1e3
-                print(json.dumps({"sweep": "iteration kernel", "N": N, "K": K, "T": T, "D": D, "B": B, "kernel": F.last_kernel(),
-                                  "us": round(us, 1), "images_per_s": round(B / us * 1e6), "GBps": round(gbs, 1),
-                                  "frac_of_hbm": round(gbs / peak, 4), "streamed_GBps": round(T * B * 2 * N * D * 2 / us / 1e3, 1),
-                                  "algorithmic_bytes_per_image": bytes_img}), file=out, flush=True)
+                # both forms of the loop: "factored" (inference: streams x^, what SLATE.__call__ runs) and "k/v" (the
+                # training forward).  Ten launches replayed from one CUDA graph: no host time between the kernels
+                for form in ("factored", "k/v"):
+                    prep = F.PreparedWeights()
+                    if form == "factored":
+                        fn = lambda: F.iterate_xhat(xh, s0, p, T, prepared=prep)  # noqa: E731
+                    else:
+                        fn = lambda: F.iterate(k, v, s0, p, T, prepared=prep)  # noqa: E731
+                    reps = 10
+                    st = torch.cuda.Stream()
+                    with torch.cuda.stream(st):
+                        for _ in range(3):
+                            fn()
+                        st.synchronize()
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g, stream=st):
+                            for _ in range(reps):
+                                fn()
+                    kern = F.last_kernel()
+                    torch.cuda.synchronize()
+                    g.replay()
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    g.replay()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    us = e0.elapsed_time(e1) / reps * 1e3
+                    gbs = B * bytes_img / us / 1e3
+                    moved = (N * 64 * 2 if form == "factored" else 2 * N * D * 2)
+                    print(json.dumps({"sweep": "iteration kernel", "form": form, "N": N, "K": K, "T": T, "D": D, "B": B, "kernel": kern,
+                                      "us": round(us, 1), "images_per_s": round(B / us * 1e6), "GBps": round(gbs, 1),
+                                      "frac_of_hbm": round(gbs / peak, 4), "streamed_GBps": round(T * B * moved / us / 1e3, 1),
+                                      "algorithmic_bytes_per_image": bytes_img}), file=out, flush=True)
+                    del g
 
 
 def _claim_stdout():
@@ -624,11 +654,13 @@ def main():
                 "data": "synthetic",
                 "config": workload(a),
                 "notes": {"mode": a.mode,
-                          "l2": "k/v working set per step %.0f MB > 126 MB L2; frame pool of %d rotates"
-                                % (a.batch * 2 * N * D * esz / 1e6, a.pool),
+                          "l2": ("inputs larger than L2: a step touches %.0f MB of its own buffers (two padded feature maps, x^ or "
+                                 "k/v, attention) and the three graphs in flight own separate buffers (%.0f MB rotating > 126 MB L2); "
+                                 "frame pool of %d rotates"
+                                 % (step_mb(a, N, D, esz), 3 * step_mb(a, N, D, esz), a.pool)),
                           "kernels": "every kernel of the step is hand-written CUDA in libocrl_sa.so (bf16 mode: mma.sync first "
-                                     "convolution, tcgen05 implicit-GEMM 64->64 convolutions, tcgen05 token stage, tcgen05 "
-                                     "iteration kernel); torch only draws the slot noise" if a.mode == "bf16" else
+                                     "convolution, tcgen05 implicit-GEMM 64->64 convolutions with paired taps, tcgen05 token stage "
+                                     "(x^ output), tcgen05 iteration kernel in its factored form); torch only draws the slot noise" if a.mode == "bf16" else
                                      "fp32 parity mode: cuDNN convolutions (library), FFMA token stage and iteration kernel",
                           "launch": ("CUDA graph replays of SLATE.__call__, three batches in flight on three streams "
                                      "(single_stream_value: one replay at a time)") if main_res["graph"] else "eager launches",

@@ -1104,6 +1104,7 @@ __global__ void __launch_bounds__(256) umma_prep_kernel(const ocrl_sa_weights w,
     if (f < len) {
       if (coef != nullptr) {
         float ax = 0.f, ay = 0.f;
+#pragma unroll 8
         for (int d = 0; d < D; ++d) {
           const float c = __ldg(coef + (size_t)d * cstride);
           const float2 m = __ldg(reinterpret_cast<const float2*>(mat + (size_t)d * mstride + f));
@@ -1205,6 +1206,9 @@ static int launch_umma(const IterFwdArgs& a_in, cudaStream_t stream) {
   if (a.max_clusters > 0) ncl = max(1, min(ncl, a.max_clusters));
   int want = (a.B + NL - 1) / NL;  // NL lanes per cluster
   if (a.B <= ncl) want = a.B;      // clusters to spare: one image each (a lane's iterations are serial: sharing a cluster only adds latency)
+  // factored pass: a cluster's passes are serial and no longer hidden behind memory, so its time grows with its images --
+  // spread the batch over every cluster (B = 16 images of 16 384 tokens: 137 us on four clusters, 5 lanes each)
+  if (C::XH) want = a.B;
   if (ncl > want) ncl = want;
   {  // fewest clusters that keep the same number of image rounds (frees SMs for concurrent work)
     const int per = (a.B + ncl - 1) / ncl;
