@@ -117,6 +117,23 @@ def test_factored_loop_shapes(K, T, B, N):
     assert torch.isfinite(s).all() and torch.allclose(a.sum(-1), torch.ones_like(a.sum(-1)), atol=1e-4)
 
 
+def test_factored_loop_beyond_the_op_table():
+    """More ops per cluster than the kernel's op table holds (2048): the per-op bookkeeping falls back to divisions."""
+    from ocrl_b200 import abi, functional as F
+
+    B, N, K, T = 1500, 64, 4, 3   # two clusters: 750 images x 3 iterations = 2250 ops each
+    p = so.random_sa_params(K, 64, 192, 192, seed=21)
+    g = torch.Generator().manual_seed(9)
+    x, s0 = torch.randn(B, N, 64, generator=g), torch.randn(B, K, 192, generator=g)
+    s, a = F.slot_attention(x.cuda(), s0.cuda(), _cuda(p), T, kv="bf16", factored=True, opts=abi.launch_opts(max_clusters=2))
+    assert F.last_kernel() == "tcgen05_xhat"
+    idx = [0, 1, 749, 750, 1498, 1499]
+    s_ref, a_ref = so.slot_attention(x[idx], s0[idx], p, T)
+    assert rel_err(s[idx].cpu(), s_ref) < BF16_TOL and rel_err(a[idx].cpu(), a_ref) < BF16_TOL
+    s2, _ = F.slot_attention(x.cuda(), s0.cuda(), _cuda(p), T, kv="bf16", factored=True)  # table path, every cluster
+    assert torch.equal(s, s2)
+
+
 def test_factored_full_size_properties():
     """BASELINE size (B = 64, N = 4096, K = 6, T = 3): finite, rows sum to one, batch-permutation equivariant bit for
     bit, independent of the cluster cap, within tolerance of the oracle and of the k/v form."""
