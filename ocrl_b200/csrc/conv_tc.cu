@@ -98,6 +98,15 @@ conv5x5_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + CF::OFF_TMEM);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (p.trace != nullptr && blockIdx.x == 0 && tid == 0) p.trace[0] = clock64();
+  // every CTA: start / end on the global timer (ns), its SM (trace[128 + 4 b ..]): spread of the persistent CTAs
+  if (p.trace != nullptr && tid == 0) {
+    unsigned long long t;
+    unsigned smid;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    p.trace[128 + 4 * blockIdx.x] = (long long)t;
+    p.trace[128 + 4 * blockIdx.x + 2] = (long long)smid;
+  }
 
   if (tid < C) s_bias[tid] = p.bias ? __ldg(p.bias + tid) : 0.f;
   if (tid == 0) {
@@ -294,6 +303,12 @@ conv5x5_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
   }
   tc::fence_before();
   __syncthreads();
+  if (p.trace != nullptr && tid == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    p.trace[128 + 4 * blockIdx.x + 1] = (long long)t;
+    p.trace[128 + 4 * blockIdx.x + 3] = (long long)(t_end - t_begin);
+  }
   if (warp == 1) tc::tmem_dealloc<512>(tmem);
 }
 

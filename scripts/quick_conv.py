@@ -77,7 +77,7 @@ print(json.dumps({"B": B, "size": S, "own_us": round(t_own * 1e3, 1), "cudnn_us"
                   "own_tflops": round(flops / t_own / 1e9, 1), "cudnn_tflops": round(flops / t_lib / 1e9, 1),
                   "own_frac_of_1678": round(flops / t_own / 1e9 / 1678.2, 3)}))
 
-trace = torch.zeros(128, dtype=torch.int64, device=dev)
+trace = torch.zeros(128 + 4 * 148, dtype=torch.int64, device=dev)
 L.ocrl_dev_conv_trace(ctypes.c_void_p(trace.data_ptr()))
 own(); own()
 torch.cuda.synchronize()
@@ -91,3 +91,17 @@ for u in range(8):
         break
     print(f" unit {u}: issuer begin {r[0]-t0:7d} slab ready {r[1]-t0:7d} acc free {r[2]-t0:7d} issued {r[3]-t0:7d} (weight waits {r[4]:6d}) | "
           f"epilogue wait {r[5]-t0:7d} acc ready {r[6]-t0:7d} done {r[7]-t0:7d}")
+
+# spread of the persistent CTAs (global timer, ns): start and end relative to the earliest start
+ct = [tr[128 + 4 * b: 132 + 4 * b] for b in range(148) if tr[128 + 4 * b]]
+if ct:
+    t0g = min(c[0] for c in ct)
+    starts = sorted(c[0] - t0g for c in ct); ends = sorted(c[1] - t0g for c in ct)
+    print(f"CTAs {len(ct)}: start min/median/max {starts[0]} / {starts[len(ct) // 2]} / {starts[-1]} ns; end min/median/max {ends[0]} / {ends[len(ct) // 2]} / {ends[-1]} ns")
+    by_tiles = {}
+    for c in ct:
+        by_tiles.setdefault(c[3], []).append(c[1] - c[0])
+    for k in sorted(by_tiles):
+        v = sorted(by_tiles[k]); print(f"  {len(v)} CTAs with {k} tiles: duration min/median/max {v[0]} / {v[len(v) // 2]} / {v[-1]} ns")
+    slow = sorted(ct, key=lambda c: c[0] - c[1])[:6]
+    print("  slowest CTAs (sm, tiles, duration ns):", [(c[2], c[3], c[1] - c[0]) for c in slow])
