@@ -28,7 +28,7 @@ using namespace pc;
 #define TRACE_OP 2
 #endif
 
-template <int D_, int H_, int CL_, int NL_, int KB_, int NKS_, int NVS_, int NWB_, int NUS_, int DEFER_ = 0, int F_ = 0>
+template <int D_, int H_, int CL_, int NL_, int KB_, int NKS_, int NVS_, int NWB_, int NUS_, int DEFER_ = 0, int F_ = 0, int BT_ = 0>
 struct Cfg {
   // NL image lanes per cluster; KB rows in the slot-indexed buffers; NKS / NVS ring slots for k / v half tiles;
   // NWB buffers for the softmax weights of a 128-token pair
@@ -54,10 +54,15 @@ struct Cfg {
   // The factored pass is short (the softmax warps are its critical path), so an op's accumulator is read out of tensor
   // memory by the update stream that consumes it, not by the softmax warps
   static constexpr bool UDRAIN = XH;
-  static constexpr int NT = 256 + 32 * UWT, HT = 64, NCH = FW / 64;
+  // BT: 256-token steps of the factored pass.  One ring tile, one barrier round and one softmax step cover 256 tokens
+  // (two tokens per softmax thread, logits as two M = 128 products side by side in tensor memory): the per-step costs of
+  // the three pass roles (mbarrier waits ~100 cycles each, commits, fences) are paid once per 256 instead of per 128 tokens
+  static constexpr bool BT = BT_ != 0;
+  static_assert(!BT || XH, "256-token steps belong to the factored pass");
+  static constexpr int NT = 256 + 32 * UWT, HT = BT ? 256 : 64, NCH = FW / 64;
   static constexpr int LX = D > H ? D : H;
   static constexpr int CH_BYTES = HT * 128, HT_BYTES = NCH * CH_BYTES;  // one 64-wide feature chunk / one half tile
-  static constexpr int WH_BYTES = 2048, WP_BYTES = 2 * WH_BYTES;        // w tile of a half ([8][16 slots][8] bf16) / a pair
+  static constexpr int WH_BYTES = 2048, WP_BYTES = (BT ? 4 : 2) * WH_BYTES;  // w tile of 64 tokens ([8][16 slots][8] bf16) / of a step
   static constexpr int OPD_BYTES = D * 2 * KS, OPX_BYTES = LX * 2 * KS;  // activation operands [features/8][KS slots][8] bf16
   static constexpr int DS = D / CL, HS = H / CL;
   // weight blocks in tensor memory (row = lane): X = W_ih (3 DS rows) | W1' (HS) | W2 (DS);  Y = W_hh (3 DS) | Wq' (DS)
@@ -70,8 +75,9 @@ struct Cfg {
   // Tensor memory columns: two logit buffers, two U accumulators (features 0-127 | 128-191), the update engine's two
   // accumulators, the weight blocks (a column holds two bf16: K features take K / 2 columns).  (No need to spread a
   // product over several accumulators: back-to-back MMAs into the same columns issue at full rate, scripts/umma_time.cu.)
-  static constexpr uint32_t COL_LG = 0, LG_STRIDE = 16, COL_U = 32, U_STRIDE = 32, U_B = 16, COL_GI = 96, COL_GH = 112;
-  static constexpr uint32_t COL_WX = 128, COL_WY = COL_WX + LX / 2, TMEM_COLS = 512;
+  static constexpr uint32_t COL_LG = 0, LG_STRIDE = BT ? 32 : 16, COL_U = 2 * LG_STRIDE, U_STRIDE = 32, U_B = 16;
+  static constexpr uint32_t COL_GI = COL_U + 64, COL_GH = COL_GI + 16;
+  static constexpr uint32_t COL_WX = COL_GH + 16, COL_WY = COL_WX + LX / 2, TMEM_COLS = 512;
   static constexpr uint32_t COL_GI2 = COL_WY + D / 2, COL_GH2 = COL_GI2 + 16;  // accumulators of the update streams 1, 2, ...: 32 columns each
   static_assert(COL_GI2 + 32 * (NUS - 1) <= 512, "tensor memory");
 
@@ -106,10 +112,10 @@ struct Cfg {
 // barrier of one update stream (ids 1, 2)
 __device__ __forceinline__ void upd_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-template <int D, int H, int CL, int NL, int KB, int NKS, int NVS, int NWB, int NUS, int DEFER, int F>
+template <int D, int H, int CL, int NL, int KB, int NKS, int NVS, int NWB, int NUS, int DEFER, int F, int BT>
 __global__ void __launch_bounds__((NUS <= 2 ? 512 : 256 + 128 * NUS), 1)
 sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v) {
-  using C = Cfg<D, H, CL, NL, KB, NKS, NVS, NWB, NUS, DEFER, F>;
+  using C = Cfg<D, H, CL, NL, KB, NKS, NVS, NWB, NUS, DEFER, F, BT>;
   constexpr int DS = C::DS, HS = C::HS, UP = C::UP, HT = C::HT, NCH = C::NCH, UW = C::UW, UT = C::UT, KS = C::KS;
   constexpr int FW = C::FW, FS = C::FS;
   constexpr bool XH = C::XH;
@@ -243,7 +249,7 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
   const int TPC = (ntiles + CL - 1) / CL;
   const int tile0 = rank * TPC;
   const int TP = max(0, min(TPC, ntiles - tile0));  // half tiles of this CTA per pass
-  const int NP = (TP + 1) / 2;                       // 128-token pairs
+  const int NP = C::BT ? TP : (TP + 1) / 2;          // steps per pass: 128-token pairs (256-token tiles with BT)
   const int total_ht = total_ops * TP;
 
   // TMA producers (warp 4: k ring, warp 6: v ring).  The whole warp walks the half-tile stream of the CTA (ops in
@@ -507,6 +513,75 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
           const uint32_t lb = gp & 1, wb = gp % NWB;
           const bool tt = tracer && tid == 0 && n == TRACE_OP && p < 4;
           if (tt) a.trace[340 + p * 12 + 0] = clock64();
+          if (C::BT) {
+            // ---- 256-token step: this thread's two tokens are rows 32 w + lane and 128 + 32 w + lane of the tile; their
+            // logits sit side by side in the thread's tensor-memory lane (columns [0, KS) and [16, 16 + KS) of the buffer)
+            mbar_wait(&lg_full[lb], (gp >> 1) & 1);
+            if (tt) a.trace[340 + p * 12 + 1] = clock64();
+            if (tid == 0 && p == 0 && n < 40) PP_TRACE(8 + n * 8);
+            tc::fence_after();
+            uint32_t r[32];
+            tc::tmem_ld32_nowait(tlane + C::COL_LG + C::LG_STRIDE * lb, r);
+            tc::tmem_ld_wait();
+            tc::fence_before();
+            __syncwarp();
+            if (lane == 0) tc::arrive(&lg_empty[lb]);
+            if (tt) a.trace[340 + p * 12 + 2] = clock64();
+            const int tp = warp * 32 + lane;
+            float xs[2][KS];
+            bool ok[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int tok = (tile0 + p) * HT + 128 * h + tp;
+              ok[h] = tok < N;
+              float mx = -INFINITY;
+#pragma unroll
+              for (int i = 0; i < KS; ++i) {
+                xs[h][i] = (i < K) ? __uint_as_float(r[16 * h + i]) : -INFINITY;
+                mx = fmaxf(mx, xs[h][i]);
+              }
+              float sum = 0.f;
+#pragma unroll
+              for (int i = 0; i < KS; ++i) {
+                xs[h][i] = ex2f(xs[h][i] - mx);
+                sum += xs[h][i];
+              }
+              const float inv = __fdividef(1.f, sum);
+#pragma unroll
+              for (int i = 0; i < KS; ++i) xs[h][i] *= inv;
+              if (last && a.attn_out != nullptr && ok[h]) {
+                float* ao = a.attn_out + ((size_t)img * N + tok) * K;
+                if ((K & 1) == 0) {
+#pragma unroll
+                  for (int i = 0; i < KS; i += 2)
+                    if (i < K) __stcs(reinterpret_cast<float2*>(ao + i), make_float2(xs[h][i], xs[h][i + 1]));
+                } else {
+#pragma unroll
+                  for (int i = 0; i < KS; ++i)
+                    if (i < K) __stcs(ao + i, xs[h][i]);
+                }
+              }
+            }
+            if (tt) a.trace[340 + p * 12 + 3] = clock64();
+            if (gp >= (uint32_t)NWB) mbar_wait(&w_empty[wb], ((gp / NWB) - 1) & 1);
+            if (tt) a.trace[340 + p * 12 + 4] = clock64();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              unsigned char* wrow = wtiles + wb * C::WP_BYTES + (2 * h + (tp >> 6)) * C::WH_BYTES + ((tp & 63) >> 3) * 256 + (tp & 7) * 2;
+#pragma unroll
+              for (int i = 0; i < KS; ++i) {
+                const float wv = (ok[h] && i < K) ? xs[h][i] + a.eps : 0.f;
+                const __nv_bfloat16 wq = __float2bfloat16_rn(wv);
+                *reinterpret_cast<__nv_bfloat16*>(wrow + i * 16) = wq;
+                Sl[i] += __bfloat162float(wq);
+              }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) tc::arrive(&w_full[wb]);
+            if (tt) a.trace[340 + p * 12 + 5] = clock64();
+            continue;
+          }
           mbar_wait(&lg_full[lb], (gp >> 1) & 1);
           if (tt) a.trace[340 + p * 12 + 1] = clock64();
           if (tid == 0 && p == 0 && n < 40) PP_TRACE(8 + n * 8);
@@ -623,6 +698,28 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
             mbar_wait(&lg_empty[lb], ((gp >> 1) - 1) & 1);
             tc::fence_after();
           }
+          if (C::BT) {  // one 256-token tile: two M = 128 products (N = 16: with 8 slot columns the second group aliases the first)
+            constexpr uint32_t ID_LG2 = tc::idesc_bf16(128, 16);
+            const int s = jk % NKS;
+            mbar_wait(&k_full[s], (uint32_t)((jk / NKS) & 1));
+            tc::fence_after();
+            const uint32_t ka = smem_u32(kring + (size_t)s * C::HT_BYTES);
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                if (leader)
+                  tc::mma_bf16(tmem + C::COL_LG + C::LG_STRIDE * lb + 16 * m, tc::smem_desc(ka + m * (128 * 128) + ks * 32, 16, 1024, tc::SW_128),
+                               tc::smem_desc(qa + ks * (32 * KS), 16 * KS, KS == 16 ? 128 : 0, tc::SW_NONE), ID_LG2, ks != 0);
+            if (leader) {
+              tc::commit(&k_empty[s]);
+              tc::commit(&lg_full[lb]);
+            }
+            __syncwarp();
+            ++jk;
+            if (tn && p < 4) a.trace[340 + p * 12 + 7] = clock64();
+            continue;
+          }
           for (int h = 0; h < 2 && 2 * p + h < TP; ++h) {
             const int s = jk % NKS;
             mbar_wait(&k_full[s], (uint32_t)((jk / NKS) & 1));
@@ -665,6 +762,26 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
           if (p == 0 && n >= 2) {  // the accumulator was last used by op n - 2
             mbar_wait(&u_accfree[n & 1], (uint32_t)(((n >> 1) - 1) & 1));
             tc::fence_after();
+          }
+          if (C::BT) {  // 256 tokens = 16 K steps on one ring tile and one w tile
+            const int s = jv % NVS;
+            mbar_wait(&v_full[s], (uint32_t)((jv / NVS) & 1));
+            tc::fence_after();
+            const uint32_t va = smem_u32(vring + (size_t)s * C::HT_BYTES);
+            const uint32_t wa = smem_u32(wtiles + wb * C::WP_BYTES);
+#pragma unroll
+            for (int ks = 0; ks < 16; ++ks)
+              if (leader)
+                tc::mma_bf16(ucol, tc::smem_desc(va + ks * 2048, 1024, 1024, tc::SW_128), tc::smem_desc(wa + ks * 512, 256, 128, tc::SW_NONE), ID_UA,
+                             (uint32_t)((p | ks) != 0));
+            if (leader) {
+              tc::commit(&v_empty[s]);
+              tc::commit(&w_empty[wb]);
+            }
+            __syncwarp();
+            ++jv;
+            if (tn && p < 4) a.trace[340 + p * 12 + 10] = clock64();
+            continue;
           }
           for (int h = 0; h < 2 && 2 * p + h < TP; ++h) {
             const int s = jv % NVS;
@@ -1143,9 +1260,9 @@ static size_t umma_prep_bytes() {
   return (size_t)CL * 2 * (LX / 2) * 128 * 4 + (size_t)CL * (2 * (H / CL) + 2 * (D / CL)) * 4;
 }
 
-template <int D, int H, int CL, int NL, int KB, int NKS, int NVS, int NWB, int NUS, int DEFER = 0, int F = 0>
+template <int D, int H, int CL, int NL, int KB, int NKS, int NVS, int NWB, int NUS, int DEFER = 0, int F = 0, int BT = 0>
 static int launch_umma(const IterFwdArgs& a_in, cudaStream_t stream) {
-  using C = Cfg<D, H, CL, NL, KB, NKS, NVS, NWB, NUS, DEFER, F>;
+  using C = Cfg<D, H, CL, NL, KB, NKS, NVS, NWB, NUS, DEFER, F, BT>;
   IterFwdArgs a = a_in;
   if (C::XH) {
     if (a.saved != nullptr || a.xhat == nullptr || a.wk == nullptr || a.wv == nullptr) {
@@ -1169,7 +1286,7 @@ static int launch_umma(const IterFwdArgs& a_in, cudaStream_t stream) {
       OCRL_CHECK_CUDA(cudaGetLastError());
     }
   }
-  auto kern = sa_iter_fwd_umma_kernel<D, H, CL, NL, KB, NKS, NVS, NWB, NUS, DEFER, F>;
+  auto kern = sa_iter_fwd_umma_kernel<D, H, CL, NL, KB, NKS, NVS, NWB, NUS, DEFER, F, BT>;
   static_assert(C::SMEM_BYTES <= 227 * 1024, "shared memory budget");
   CUtensorMap tm_k, tm_v;
   const uint64_t rows = (uint64_t)a.B * a.N;
@@ -1233,14 +1350,20 @@ int sa_iter_fwd_umma_dispatch(const IterFwdArgs& a, cudaStream_t s) {
   }
   if (a.xhat != nullptr) {  // factored pass (inference)
     if (a.D == 192 && a.H == 192 && a.F == 64) {
-      // five images in flight per cluster, three update streams (768 threads).  Measured at B = 64, N = 4096, K = 6, T = 3
-      // (graph replays, us; lanes / streams): 3 / 2: 77.0, 5 / 3: 69.5, 5 / 4: 73.4
+      // five images in flight per cluster, three update streams (640 threads); from 2048 tokens up (every CTA of the
+      // cluster owns at least one full tile) 256-token steps.  Measured at B = 64, N = 4096, K = 6, T = 3 (graph replays,
+      // us; lanes / streams): 3 / 2: 77.0, 5 / 3: 69.5, 5 / 4: 73.4; 5 / 3 with 256-token steps: 63.1
+      const bool big = a.N >= 2048 && g_dev_variant != 5;
       if (a.K <= 6) {
         if (g_dev_variant == 2) return umma::launch_umma<192, 192, 8, 3, 6, 8, 8, 2, 2, 0, 64>(a, s);
-        if (g_dev_variant == 3) return umma::launch_umma<192, 192, 8, 5, 6, 8, 8, 2, 4, 0, 64>(a, s);
+        if (g_dev_variant == 4) return umma::launch_umma<192, 192, 8, 5, 6, 2, 2, 2, 4, 0, 64, 1>(a, s);
+        if (big) return umma::launch_umma<192, 192, 8, 5, 6, 3, 3, 2, 3, 0, 64, 1>(a, s);
         return umma::launch_umma<192, 192, 8, 5, 6, 8, 8, 2, 3, 0, 64>(a, s);
       }
-      if (a.K <= 8) return umma::launch_umma<192, 192, 8, 5, 8, 8, 8, 2, 3, 0, 64>(a, s);
+      if (a.K <= 8) {
+        if (big) return umma::launch_umma<192, 192, 8, 5, 8, 3, 3, 2, 3, 0, 64, 1>(a, s);
+        return umma::launch_umma<192, 192, 8, 5, 8, 8, 8, 2, 3, 0, 64>(a, s);
+      }
       if (a.K <= 12) return umma::launch_umma<192, 192, 8, 3, 12, 6, 6, 2, 2, 0, 64>(a, s);
       return umma::launch_umma<192, 192, 8, 3, 16, 6, 6, 2, 2, 0, 64>(a, s);
     }

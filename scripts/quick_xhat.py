@@ -47,7 +47,7 @@ k, v, _ = F.kv_project(x, p, kv="bf16")
 print("token stage  kv   %.1f us" % timeit(lambda: F.kv_project(x, p, kv="bf16")))
 print("token stage  xhat %.1f us" % timeit(lambda: F.kv_project(x, p, kv="bf16", xhat_only=True)))
 print("iteration    kv   %.1f us" % timeit(lambda: F.iterate(k, v, s0, p, 3, prepared=prep)))
-for dv in (2, 5, 4, 3, 0):  # development variants of the dispatcher (lanes, update streams): 2 = (3, 2), 5 = (4, 3), 4 = (5, 3), 3 = (4, 4), 0 = (5, 4)
+for dv in (0, 5, 2, 4):  # dispatcher variants: 0 = default (256-token steps), 5 = 64-token half tiles, 2 = 3 lanes / 2 streams, 4 = 256-token steps with 4 streams
     abi.lib().ocrl_dev_iter_variant(dv)
     for mc in (0,):
         o = abi.launch_opts(max_clusters=mc)
