@@ -269,7 +269,19 @@ def measure(a, mode, steps, warmup, dev, dist, rank, world, pool_host, pool_dev,
         with torch.no_grad():
             return model(batch_dev(i))
 
-    ms_eager, events = timed(step_eager, steps, warmup, kernel_timers=want_events)
+    ms_eager, events = timed(step_eager, steps, warmup, kernel_timers=False)
+    if want_events:
+        # Per-kernel CUDA events of the same eager steps.  The kernels of the step are now shorter than the host time of
+        # the Python call that launches them, so events recorded in a free-running eager loop bracket host gaps as well;
+        # here the stream is held back (a spin kernel of ~20 ms) while the host enqueues every step, and the events then
+        # bracket kernels that run back to back in step order (inputs produced by the preceding kernel of the step).
+        barrier()
+        F.KERNEL_EVENTS = []
+        torch.cuda._sleep(int(4e7))
+        for i in range(steps):
+            step_eager(warmup + i)
+        barrier()
+        events, F.KERNEL_EVENTS = F.KERNEL_EVENTS, None
     # kernels of libocrl_sa.so per step: the library counts its own launches (ocrl_launch_count); one warm eager step
     # launches what one graph replay holds as kernel nodes (the graphs are captured from the same call)
     from ocrl_b200 import abi
