@@ -219,7 +219,9 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
     }
   };
   const uint32_t* optab = reinterpret_cast<const uint32_t*>(sm + C::OFF_OPTAB);
-  const bool use_tab = (C::OPT_MAX > 0) && total_ops <= C::OPT_MAX && T < 256;
+  // (the launcher splits a batch whose clusters would hold more ops than the table: with the table the segment arrays
+  // above are dead after the setup -- in a kernel that runs 640 threads at the 96-register limit that is what matters)
+  constexpr bool use_tab = C::OPT_MAX > 0;
   if (use_tab) {
     uint32_t* tab = reinterpret_cast<uint32_t*>(sm + C::OFF_OPTAB);
     for (int n = threadIdx.x; n < total_ops; n += C::NT) {
@@ -1330,6 +1332,28 @@ static int launch_umma(const IterFwdArgs& a_in, cudaStream_t stream) {
   {  // fewest clusters that keep the same number of image rounds (frees SMs for concurrent work)
     const int per = (a.B + ncl - 1) / ncl;
     ncl = (a.B + per - 1) / per;
+  }
+  if (C::OPT_MAX > 0) {  // the kernel's op table holds OPT_MAX ops per cluster: larger batches go in several launches
+    if (a.T >= 256) {
+      set_error("sa_iter_fwd(tcgen05, factored): T = %d (< 256)", a.T);
+      return OCRL_E_SHAPE;
+    }
+    const int per = (a.B + ncl - 1) / ncl;
+    if (per * a.T > C::OPT_MAX) {
+      const int chunk = ncl * (C::OPT_MAX / a.T);
+      for (int b0 = 0; b0 < a_in.B; b0 += chunk) {
+        IterFwdArgs c = a_in;
+        c.B = min(chunk, a_in.B - b0);
+        c.xhat = reinterpret_cast<const unsigned char*>(a_in.xhat) + (size_t)b0 * a_in.N * C::FW * 2;
+        c.slots0 = a_in.slots0 + (size_t)b0 * a_in.K * D;
+        c.slots_out = a_in.slots_out + (size_t)b0 * a_in.K * D;
+        if (a_in.attn_out != nullptr) c.attn_out = a_in.attn_out + (size_t)b0 * a_in.N * a_in.K;
+        c.prepared = 1;  // the weights were prepared above (or by the caller)
+        const int rc = launch_umma<D, H, CL, NL, KB, NKS, NVS, NWB, NUS, DEFER, F, BT>(c, stream);
+        if (rc != OCRL_OK) return rc;
+      }
+      return OCRL_OK;
+    }
   }
   cfg.gridDim = dim3((unsigned)(ncl * CL));
   OCRL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, a, tm_k, tm_v));
