@@ -1379,7 +1379,7 @@ int sa_iter_fwd_umma_dispatch(const IterFwdArgs& a, cudaStream_t s) {
       // us; lanes / streams): 3 / 2: 77.0, 5 / 3: 69.5, 5 / 4: 73.4; 5 / 3 with 256-token steps: 63.1
       const bool big = a.N >= 2048 && g_dev_variant != 5;
       if (a.K <= 6) {
-        if (g_dev_variant == 2) return umma::launch_umma<192, 192, 8, 3, 6, 8, 8, 2, 2, 0, 64>(a, s);
+        if (g_dev_variant == 2) return umma::launch_umma<192, 192, 8, 5, 6, 3, 3, 2, 2, 0, 64, 1>(a, s);
         if (g_dev_variant == 4) return umma::launch_umma<192, 192, 8, 5, 6, 2, 2, 2, 4, 0, 64, 1>(a, s);
         if (big) return umma::launch_umma<192, 192, 8, 5, 6, 3, 3, 2, 3, 0, 64, 1>(a, s);
         return umma::launch_umma<192, 192, 8, 5, 6, 8, 8, 2, 3, 0, 64>(a, s);
