@@ -20,6 +20,7 @@ BUILD = os.path.join(CSRC, "build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+FLAGS += os.environ.get("OCRL_NVCC_FLAGS", "").split()  # development builds, e.g. -DOCRL_UMMA_TRACE=1 (part of the digest)
 
 
 def _sources():

@@ -27,6 +27,12 @@ using namespace pc;
 #ifndef TRACE_OP
 #define TRACE_OP 2
 #endif
+// The clock64 phase stamps (ocrl_sa_launch_opts.trace, scripts/trace_umma.py) are compiled in only on request
+//   OCRL_NVCC_FLAGS=-DOCRL_UMMA_TRACE=1 python -m ocrl_b200.build
+// -- the factored kernel runs 640 threads at the 96-register limit and pays for every live value.
+#ifndef OCRL_UMMA_TRACE
+#define OCRL_UMMA_TRACE 0
+#endif
 
 template <int D_, int H_, int CL_, int NL_, int KB_, int NKS_, int NVS_, int NWB_, int NUS_, int DEFER_ = 0, int F_ = 0, int BT_ = 0>
 struct Cfg {
@@ -128,10 +134,10 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
   const int cid = blockIdx.x / CL, ncl = gridDim.x / CL;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K = a.K, N = a.N, T = a.T, B = a.B;
-  const bool tracer = (a.trace != nullptr && blockIdx.x == 0);
+  const bool tracer = OCRL_UMMA_TRACE && (a.trace != nullptr && blockIdx.x == 0);
 #define PP_TRACE(i) do { if (tracer) a.trace[(i)] = clock64(); } while (0)
   // kernel start / end of setup / kernel end of the first and the last cluster's CTA 0: trace[1..3], trace[4..6]
-  const bool tracer2 = (a.trace != nullptr && blockIdx.x == gridDim.x - CL && tid == 0);
+  const bool tracer2 = OCRL_UMMA_TRACE && (a.trace != nullptr && blockIdx.x == gridDim.x - CL && tid == 0);
   if (tracer && tid == 0) a.trace[1] = clock64();
   if (tracer2) a.trace[4] = clock64();
 
@@ -1097,7 +1103,7 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
           const float nn = tanhf(gin + r * ghn);
           hp = (1.f - z) * nn + z * own[i];
           own[i] = hp;
-          if (a.saved != nullptr) {
+          if (!XH && a.saved != nullptr) {
             float* sv = saved_at(img, t);
             const int f = slot * D + rank * DS + dl;
             sv[SL.off_r() + f] = r;
@@ -1127,7 +1133,7 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
           const int slot = i / HS, hl = i % HS;
           const float acc = P_GI[(3 * DS + hl) * KS + slot];
           const float pre = s_rstd[slot] * (acc - s_mean[slot] * s_c1[hl]) + s_b1f[hl];
-          if (a.saved != nullptr) saved_at(img, t)[SL.off_pre() + slot * H + rank * HS + hl] = pre;
+          if (!XH && a.saved != nullptr) saved_at(img, t)[SL.off_pre() + slot * H + rank * HS + hl] = pre;
           hid = fmaxf(pre, 0.f);
         }
         quad_push(round, hid, i, HS, act(round));

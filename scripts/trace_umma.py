@@ -1,4 +1,5 @@
-"""Timeline of the tcgen05 iteration kernel (clock64 of CTA 0).   python scripts/trace_umma.py [B] [lanes] [xhat]"""
+"""Timeline of the tcgen05 iteration kernel (clock64 of CTA 0).   python scripts/trace_umma.py [B] [lanes] [xhat]
+(needs a build with the stamps compiled in:  OCRL_NVCC_FLAGS=-DOCRL_UMMA_TRACE=1 python -m ocrl_b200.build)"""
 import os
 import sys
 
