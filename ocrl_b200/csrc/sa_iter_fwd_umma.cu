@@ -115,6 +115,11 @@ struct Cfg {
   static constexpr int SMEM_BYTES = OFF_OPTAB + 4 * OPT_MAX;
 };
 
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 // barrier of one update stream (ids 1, 2)
 __device__ __forceinline__ void upd_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
@@ -863,25 +868,37 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
     };
     // mean / rstd of the K rows (bf16, length D, operand layout) that just arrived: one warp per row
     auto row_stats = [&](const unsigned char* opnd) {
+      // The round sits on the critical path of every update twice (traced: 1.7-2.3 k cycles as two rounds of two serial
+      // butterfly reductions each).  One pass (sum and sum of squares), two rows per warp and round: four independent
+      // shuffle chains in flight, K <= 8 rows in a single round.
       constexpr int NCD = D / 64;  // (rows of slot features; NCH counts the chunks of the streamed tiles)
-      for (int row = uwarp; row < K; row += UW) {
-        float2 x[NCD];
-        float s = 0.f;
+      for (int row0 = uwarp; row0 < K; row0 += 2 * UW) {
+        const int row1 = row0 + UW;
+        const bool two = row1 < K;
+        float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
 #pragma unroll
         for (int c = 0; c < NCD; ++c) {
-          const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(opnd + opnd_off(row, 64 * c + 2 * lane));
-          x[c] = make_float2(__low2float(v), __high2float(v));
-          s += x[c].x + x[c].y;
+          const __nv_bfloat162 v0 = *reinterpret_cast<const __nv_bfloat162*>(opnd + opnd_off(row0, 64 * c + 2 * lane));
+          const __nv_bfloat162 v1 = *reinterpret_cast<const __nv_bfloat162*>(opnd + opnd_off(two ? row1 : row0, 64 * c + 2 * lane));
+          const float x0 = __low2float(v0), y0 = __high2float(v0), x1 = __low2float(v1), y1 = __high2float(v1);
+          s0 += x0 + y0;
+          q0 = fmaf(x0, x0, fmaf(y0, y0, q0));
+          s1 += x1 + y1;
+          q1 = fmaf(x1, x1, fmaf(y1, y1, q1));
         }
-        const float mean = warp_sum(s) * (1.f / D);
-        float q = 0.f;
 #pragma unroll
-        for (int c = 0; c < NCD; ++c) {
-          const float dx = x[c].x - mean, dy = x[c].y - mean;
-          q = fmaf(dx, dx, fmaf(dy, dy, q));
+        for (int off = 16; off > 0; off >>= 1) {
+          const float a0 = __shfl_xor_sync(FULL, s0, off), b0 = __shfl_xor_sync(FULL, q0, off);
+          const float a1 = __shfl_xor_sync(FULL, s1, off), b1 = __shfl_xor_sync(FULL, q1, off);
+          s0 += a0; q0 += b0; s1 += a1; q1 += b1;
         }
-        const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + a.ln_eps);
-        if (lane == 0) { s_mean[row] = mean; s_rstd[row] = rstd; }
+        const float m0 = s0 * (1.f / D), m1 = s1 * (1.f / D);
+        const float r0 = rsqrtf(fmaxf(q0 * (1.f / D) - m0 * m0, 0.f) + a.ln_eps);
+        const float r1 = rsqrtf(fmaxf(q1 * (1.f / D) - m1 * m1, 0.f) + a.ln_eps);
+        if (lane == 0) {
+          s_mean[row0] = m0; s_rstd[row0] = r0;
+          if (two) { s_mean[row1] = m1; s_rstd[row1] = r1; }
+        }
       }
     };
     // Products: D[128 weight rows x 16] = W block (tensor memory, `wcol`) x operand (K-major [k/8][8 slots][8] bf16,
@@ -1089,6 +1106,34 @@ sa_iter_fwd_umma_kernel(const IterFwdArgs a, const __grid_constant__ CUtensorMap
       upd_sync();
       PP_T(4);
       // ============================================================ R3: all-gather h'
+      // Factored form: the K * DS elements of the slice are one and a bit rounds of the stream's threads (144 on 128);
+      // two elements per thread as ONE straight-line block (clamped indices, results masked afterwards) let the second
+      // round overlap the first instead of following it (traced: 2.2 k cycles for the two serial rounds), and the gates
+      // take the single-instruction tanh (tanh.approx.f32: 2^-11 relative, below the bf16 rounding of their operands).
+      if (XH) {
+        const int NE = K * DS;
+        auto gate = [&](int i) {
+          const int slot = i / DS, dl = i - slot * DS;
+          const float gir = P_GI[(dl) * KS + slot] + s_bih[dl], ghr = P_GH[(dl) * KS + slot] + s_bhh[dl];
+          const float giz = P_GI[(DS + dl) * KS + slot] + s_bih[DS + dl];
+          const float ghz = P_GH[(DS + dl) * KS + slot] + s_bhh[DS + dl];
+          const float gin = P_GI[(2 * DS + dl) * KS + slot] + s_bih[2 * DS + dl];
+          const float ghn = P_GH[(2 * DS + dl) * KS + slot] + s_bhh[2 * DS + dl];
+          const float r = fmaf(0.5f, tanh_approx(0.5f * (gir + ghr)), 0.5f), z = fmaf(0.5f, tanh_approx(0.5f * (giz + ghz)), 0.5f);
+          const float nn = tanh_approx(fmaf(r, ghn, gin));
+          return fmaf(z, own[i] - nn, nn);  // (1 - z) n + z h
+        };
+        for (int i0 = uwarp * 32; i0 < NE; i0 += 2 * UT) {
+          const int iA = i0 + lane, iB = iA + UT;
+          const bool second = (i0 + UT) < NE;  // warp-uniform
+          const float hA = gate(min(iA, NE - 1));
+          const float hB = gate(min(iB, NE - 1));
+          if (iA < NE) own[iA] = hA;
+          if (iB < NE) own[iB] = hB;
+          quad_push(round, iA < NE ? hA : 0.f, iA, DS, act(round));
+          if (second) quad_push(round, iB < NE ? hB : 0.f, iB, DS, act(round));
+        }
+      } else
       for (int i0 = uwarp * 32; i0 < K * DS; i0 += UT) {
         const int i = i0 + lane;
         float hp = 0.f;
