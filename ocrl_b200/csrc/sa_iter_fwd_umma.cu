@@ -1439,8 +1439,12 @@ int sa_iter_fwd_umma_dispatch(const IterFwdArgs& a, cudaStream_t s) {
         if (big) return umma::launch_umma<192, 192, 8, 5, 8, 3, 3, 2, 3, 0, 64, 1>(a, s);
         return umma::launch_umma<192, 192, 8, 5, 8, 8, 8, 2, 3, 0, 64>(a, s);
       }
-      if (a.K <= 12) return umma::launch_umma<192, 192, 8, 3, 12, 6, 6, 2, 2, 0, 64>(a, s);
-      return umma::launch_umma<192, 192, 8, 3, 16, 6, 6, 2, 2, 0, 64>(a, s);
+      if (g_dev_variant == 6 || !big) {
+        if (a.K <= 12) return umma::launch_umma<192, 192, 8, 3, 12, 6, 6, 2, 2, 0, 64>(a, s);
+        return umma::launch_umma<192, 192, 8, 3, 16, 6, 6, 2, 2, 0, 64>(a, s);
+      }
+      if (a.K <= 12) return umma::launch_umma<192, 192, 8, 3, 12, 2, 2, 2, 2, 0, 64, 1>(a, s);
+      return umma::launch_umma<192, 192, 8, 3, 16, 2, 2, 2, 2, 0, 64, 1>(a, s);
     }
     set_error("sa_iter_fwd(tcgen05, factored): D=%d H=%d C_in=%d not instantiated", a.D, a.H, a.F);
     return OCRL_E_SHAPE;

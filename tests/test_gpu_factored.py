@@ -99,7 +99,9 @@ def test_factored_loop_on_exact_bf16_inputs():
 
 
 @pytest.mark.parametrize("K,T,B,N", [(1, 1, 1, 64), (3, 2, 7, 320), (6, 3, 40, 256), (8, 5, 2, 1000), (9, 3, 3, 512),
-                                     (16, 2, 2, 300), (6, 7, 80, 128)])
+                                     (16, 2, 2, 300), (6, 7, 80, 128),
+                                     # from 2048 tokens up the pass runs 256-token steps (ragged last tile, 8 and 16 slot columns)
+                                     (6, 3, 3, 2048), (8, 2, 2, 2500), (11, 5, 2, 4096), (16, 3, 3, 2304)])
 def test_factored_loop_shapes(K, T, B, N):
     """Slot counts 1..16, ragged token counts, more images than lanes x clusters, T up to 7."""
     from ocrl_b200 import functional as F
